@@ -1,0 +1,141 @@
+"""Scene builders: the MJCF assembly the reference tasks perform, done once on the host.
+
+* reorient: reference manipulation/tasks/reorient.py:324-364 (`reorient_task`) +
+  ReOrient.__init__ :113-168 — Standard arena, Shadow hand attached at its
+  palm-upright pose, free OpenAI cube (half-size 0.02), contact-less hint cube.
+* reach (Shadow): reference manipulation/tasks/reach.py:91-139 with the Shadow hand
+  as BASELINE.json configs[0..1] state; ground collisions disabled (:131-132).
+* hand_only: the model `IKSolver` builds its private physics from
+  (reference inverse_kinematics/ik_solver.py:46).
+
+The vendored MJCF/STL model data is read from the reference checkout
+(`DEXTERITY_REFERENCE_ROOT`, default /root/reference) at *compile* time only; the
+compiled blobs are committed under dexterity_b200/assets/ (tools/build_assets.py)
+so nothing at run time needs the reference tree.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+
+from dexterity_b200.model import compile as compile_lib
+from dexterity_b200.model import mjcf
+
+ASSET_DIR = os.path.join(os.path.dirname(__file__), "..", "assets")
+
+# reference models/hands/shadow_hand_e.py:13-14
+SHADOW_PALM_UPRIGHT_POS = (0.0, 0.2, 0.1)
+SHADOW_PALM_UPRIGHT_QUAT = (0.0, 0.0, 0.707106781186, -0.707106781186)
+SHADOW_FINGERTIPS = ("fftip", "mftip", "rftip", "lftip", "thtip")
+
+# reference manipulation/tasks/reorient.py:41-78
+REORIENT_PROP_SIZE = 0.02
+REORIENT_HINT_POS = (0.12, 0.0, 0.15)
+REORIENT_PHYSICS_TIMESTEP = 0.005
+REORIENT_CONTROL_TIMESTEP = 0.025
+# reference manipulation/tasks/reach.py:54,59
+REACH_PHYSICS_TIMESTEP = 0.02
+REACH_CONTROL_TIMESTEP = 0.02
+
+
+def reference_root() -> str:
+    return os.environ.get("DEXTERITY_REFERENCE_ROOT", "/root/reference")
+
+
+def _paths():
+    root = os.path.join(reference_root(), "dexterity", "models")
+    return dict(
+        arena=os.path.join(root, "arenas", "arena.xml"),
+        shadow=os.path.join(root, "vendor", "shadow_robot", "shadow_hand_description", "mjcf",
+                            "shadow_hand_series_e.xml"),
+        adroit=os.path.join(root, "vendor", "adroit", "adroit_hand_description", "mjcf", "adroit_hand.xml"),
+    )
+
+
+def _standard_arena(ground_collides: bool = True) -> mjcf.Scene:
+    """reference models/arenas/arena.py:15-20 + standard.py:13-22."""
+    arena = mjcf.load(_paths()["arena"], name="arena")
+    ground = mjcf.Geom(
+        name="ground", type="plane", pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]),
+        size=np.array([1.0, 1.0, 0.1]),
+        contype=1 if ground_collides else 0, conaffinity=1 if ground_collides else 0,
+        condim=3, priority=0, friction=np.array([0.4, 0.005, 0.0001]),
+        solref=np.array([0.002, 1.0]), solimp=np.array([0.95, 0.99, 0.001, 0.5, 2.0]),
+        solmix=1.0, margin=0.0, gap=0.0, density=1000.0, mass=None, mesh=None,
+    )
+    arena.world.geoms.append(ground)
+    return mjcf.Scene(arena)
+
+
+def _shadow_hand(scene: mjcf.Scene, name: str = "shadow_hand_e") -> mjcf.Model:
+    hand = mjcf.load(_paths()["shadow"], name=name, base_defaults=scene.root_defaults)
+    # fingertip sites, reference models/hands/shadow_hand_e.py:151-169
+    for tip in SHADOW_FINGERTIPS:
+        hand.find_body(tip).sites.append(
+            mjcf.Site(name=tip + "_site", pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0])))
+    return hand
+
+
+def reorient_scene() -> compile_lib.CompiledModel:
+    scene = _standard_arena()
+    hand = _shadow_hand(scene)
+    scene.attach(hand, pos=SHADOW_PALM_UPRIGHT_POS, quat=SHADOW_PALM_UPRIGHT_QUAT)
+    prop = mjcf.primitive_model("prop", "box", [REORIENT_PROP_SIZE] * 3, scene.root_defaults)
+    scene.attach(prop, free=True)
+    # _hintify (reorient.py:294-321): contype = conaffinity = 0, fixed to the world
+    hint = mjcf.primitive_model("target_prop", "box", [REORIENT_PROP_SIZE] * 3, scene.root_defaults,
+                                contype=0, conaffinity=0)
+    scene.attach(hint, pos=REORIENT_HINT_POS)
+    return compile_lib.compile_model(
+        scene.model, timestep=REORIENT_PHYSICS_TIMESTEP, nconmax=48,
+        xfrc_gravcomp_prefix="shadow_hand_e/")
+
+
+def reach_shadow_scene() -> compile_lib.CompiledModel:
+    scene = _standard_arena(ground_collides=False)
+    hand = _shadow_hand(scene)
+    scene.attach(hand, pos=SHADOW_PALM_UPRIGHT_POS, quat=SHADOW_PALM_UPRIGHT_QUAT)
+    return compile_lib.compile_model(
+        scene.model, timestep=REACH_PHYSICS_TIMESTEP, nconmax=48,
+        xfrc_gravcomp_prefix="shadow_hand_e/")
+
+
+def shadow_hand_only() -> compile_lib.CompiledModel:
+    """The hand's own root model (no arena, no attachment offset): IKSolver's physics."""
+    scene = mjcf.Scene(mjcf.Model("ik", mjcf.Body("world", np.zeros(3), np.array([1.0, 0, 0, 0]), None),
+                                  {}, [], [], [], [], {}, {}))
+    hand = mjcf.load(_paths()["shadow"], name="shadow_hand_e")
+    for tip in SHADOW_FINGERTIPS:
+        hand.find_body(tip).sites.append(
+            mjcf.Site(name=tip + "_site", pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0])))
+    # the IK physics is the un-attached model: bodies live directly in the world
+    scene.model.world.children = hand.world.children
+    scene.model.meshes = hand.meshes
+    scene.model.tendons, scene.model.actuators = hand.tendons, hand.actuators
+    scene.model.excludes = hand.excludes
+    scene.model.option = hand.option
+    return compile_lib.compile_model(scene.model, timestep=0.002, nconmax=48)
+
+
+_BUILDERS = {
+    "reorient_shadow": reorient_scene,
+    "reach_shadow": reach_shadow_scene,
+    "shadow_hand_only": shadow_hand_only,
+}
+
+
+def load_compiled(name: str, rebuild: bool = False) -> compile_lib.CompiledModel:
+    """Loads the committed compiled blob; recompiles from the reference MJCF when asked
+    (or when the asset is missing and the reference checkout is present)."""
+    path = os.path.join(ASSET_DIR, name + ".npz")
+    if not rebuild and os.path.exists(path):
+        return compile_lib.CompiledModel.load(path)
+    if not os.path.isdir(reference_root()):
+        raise FileNotFoundError(
+            f"compiled model {path} missing and reference MJCF not found at {reference_root()}")
+    model = _BUILDERS[name]()
+    os.makedirs(ASSET_DIR, exist_ok=True)
+    model.save(path)
+    return model
