@@ -1,0 +1,701 @@
+// dex_dynamics.cuh — K2: warp-per-env smooth dynamics, constraint assembly, Newton solve and
+// semi-implicit Euler (restates SURVEY.md §8a rows 11-13 and 15-20):
+//   mj_comPos (cinert/cdof about a per-tree reference point), mj_crb (dense M in smem),
+//   mj_comVel, mj_rne (bias; constant xfrc_applied folded in as external body forces),
+//   mj_passive (joint damping), mj_fwdActuation (affine actuators over joints / fixed tendons),
+//   mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint (dof friction loss, joint
+//   limits, pyramidal contacts), mj_solNewton (exact Hessian M + J^T D J, warp Cholesky, exact
+//   line search), mj_Euler with implicit joint damping.
+//
+// Lane mapping: lane = dof for every per-dof vector (kept in registers), lane = body for the
+// tree passes (level by level), lane = contact for per-contact scalars.  The contact-frame
+// Jacobian Jc[c][3][nv] lives in the warp's shared-memory slice; rows of friction loss and
+// joint limits are +-unit vectors and are never materialised.
+#ifndef DEX_DYNAMICS_CUH_
+#define DEX_DYNAMICS_CUH_
+
+#include "dex_kin.cuh"
+
+#define DEX_MSTRIDE 33
+#define DEX_JSTRIDE 33
+// shared memory per warp (units of T)
+#define DEX_K2_OFF_XPOS 0
+#define DEX_K2_OFF_XQUAT (DEX_K2_OFF_XPOS + DEX_MAXBODY * 3)
+#define DEX_K2_OFF_XMAT (DEX_K2_OFF_XQUAT + DEX_MAXBODY * 4)
+#define DEX_K2_OFF_XANCHOR (DEX_K2_OFF_XMAT + DEX_MAXBODY * 9)
+#define DEX_K2_OFF_XAXIS (DEX_K2_OFF_XANCHOR + DEX_MAXJNT * 3)
+#define DEX_K2_OFF_REF (DEX_K2_OFF_XAXIS + DEX_MAXJNT * 3)
+#define DEX_K2_OFF_CDOF (DEX_K2_OFF_REF + 16)
+#define DEX_K2_OFF_QPOS (DEX_K2_OFF_CDOF + DEX_MAXDOF * 6)
+#define DEX_K2_OFF_QVEL (DEX_K2_OFF_QPOS + 48)
+#define DEX_K2_OFF_VECA (DEX_K2_OFF_QVEL + 32)
+#define DEX_K2_OFF_VECB (DEX_K2_OFF_VECA + 32)
+#define DEX_K2_OFF_DINV (DEX_K2_OFF_VECB + 32)
+#define DEX_K2_OFF_M (DEX_K2_OFF_DINV + 32)
+#define DEX_K2_OFF_H (DEX_K2_OFF_M + 32 * DEX_MSTRIDE)
+#define DEX_K2_OFF_UNION (DEX_K2_OFF_H + 32 * DEX_MSTRIDE)
+//   union A (tree passes)
+#define DEX_K2_OFF_CINERT DEX_K2_OFF_UNION
+#define DEX_K2_OFF_CRB (DEX_K2_OFF_CINERT + DEX_MAXBODY * 10)
+#define DEX_K2_OFF_CVEL (DEX_K2_OFF_CRB + DEX_MAXBODY * 10)
+#define DEX_K2_OFF_CDOFDOT (DEX_K2_OFF_CVEL + DEX_MAXBODY * 6)
+#define DEX_K2_OFF_CACC (DEX_K2_OFF_CDOFDOT + DEX_MAXDOF * 6)
+#define DEX_K2_OFF_CFRC (DEX_K2_OFF_CACC + DEX_MAXBODY * 6)
+#define DEX_K2_UNION_A (DEX_MAXBODY * 38 + DEX_MAXDOF * 6)
+//   union B (constraints)
+#define DEX_K2_OFF_JC DEX_K2_OFF_UNION
+#define DEX_K2_OFF_CDAT (DEX_K2_OFF_JC + DEX_MAXCON * 3 * DEX_JSTRIDE)
+#define DEX_CDAT_STRIDE 24
+#define DEX_K2_OFF_CDOT (DEX_K2_OFF_CDAT + DEX_MAXCON * DEX_CDAT_STRIDE)
+#define DEX_K2_UNION_B (DEX_MAXCON * 3 * DEX_JSTRIDE + DEX_MAXCON * DEX_CDAT_STRIDE + 96)
+#define DEX_K2_SMEM_T (DEX_K2_OFF_UNION + (DEX_K2_UNION_A > DEX_K2_UNION_B ? DEX_K2_UNION_A : DEX_K2_UNION_B))
+
+// cdat layout per contact
+enum { CD_MU = 0, CD_D = 1, CD_AREF = 2 /*4*/, CD_JAR = 6 /*4*/, CD_JV = 10 /*4*/, CD_F = 14 /*3 frame-space force*/,
+       CD_W = 17 /*5: W00 W01 W02 W11 W22*/, CD_MASK = 22 /*dof mask as int bits*/ };
+
+// optional per-env debug outputs (null = off); used by the parity tests
+template <typename T>
+struct DynDebug {
+  T* M;            // [nenv][nv*nv]
+  T* qfrc_smooth;  // [nenv][nv]
+  T* qacc;         // [nenv][nv]  solver output
+  T* qfrc_constraint;  // [nenv][nv]
+  T* efc;          // [nenv][DEX_MAXCON][8]: D, aref[4], mu, imp, R
+};
+
+template <typename T>
+DEX_DEV void dex_impedance(const T* solimp, T pos, T margin, T* imp) {  // getimpedance
+  T dmin = dx_clamp(solimp[0], T(0.0001), T(0.9999));
+  T dmax = dx_clamp(solimp[1], T(0.0001), T(0.9999));
+  T width = dx_max(solimp[2], Real<T>::minval());
+  T mid = dx_clamp(solimp[3], T(0.0001), T(0.9999));
+  T power = dx_max(solimp[4], T(1));
+  T x = dx_abs((pos - margin) / width);
+  if (x >= 1) { *imp = dmax; return; }
+  if (x <= 0) { *imp = dmin; return; }
+  T y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = pow(x / mid, power) * mid;
+  else y = 1 - pow((1 - x) / (1 - mid), power) * (1 - mid);
+  *imp = dmin + y * (dmax - dmin);
+}
+template <typename T>
+DEX_DEV void dex_kb(const T* solref, const T* solimp, T timestep, T* K, T* B) {
+  T dmax = dx_clamp(solimp[1], T(0.0001), T(0.9999));
+  T tc = solref[0], dr = solref[1];
+  if (tc > 0) {
+    tc = dx_max(tc, 2 * timestep);  // refsafe
+    *K = 1 / dx_max(Real<T>::minval(), dmax * dmax * tc * tc * dr * dr);
+    *B = 2 / dx_max(Real<T>::minval(), dmax * tc);
+  } else {
+    *K = -tc / dx_max(Real<T>::minval(), dmax * dmax);
+    *B = -dr / dx_max(Real<T>::minval(), dmax);
+  }
+}
+
+// In-place lower Cholesky of the nv x nv matrix A (smem, stride DEX_MSTRIDE), lane = row.
+// dinv[k] = 1 / L[k][k].  Returns false (warp-uniform) if a pivot is not positive.
+template <typename T>
+DEX_DEV bool dex_cholesky(T* A, T* dinv, int nv) {
+  const int i = dex_lane();
+  bool ok = true;
+  for (int k = 0; k < nv; ++k) {
+    T s = (i >= k && i < nv) ? A[i * DEX_MSTRIDE + k] : T(0);
+    const T* rowi = A + (i < nv ? i : 0) * DEX_MSTRIDE;
+    const T* rowk = A + k * DEX_MSTRIDE;
+    for (int j = 0; j < k; ++j) s -= rowi[j] * rowk[j];
+    T dkk = dex_shfl(s, k);
+    if (!(dkk > Real<T>::minval())) { ok = false; dkk = Real<T>::minval(); }
+    T inv = T(1) / dx_sqrt(dkk);
+    if (i >= k && i < nv) A[i * DEX_MSTRIDE + k] = s * inv;
+    if (i == k) dinv[k] = inv;
+    dex_syncwarp();
+  }
+  return ok;
+}
+// Solves L L^T x = b; lane i holds b_i on entry and x_i on return.
+template <typename T>
+DEX_DEV T dex_chol_solve(const T* L, const T* dinv, int nv, T b) {
+  const int i = dex_lane();
+  for (int k = 0; k < nv; ++k) {
+    T yk = dex_shfl(b, k) * dinv[k];
+    if (i == k) b = yk;
+    else if (i > k && i < nv) b -= L[i * DEX_MSTRIDE + k] * yk;
+  }
+  for (int k = nv - 1; k >= 0; --k) {
+    T xk = dex_shfl(b, k) * dinv[k];
+    if (i == k) b = xk;
+    else if (i < k) b -= L[k * DEX_MSTRIDE + i] * xk;
+  }
+  return b;
+}
+// y_i = sum_j M[i][j] x_j with x in smem (nv entries), lane = row
+template <typename T>
+DEX_DEV T dex_matvec(const T* M, const T* x, int nv) {
+  const int i = dex_lane();
+  const T* row = M + (i < nv ? i : 0) * DEX_MSTRIDE;
+  T s = 0;
+  for (int j = 0; j < nv; ++j) s += row[j] * x[j];
+  return i < nv ? s : T(0);
+}
+// out[t] = Jc[t] . x  for the 3*ncon contact-frame Jacobian rows (one row per lane per round)
+template <typename T>
+DEX_DEV void dex_contact_dots(const T* Jc, const T* x, int nrows, int nv, T* out) {
+  for (int t = dex_lane(); t < nrows; t += 32) {
+    const T* row = Jc + t * DEX_JSTRIDE;
+    T s = 0;
+    for (int j = 0; j < nv; ++j) s += row[j] * x[j];
+    out[t] = s;
+  }
+  dex_syncwarp();
+}
+
+template <typename T>
+DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int env,
+                              T* smem, int integrate) {
+  const int lane = dex_lane();
+  const int nv = m.nv, nb = m.nbody;
+  T* xpos = smem + DEX_K2_OFF_XPOS;
+  T* xquat = smem + DEX_K2_OFF_XQUAT;
+  T* xmat = smem + DEX_K2_OFF_XMAT;
+  T* xanchor = smem + DEX_K2_OFF_XANCHOR;
+  T* xaxis = smem + DEX_K2_OFF_XAXIS;
+  T* ref = smem + DEX_K2_OFF_REF;
+  T* cdof = smem + DEX_K2_OFF_CDOF;
+  T* qpos = smem + DEX_K2_OFF_QPOS;
+  T* qvel = smem + DEX_K2_OFF_QVEL;
+  T* vecA = smem + DEX_K2_OFF_VECA;
+  T* vecB = smem + DEX_K2_OFF_VECB;
+  T* dinv = smem + DEX_K2_OFF_DINV;
+  T* M = smem + DEX_K2_OFF_M;
+  T* H = smem + DEX_K2_OFF_H;
+  T* cinert = smem + DEX_K2_OFF_CINERT;
+  T* crb = smem + DEX_K2_OFF_CRB;
+  T* cvel = smem + DEX_K2_OFF_CVEL;
+  T* cdofdot = smem + DEX_K2_OFF_CDOFDOT;
+  T* cacc = smem + DEX_K2_OFF_CACC;
+  T* cfrc = smem + DEX_K2_OFF_CFRC;
+  T* Jc = smem + DEX_K2_OFF_JC;
+  T* cdat = smem + DEX_K2_OFF_CDAT;
+  T* cdot = smem + DEX_K2_OFF_CDOT;
+  const T h = m.timestep;
+  unsigned status = 0;
+
+  // ------------------------------------------------------------------ load state
+  for (int i = lane; i < m.nq; i += 32) qpos[i] = st.qpos[(size_t)env * st.qpos_stride + i];
+  const bool isdof = lane < nv;
+  const T qv = isdof ? st.qvel[(size_t)env * st.qvel_stride + lane] : T(0);
+  T qacc = isdof ? st.warm[(size_t)env * st.warm_stride + lane] : T(0);
+  qvel[lane] = qv;
+  dex_syncwarp();
+
+  // ------------------------------------------------------------------ kinematics
+  KinBuf<T> kb = {xpos, xquat, xmat, xanchor, xaxis};
+  dex_fk(m, qpos, kb);
+  if (lane < m.ntree) {
+    const int rb = dex_ldg(m.tree_refbody + lane);
+    ref[3 * lane] = xpos[3 * rb]; ref[3 * lane + 1] = xpos[3 * rb + 1]; ref[3 * lane + 2] = xpos[3 * rb + 2];
+  }
+  dex_syncwarp();
+
+  // ------------------------------------------------------------------ cdof (lane = dof), cinert (lane = body)
+  T cd[6] = {0, 0, 0, 0, 0, 0};
+  int dbody = 0, dpar = -1;
+  if (isdof) {
+    const int j = dex_ldg(m.dof_jnt + lane);
+    dbody = dex_ldg(m.dof_body + lane);
+    dpar = dex_ldg(m.dof_parent + lane);
+    const T* rp = ref + 3 * dex_ldg(m.dof_tree + lane);
+    if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+      const int k = lane - dex_ldg(m.jnt_dofadr + j);
+      if (k < 3) cd[3 + k] = 1;
+      else {
+        const T* R = xmat + 9 * dbody;
+        T ax[3] = {R[k - 3], R[3 + k - 3], R[6 + k - 3]};
+        T off[3] = {rp[0] - xpos[3 * dbody], rp[1] - xpos[3 * dbody + 1], rp[2] - xpos[3 * dbody + 2]};
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+        cross3(cd + 3, ax, off);
+      }
+    } else {
+      T ax[3] = {xaxis[3 * j], xaxis[3 * j + 1], xaxis[3 * j + 2]};
+      T off[3] = {rp[0] - xanchor[3 * j], rp[1] - xanchor[3 * j + 1], rp[2] - xanchor[3 * j + 2]};
+      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+      cross3(cd + 3, ax, off);
+    }
+    for (int k = 0; k < 6; ++k) cdof[6 * lane + k] = cd[k];
+  }
+  for (int b = lane; b < nb; b += 32) {
+    T c[10];
+    const T mass = dex_ldg(m.body_mass + b);
+    const T* R = xmat + 9 * b;
+    T ip[3] = {dex_ldg(m.body_ipos + 3 * b), dex_ldg(m.body_ipos + 3 * b + 1), dex_ldg(m.body_ipos + 3 * b + 2)}, off[3];
+    rot_vec(off, R, ip);
+    const T* rp = ref + 3 * dex_ldg(m.body_tree + b);
+    off[0] += xpos[3 * b] - rp[0]; off[1] += xpos[3 * b + 1] - rp[1]; off[2] += xpos[3 * b + 2] - rp[2];
+    // I_world = R I_body R^T, I_body = [xx yy zz xy xz yz]
+    const T* I6 = m.body_inertia6 + 6 * b;
+    T Ib[9] = {dex_ldg(I6), dex_ldg(I6 + 3), dex_ldg(I6 + 4), dex_ldg(I6 + 3), dex_ldg(I6 + 1), dex_ldg(I6 + 5),
+               dex_ldg(I6 + 4), dex_ldg(I6 + 5), dex_ldg(I6 + 2)};
+    T RI[9];
+    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc)
+      RI[3 * r + cc] = R[3 * r] * Ib[cc] + R[3 * r + 1] * Ib[3 + cc] + R[3 * r + 2] * Ib[6 + cc];
+    T Iw[6];  // xx yy zz xy xz yz
+    Iw[0] = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2];
+    Iw[1] = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5];
+    Iw[2] = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8];
+    Iw[3] = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5];
+    Iw[4] = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8];
+    Iw[5] = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8];
+    const T o2 = dot3(off, off);
+    c[0] = Iw[0] + mass * (o2 - off[0] * off[0]);
+    c[1] = Iw[1] + mass * (o2 - off[1] * off[1]);
+    c[2] = Iw[2] + mass * (o2 - off[2] * off[2]);
+    c[3] = Iw[3] - mass * off[0] * off[1];
+    c[4] = Iw[4] - mass * off[0] * off[2];
+    c[5] = Iw[5] - mass * off[1] * off[2];
+    c[6] = mass * off[0]; c[7] = mass * off[1]; c[8] = mass * off[2]; c[9] = mass;
+    for (int k = 0; k < 10; ++k) { cinert[10 * b + k] = c[k]; crb[10 * b + k] = c[k]; }
+    // external spatial force about the reference point: [tau + off x f ; f]
+    const T* xf = m.body_xfrc + 6 * b;
+    T f[3] = {dex_ldg(xf), dex_ldg(xf + 1), dex_ldg(xf + 2)}, tq[3];
+    cross3(tq, off, f);
+    cfrc[6 * b] = -(dex_ldg(xf + 3) + tq[0]); cfrc[6 * b + 1] = -(dex_ldg(xf + 4) + tq[1]); cfrc[6 * b + 2] = -(dex_ldg(xf + 5) + tq[2]);
+    cfrc[6 * b + 3] = -f[0]; cfrc[6 * b + 4] = -f[1]; cfrc[6 * b + 5] = -f[2];
+  }
+  for (int t = lane; t < 32 * DEX_MSTRIDE; t += 32) M[t] = 0;
+  dex_syncwarp();
+
+  // ------------------------------------------------------------------ composite inertia (backward), M
+  for (int L = m.maxdepth; L >= 1; --L) {
+    for (int b = lane; b < nb; b += 32) {
+      if (dex_ldg(m.body_depth + b) != L) continue;
+      const int p = dex_ldg(m.body_parent + b);
+      if (p > 0) for (int k = 0; k < 10; ++k) dex_atomic_add(crb + 10 * p + k, crb[10 * b + k]);
+    }
+    dex_syncwarp();
+  }
+  if (isdof) {
+    T buf[6];
+    mul_inert_vec(buf, crb + 10 * dbody, cd);
+    for (int j = lane; j >= 0; j = dex_ldg(m.dof_parent + j)) {
+      const T* cj = cdof + 6 * j;
+      T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+      if (j == lane) s += dex_ldg(m.dof_armature + lane);
+      M[lane * DEX_MSTRIDE + j] = s;
+      M[j * DEX_MSTRIDE + lane] = s;
+    }
+  }
+  dex_syncwarp();
+
+  // ------------------------------------------------------------------ mj_comVel + mj_rne (forward), lane = body by level
+  for (int L = 0; L <= m.maxdepth; ++L) {
+    for (int b = lane; b < nb; b += 32) {
+      if (dex_ldg(m.body_depth + b) != L) continue;
+      T v[6], a[6];
+      if (b == 0) {
+        for (int k = 0; k < 6; ++k) { v[k] = 0; a[k] = 0; }
+        a[3] = -m.gravity[0]; a[4] = -m.gravity[1]; a[5] = -m.gravity[2];
+      } else {
+        const int p = dex_ldg(m.body_parent + b);
+        for (int k = 0; k < 6; ++k) { v[k] = cvel[6 * p + k]; a[k] = cacc[6 * p + k]; }
+        const int ja = dex_ldg(m.body_jntadr + b), jn = dex_ldg(m.body_jntnum + b);
+        for (int j = ja; j < ja + jn; ++j) {
+          const int da = dex_ldg(m.jnt_dofadr + j);
+          if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+            for (int i = 0; i < 3; ++i) {
+              for (int k = 0; k < 6; ++k) { cdofdot[6 * (da + i) + k] = 0; v[k] += cdof[6 * (da + i) + k] * qvel[da + i]; }
+            }
+            T cdd[3][6];
+            for (int i = 0; i < 3; ++i) cross_motion(cdd[i], v, cdof + 6 * (da + 3 + i));
+            for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) {
+              cdofdot[6 * (da + 3 + i) + k] = cdd[i][k];
+              v[k] += cdof[6 * (da + 3 + i) + k] * qvel[da + 3 + i];
+              a[k] += cdd[i][k] * qvel[da + 3 + i];
+            }
+          } else {
+            T cdd[6];
+            cross_motion(cdd, v, cdof + 6 * da);
+            for (int k = 0; k < 6; ++k) {
+              cdofdot[6 * da + k] = cdd[k];
+              v[k] += cdof[6 * da + k] * qvel[da];
+              a[k] += cdd[k] * qvel[da];
+            }
+          }
+        }
+      }
+      for (int k = 0; k < 6; ++k) { cvel[6 * b + k] = v[k]; cacc[6 * b + k] = a[k]; }
+      if (b > 0) {
+        T t1[6], t2[6], t3[6];
+        mul_inert_vec(t1, cinert + 10 * b, a);
+        mul_inert_vec(t2, cinert + 10 * b, v);
+        cross_force(t3, v, t2);
+        for (int k = 0; k < 6; ++k) cfrc[6 * b + k] += t1[k] + t3[k];
+      }
+    }
+    dex_syncwarp();
+  }
+  for (int L = m.maxdepth; L >= 1; --L) {
+    for (int b = lane; b < nb; b += 32) {
+      if (dex_ldg(m.body_depth + b) != L) continue;
+      const int p = dex_ldg(m.body_parent + b);
+      if (p > 0) for (int k = 0; k < 6; ++k) dex_atomic_add(cfrc + 6 * p + k, cfrc[6 * b + k]);
+    }
+    dex_syncwarp();
+  }
+  T bias = 0;
+  if (isdof) {
+    const T* cf = cfrc + 6 * dbody;
+    bias = cd[0] * cf[0] + cd[1] * cf[1] + cd[2] * cf[2] + cd[3] * cf[3] + cd[4] * cf[4] + cd[5] * cf[5];
+  }
+
+  // ------------------------------------------------------------------ actuation (lane = actuator), passive
+  vecA[lane] = 0;
+  dex_syncwarp();
+  if (lane < m.nu) {
+    const int a = lane, tid = dex_ldg(m.act_trnid + a);
+    const T gear = dex_ldg(m.act_gear + a);
+    T length = 0, vel = 0;
+    if (dex_ldg(m.act_trntype + a) == 0) {
+      length = qpos[dex_ldg(m.jnt_qposadr + tid)];
+      vel = qvel[dex_ldg(m.jnt_dofadr + tid)];
+    } else {
+      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
+      for (int w = wa; w < wa + wn; ++w) {
+        const int j = dex_ldg(m.wrap_jnt + w);
+        const T c = dex_ldg(m.wrap_coef + w);
+        length += c * qpos[dex_ldg(m.jnt_qposadr + j)];
+        vel += c * qvel[dex_ldg(m.jnt_dofadr + j)];
+      }
+    }
+    length *= gear; vel *= gear;
+    T c = st.ctrl[(size_t)env * st.ctrl_stride + a];
+    if (dex_ldg(m.act_ctrllimited + a)) c = dx_clamp(c, dex_ldg(m.act_ctrlrange + 2 * a), dex_ldg(m.act_ctrlrange + 2 * a + 1));
+    T f = dex_ldg(m.act_gainprm + 3 * a) * c + dex_ldg(m.act_biasprm + 3 * a) + dex_ldg(m.act_biasprm + 3 * a + 1) * length +
+          dex_ldg(m.act_biasprm + 3 * a + 2) * vel;
+    if (dex_ldg(m.act_forcelimited + a)) f = dx_clamp(f, dex_ldg(m.act_forcerange + 2 * a), dex_ldg(m.act_forcerange + 2 * a + 1));
+    if (dex_ldg(m.act_trntype + a) == 0) dex_atomic_add(vecA + dex_ldg(m.jnt_dofadr + tid), gear * f);
+    else {
+      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
+      for (int w = wa; w < wa + wn; ++w)
+        dex_atomic_add(vecA + dex_ldg(m.jnt_dofadr + dex_ldg(m.wrap_jnt + w)), gear * dex_ldg(m.wrap_coef + w) * f);
+    }
+  }
+  dex_syncwarp();
+  const T damping = isdof ? dex_ldg(m.dof_damping + lane) : T(0);
+  const T fs = isdof ? (-damping * qv - bias + vecA[lane]) : T(0);  // qfrc_smooth
+  dex_syncwarp();  // union A is dead from here on (cinert/crb/cvel/cacc/cfrc); union B may be written
+
+  // ------------------------------------------------------------------ constraint rows
+  // friction loss (lane = dof)
+  T f_loss = 0, f_R = 1, f_D = 0, f_aref = 0;
+  if (isdof) {
+    f_loss = dex_ldg(m.dof_frictionloss + lane);
+    if (f_loss > 0) {
+      T si[5], sr[2], imp, K, B;
+      for (int k = 0; k < 5; ++k) si[k] = dex_ldg(m.dof_solimp + 5 * lane + k);
+      sr[0] = dex_ldg(m.dof_solref + 2 * lane); sr[1] = dex_ldg(m.dof_solref + 2 * lane + 1);
+      dex_impedance(si, T(0), T(0), &imp);
+      dex_kb(sr, si, h, &K, &B);
+      f_R = dx_max(Real<T>::minval(), (1 - imp) / imp * dex_ldg(m.dof_invweight0 + lane));
+      f_D = 1 / f_R;
+      f_aref = -B * qv;
+    }
+  }
+  // joint limit (lane = dof of a limited hinge/slide joint; at most one side active)
+  T l_sign = 0, l_D = 0, l_aref = 0;
+  if (isdof) {
+    const int j = dex_ldg(m.dof_jnt + lane);
+    if (dex_ldg(m.jnt_limited + j) && dex_ldg(m.jnt_type + j) >= DEX_JNT_SLIDE) {
+      const T value = qpos[dex_ldg(m.jnt_qposadr + j)];
+      const T margin = dex_ldg(m.jnt_margin + j);
+      const T dlo = value - dex_ldg(m.jnt_range + 2 * j), dhi = dex_ldg(m.jnt_range + 2 * j + 1) - value;
+      T pos = 0;
+      if (dlo < margin) { l_sign = 1; pos = dlo; }
+      else if (dhi < margin) { l_sign = -1; pos = dhi; }
+      if (l_sign != 0) {
+        T si[5], sr[2], imp, K, B;
+        for (int k = 0; k < 5; ++k) si[k] = dex_ldg(m.jnt_solimp + 5 * j + k);
+        sr[0] = dex_ldg(m.jnt_solref + 2 * j); sr[1] = dex_ldg(m.jnt_solref + 2 * j + 1);
+        dex_impedance(si, pos, margin, &imp);
+        dex_kb(sr, si, h, &K, &B);
+        T R = dx_max(Real<T>::minval(), (1 - imp) / imp * dex_ldg(m.dof_invweight0 + lane));
+        l_D = 1 / R;
+        l_aref = -B * (l_sign * qv) - K * imp * (pos - margin);
+      }
+    }
+  }
+  // contacts: frame Jacobians (lane = dof)
+  int ncon = st.ncon[env];
+  if (ncon > DEX_MAXCON) ncon = DEX_MAXCON;
+  const T* cin = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
+  for (int c = 0; c < ncon; ++c) {
+    const T* cc = cin + c * DEX_CON_STRIDE;
+    T frame[9] = {cc[4], cc[5], cc[6], 0, 0, 0, 0, 0, 0};
+    make_frame(frame);
+    const int pr = (int)cc[7];
+    const int b1 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr)), b2 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr));
+    const unsigned m1 = (unsigned)dex_ldg(m.body_dofmask + b1), m2 = (unsigned)dex_ldg(m.body_dofmask + b2);
+    T j0 = 0, j1 = 0, j2 = 0;
+    if (isdof) {
+      const T sgn = T((m2 >> lane) & 1u) - T((m1 >> lane) & 1u);
+      if (sgn != 0) {
+        const T* rp = ref + 3 * dex_ldg(m.dof_tree + lane);
+        T off[3] = {cc[1] - rp[0], cc[2] - rp[1], cc[3] - rp[2]}, v[3];
+        cross3(v, cd, off);
+        v[0] += cd[3]; v[1] += cd[4]; v[2] += cd[5];
+        j0 = sgn * dot3(frame, v); j1 = sgn * dot3(frame + 3, v); j2 = sgn * dot3(frame + 6, v);
+      }
+    }
+    Jc[(3 * c) * DEX_JSTRIDE + lane] = j0;
+    Jc[(3 * c + 1) * DEX_JSTRIDE + lane] = j1;
+    Jc[(3 * c + 2) * DEX_JSTRIDE + lane] = j2;
+    if (lane == 0) *(int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK) = (int)(m1 | m2);
+  }
+  dex_syncwarp();
+  dex_contact_dots(Jc, qvel, 3 * ncon, nv, cdot);  // contact-frame velocities
+  if (lane < ncon) {  // lane = contact: impedance, R, aref of the 4 pyramid rows
+    const int c = lane;
+    const T* cc = cin + c * DEX_CON_STRIDE;
+    const int pr = (int)cc[7];
+    const int b1 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr)), b2 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr));
+    const T mu = dex_ldg(m.pair_friction + 5 * pr);
+    const T cmargin = dex_ldg(m.pair_margin + pr) - dex_ldg(m.pair_gap + pr);
+    T si[5], sr[2], imp, K, B;
+    for (int k = 0; k < 5; ++k) si[k] = dex_ldg(m.pair_solimp + 5 * pr + k);
+    sr[0] = dex_ldg(m.pair_solref + 2 * pr); sr[1] = dex_ldg(m.pair_solref + 2 * pr + 1);
+    dex_impedance(si, cc[0], cmargin, &imp);
+    dex_kb(sr, si, h, &K, &B);
+    const T tran = dex_ldg(m.body_invweight0 + 2 * b1) + dex_ldg(m.body_invweight0 + 2 * b2);
+    const T R0 = dx_max(Real<T>::minval(), (1 - imp) / imp * (tran + mu * mu * tran));
+    const T Rpy = 2 * mu * mu * R0;
+    T* cdt = cdat + c * DEX_CDAT_STRIDE;
+    cdt[CD_MU] = mu;
+    cdt[CD_D] = 1 / Rpy;
+    const T vn = cdot[3 * c], v1 = cdot[3 * c + 1], v2 = cdot[3 * c + 2];
+    const T kp = K * imp * (cc[0] - cmargin);
+    cdt[CD_AREF + 0] = -B * (vn + mu * v1) - kp;
+    cdt[CD_AREF + 1] = -B * (vn - mu * v1) - kp;
+    cdt[CD_AREF + 2] = -B * (vn + mu * v2) - kp;
+    cdt[CD_AREF + 3] = -B * (vn - mu * v2) - kp;
+    if (dbg.efc) {
+      T* e = dbg.efc + ((size_t)env * DEX_MAXCON + c) * 8;
+      e[0] = cdt[CD_D]; e[1] = cdt[CD_AREF]; e[2] = cdt[CD_AREF + 1]; e[3] = cdt[CD_AREF + 2]; e[4] = cdt[CD_AREF + 3];
+      e[5] = mu; e[6] = imp; e[7] = Rpy;
+    }
+  }
+  dex_syncwarp();
+
+  // ------------------------------------------------------------------ Newton solver (mj_solNewton)
+  const T scale = 1 / (m.meaninertia * (nv > 1 ? nv : 1));
+  const T tol = dx_max(m.tolerance, sizeof(T) == 4 ? T(1e-6) : T(1e-12));
+  vecA[lane] = qacc;
+  dex_syncwarp();
+  T Ma = dex_matvec(M, vecA, nv);
+  dex_contact_dots(Jc, vecA, 3 * ncon, nv, cdot);
+  if (lane < ncon) {
+    T* cdt = cdat + lane * DEX_CDAT_STRIDE;
+    const T mu = cdt[CD_MU], an = cdot[3 * lane], a1 = cdot[3 * lane + 1], a2 = cdot[3 * lane + 2];
+    cdt[CD_JAR + 0] = an + mu * a1 - cdt[CD_AREF + 0];
+    cdt[CD_JAR + 1] = an - mu * a1 - cdt[CD_AREF + 1];
+    cdt[CD_JAR + 2] = an + mu * a2 - cdt[CD_AREF + 2];
+    cdt[CD_JAR + 3] = an - mu * a2 - cdt[CD_AREF + 3];
+  }
+  T grad = 0, cost = 0, oldcost = 0, gnorm_prev = 0;
+  int iter = 0;
+  const int maxiter = m.iterations;
+  for (;; ++iter) {
+    // ---- forces, active sets, cost (PrimalUpdateConstraint)
+    T mycost = 0, fdof = 0, hdiag = 0;
+    if (isdof) {
+      mycost = T(0.5) * qacc * Ma - qacc * fs;
+      if (f_loss > 0) {
+        const T x = qacc - f_aref;
+        if (x <= -f_R * f_loss) { mycost += f_loss * (T(-0.5) * f_R * f_loss - x); fdof += f_loss; }
+        else if (x >= f_R * f_loss) { mycost += f_loss * (T(-0.5) * f_R * f_loss + x); fdof -= f_loss; }
+        else { mycost += T(0.5) * f_D * x * x; fdof -= f_D * x; hdiag += f_D; }
+      }
+      if (l_sign != 0) {
+        const T x = l_sign * qacc - l_aref;
+        if (x < 0) { mycost += T(0.5) * l_D * x * x; fdof -= l_sign * l_D * x; hdiag += l_D; }
+      }
+    }
+    if (lane < ncon) {
+      T* cdt = cdat + lane * DEX_CDAT_STRIDE;
+      const T D = cdt[CD_D], mu = cdt[CD_MU];
+      T f[4], w[4];
+      for (int r = 0; r < 4; ++r) {
+        const T x = cdt[CD_JAR + r];
+        if (x < 0) { f[r] = -D * x; w[r] = D; mycost += T(0.5) * D * x * x; } else { f[r] = 0; w[r] = 0; }
+      }
+      cdt[CD_F + 0] = f[0] + f[1] + f[2] + f[3];
+      cdt[CD_F + 1] = mu * (f[0] - f[1]);
+      cdt[CD_F + 2] = mu * (f[2] - f[3]);
+      cdt[CD_W + 0] = w[0] + w[1] + w[2] + w[3];
+      cdt[CD_W + 1] = mu * (w[0] - w[1]);
+      cdt[CD_W + 2] = mu * (w[2] - w[3]);
+      cdt[CD_W + 3] = mu * mu * (w[0] + w[1]);
+      cdt[CD_W + 4] = mu * mu * (w[2] + w[3]);
+    }
+    dex_syncwarp();
+    oldcost = cost;
+    cost = dex_warp_sum(mycost);
+    // ---- gradient = M a - qfrc_smooth - J^T f
+    T jtf = fdof;
+    if (isdof) {
+      for (int c = 0; c < ncon; ++c) {
+        const T* cdt = cdat + c * DEX_CDAT_STRIDE;
+        jtf += Jc[(3 * c) * DEX_JSTRIDE + lane] * cdt[CD_F] + Jc[(3 * c + 1) * DEX_JSTRIDE + lane] * cdt[CD_F + 1] +
+               Jc[(3 * c + 2) * DEX_JSTRIDE + lane] * cdt[CD_F + 2];
+      }
+    }
+    grad = isdof ? (Ma - fs - jtf) : T(0);
+    const T gnorm = dx_sqrt(dex_warp_sum(grad * grad));
+    if (scale * gnorm < tol) break;
+    if (iter > 0) {
+      // MuJoCo stops on improvement < tolerance; in FP32 the cost is only good to ~1e-7 relative,
+      // so the improvement test is honoured only once the gradient has stopped shrinking.
+      const T improvement = scale * (oldcost - cost);
+      if (improvement < tol && (sizeof(T) == 8 || gnorm > T(0.5) * gnorm_prev)) break;
+    }
+    gnorm_prev = gnorm;
+    if (iter >= maxiter) { status |= DEX_STATUS_SOLVER_MAXITER; break; }
+
+    // ---- Hessian H = M + J^T D_active J, Cholesky, search = -H^{-1} grad
+    if (isdof) {
+      for (int j = 0; j < nv; ++j) H[lane * DEX_MSTRIDE + j] = M[lane * DEX_MSTRIDE + j];
+      H[lane * DEX_MSTRIDE + lane] += hdiag;
+    }
+    for (int c = 0; c < ncon; ++c) {
+      const T* cdt = cdat + c * DEX_CDAT_STRIDE;
+      const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
+      if (w00 == 0) continue;  // no active row (warp-uniform)
+      unsigned mask = (unsigned)*(const int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK);
+      const T* J0 = Jc + (3 * c) * DEX_JSTRIDE;
+      const T* J1 = J0 + DEX_JSTRIDE;
+      const T* J2 = J1 + DEX_JSTRIDE;
+      const T a0 = J0[lane], a1 = J1[lane], a2 = J2[lane];
+      const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
+      const bool mine = isdof && ((mask >> lane) & 1u);
+      while (mask) {
+        const int j = dex_ffs(mask) - 1;
+        mask &= mask - 1;
+        if (mine) H[lane * DEX_MSTRIDE + j] += t0 * J0[j] + t1 * J1[j] + t2 * J2[j];
+      }
+    }
+    dex_syncwarp();
+    if (!dex_cholesky(H, dinv, nv)) status |= DEX_STATUS_CHOL_FAIL;
+    const T search = dex_chol_solve(H, dinv, nv, isdof ? -grad : T(0));
+
+    // ---- exact line search along `search` (PrimalSearch)
+    vecB[lane] = isdof ? search : T(0);
+    dex_syncwarp();
+    const T Mv = dex_matvec(M, vecB, nv);
+    dex_contact_dots(Jc, vecB, 3 * ncon, nv, cdot);
+    if (lane < ncon) {
+      T* cdt = cdat + lane * DEX_CDAT_STRIDE;
+      const T mu = cdt[CD_MU], sn = cdot[3 * lane], s1 = cdot[3 * lane + 1], s2 = cdot[3 * lane + 2];
+      cdt[CD_JV + 0] = sn + mu * s1; cdt[CD_JV + 1] = sn - mu * s1;
+      cdt[CD_JV + 2] = sn + mu * s2; cdt[CD_JV + 3] = sn - mu * s2;
+    }
+    dex_syncwarp();
+    const T q1 = isdof ? search * (Ma - fs) : T(0), q2 = isdof ? search * Mv : T(0);
+    T alpha = 0, lo = 0, hi = -1, g0 = 0;
+    for (int ls = 0; ls < 24; ++ls) {
+      T g = q1 + alpha * q2, hh = q2;
+      if (isdof) {
+        if (f_loss > 0) {
+          const T x = qacc + alpha * search - f_aref;
+          if (x <= -f_R * f_loss) g -= f_loss * search;
+          else if (x >= f_R * f_loss) g += f_loss * search;
+          else { g += f_D * x * search; hh += f_D * search * search; }
+        }
+        if (l_sign != 0) {
+          const T jv = l_sign * search, x = l_sign * qacc - l_aref + alpha * jv;
+          if (x < 0) { g += l_D * x * jv; hh += l_D * jv * jv; }
+        }
+      }
+      if (lane < ncon) {
+        const T* cdt = cdat + lane * DEX_CDAT_STRIDE;
+        const T D = cdt[CD_D];
+        for (int r = 0; r < 4; ++r) {
+          const T jv = cdt[CD_JV + r], x = cdt[CD_JAR + r] + alpha * jv;
+          if (x < 0) { g += D * x * jv; hh += D * jv * jv; }
+        }
+      }
+      g = dex_warp_sum(g);
+      hh = dex_warp_sum(hh);
+      if (ls == 0) {
+        g0 = g;
+        if (!(g < 0) || !(hh > 0)) break;  // not a descent direction: alpha stays 0
+      } else if (dx_abs(g) <= (sizeof(T) == 4 ? T(1e-5) : T(1e-12)) * dx_abs(g0)) break;
+      if (g < 0) lo = alpha; else hi = alpha;
+      T next = alpha - g / hh;
+      if (hi >= 0 && (next <= lo || next >= hi)) next = T(0.5) * (lo + hi);
+      if (next == alpha) break;
+      alpha = next;
+    }
+    if (alpha == 0) break;
+    // ---- move
+    if (isdof) { qacc += alpha * search; Ma += alpha * Mv; }
+    if (lane < ncon) {
+      T* cdt = cdat + lane * DEX_CDAT_STRIDE;
+      for (int r = 0; r < 4; ++r) cdt[CD_JAR + r] += alpha * cdt[CD_JV + r];
+    }
+    dex_syncwarp();
+  }
+
+  // ------------------------------------------------------------------ outputs of the forward pass
+  const T qfrc_constraint = isdof ? (Ma - grad - fs) : T(0);  // = J^T f at the final iterate
+  if (dbg.qacc && isdof) dbg.qacc[(size_t)env * nv + lane] = qacc;
+  if (dbg.qfrc_smooth && isdof) dbg.qfrc_smooth[(size_t)env * nv + lane] = fs;
+  if (dbg.qfrc_constraint && isdof) dbg.qfrc_constraint[(size_t)env * nv + lane] = qfrc_constraint;
+  if (dbg.M && isdof) for (int j = 0; j < nv; ++j) dbg.M[((size_t)env * nv + lane) * nv + j] = M[lane * DEX_MSTRIDE + j];
+  const bool bad = isdof && !(dx_abs(qacc) < T(1e10));  // mj_checkAcc (also catches NaN)
+  if (dex_ballot(bad)) status |= DEX_STATUS_BADQACC;
+  if (lane == 0) {
+    st.niter[env] = iter;
+    if (status) st.status[env] |= status;
+  }
+  if (!integrate) return;
+
+  // ------------------------------------------------------------------ mj_Euler (implicit joint damping)
+  if (isdof) {
+    for (int j = 0; j < nv; ++j) H[lane * DEX_MSTRIDE + j] = M[lane * DEX_MSTRIDE + j];
+    H[lane * DEX_MSTRIDE + lane] += h * damping;
+  }
+  dex_syncwarp();
+  dex_cholesky(H, dinv, nv);
+  const T qacc_e = dex_chol_solve(H, dinv, nv, isdof ? (fs + qfrc_constraint) : T(0));
+  const T qv_new = qv + h * qacc_e;
+  dex_syncwarp();
+  qvel[lane] = qv_new;
+  dex_syncwarp();
+  if (isdof) {
+    const int j = dex_ldg(m.dof_jnt + lane), da = dex_ldg(m.jnt_dofadr + j), qa = dex_ldg(m.jnt_qposadr + j);
+    if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+      if (lane == da) {
+        T* qp = st.qpos + (size_t)env * st.qpos_stride + qa;
+        for (int k = 0; k < 3; ++k) qp[k] = qpos[qa + k] + h * qvel[da + k];
+        T w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+        T q[4] = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
+        T n = dx_sqrt(dot3(w, w));
+        if (n >= Real<T>::minval()) {  // mju_quatIntegrate
+          T ax[3] = {w[0] / n, w[1] / n, w[2] / n}, dq[4], r[4];
+          axisangle2quat(dq, ax, h * n);
+          quat_mul(r, q, dq);
+          quat_normalize(r);
+          q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3];
+        }
+        for (int k = 0; k < 4; ++k) qp[3 + k] = q[k];
+      }
+    } else {
+      st.qpos[(size_t)env * st.qpos_stride + qa] = qpos[qa] + h * qv_new;
+    }
+    st.qvel[(size_t)env * st.qvel_stride + lane] = qv_new;
+    st.warm[(size_t)env * st.warm_stride + lane] = qacc;
+  }
+  if (lane == 0) st.time[env] += h;
+}
+
+#endif  // DEX_DYNAMICS_CUH_

@@ -1,0 +1,256 @@
+// dex_host_model.h — host-side preparation of the device model from the compiled blob
+// (include/dex_model_blob.h).  Pure C++ (no CUDA): derives the tables the kernels want
+// (tree depths, per-body dof masks, body-frame inertia matrices and hull vertices, body
+// bounding spheres, candidate pairs grouped by body pair, per-tree reference bodies) and
+// validates the model against the kernels' compile-time capacities.
+#ifndef DEX_HOST_MODEL_H_
+#define DEX_HOST_MODEL_H_
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dex_model_blob.h"
+#include "dex_model.cuh"
+
+struct HostModel {
+  int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
+  int nconmax, iterations, mpr_iterations;
+  double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia;
+#define DEX_X_I(name) std::vector<int> name;
+#define DEX_X_R(name) std::vector<double> name;
+#define DEX_X(t, name) DEX_X_##t(name)
+  DEX_DEVMODEL_ARRAYS(DEX_X)
+#undef DEX_X
+#undef DEX_X_I
+#undef DEX_X_R
+};
+
+namespace dex_host {
+
+inline void q2m(const double* q, double* m) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+
+// returns "" on success, else an error message
+inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
+  const uint8_t* base = (const uint8_t*)blob;
+  const DexBlobHeader* hd = (const DexBlobHeader*)blob;
+  if (nbytes < sizeof(DexBlobHeader) || hd->magic != DEX_BLOB_MAGIC) return "bad blob magic";
+  if (hd->version != DEX_BLOB_VERSION) return "blob version mismatch";
+  if (hd->nfields != DEXF_COUNT || hd->total_bytes != nbytes) return "blob size/field count mismatch";
+  const DexBlobEntry* ent = (const DexBlobEntry*)(base + sizeof(DexBlobHeader));
+  auto I = [&](int f) { return std::vector<int>((const int32_t*)(base + ent[f].offset), (const int32_t*)(base + ent[f].offset) + ent[f].count); };
+  auto F = [&](int f) { return std::vector<double>((const double*)(base + ent[f].offset), (const double*)(base + ent[f].offset) + ent[f].count); };
+  std::vector<int> D = I(DEXF_DIMS);
+  std::vector<double> O = F(DEXF_OPT);
+  M.nbody = D[DEXD_NBODY]; M.njnt = D[DEXD_NJNT]; M.nq = D[DEXD_NQ]; M.nv = D[DEXD_NV]; M.nu = D[DEXD_NU];
+  M.ntendon = D[DEXD_NTENDON]; M.ngeom = D[DEXD_NGEOM]; M.npair = D[DEXD_NPAIR]; M.nsite = D[DEXD_NSITE];
+  M.nconmax = D[DEXD_NCONMAX]; M.iterations = D[DEXD_SOLVER_ITERATIONS]; M.mpr_iterations = D[DEXD_MPR_ITERATIONS];
+  M.timestep = O[DEXO_TIMESTEP]; M.gravity[0] = O[DEXO_GRAVITY_X]; M.gravity[1] = O[DEXO_GRAVITY_Y]; M.gravity[2] = O[DEXO_GRAVITY_Z];
+  M.tolerance = O[DEXO_TOLERANCE]; M.mpr_tolerance = O[DEXO_MPR_TOLERANCE]; M.meaninertia = O[DEXO_MEANINERTIA];
+  if (M.nbody > DEX_MAXBODY) return "nbody exceeds DEX_MAXBODY";
+  if (M.nv > DEX_MAXDOF) return "nv exceeds DEX_MAXDOF (32)";
+  if (M.njnt > DEX_MAXJNT) return "njnt exceeds DEX_MAXJNT";
+  if (M.nu > DEX_MAXU) return "nu exceeds DEX_MAXU";
+  if (M.nq > 48) return "nq exceeds 48";
+  if (M.npair >= (1 << 24)) return "too many candidate pairs";
+
+  M.body_parent = I(DEXF_BODY_PARENT); M.body_jntadr = I(DEXF_BODY_JNTADR); M.body_jntnum = I(DEXF_BODY_JNTNUM);
+  M.body_dofadr = I(DEXF_BODY_DOFADR); M.body_dofnum = I(DEXF_BODY_DOFNUM); M.body_weld = I(DEXF_BODY_WELD);
+  M.body_pos = F(DEXF_BODY_POS); M.body_quat = F(DEXF_BODY_QUAT); M.body_ipos = F(DEXF_BODY_IPOS);
+  M.body_mass = F(DEXF_BODY_MASS); M.body_xfrc = F(DEXF_BODY_XFRC); M.body_invweight0 = F(DEXF_BODY_INVWEIGHT0);
+  M.jnt_type = I(DEXF_JNT_TYPE); M.jnt_body = I(DEXF_JNT_BODY); M.jnt_qposadr = I(DEXF_JNT_QPOSADR);
+  M.jnt_dofadr = I(DEXF_JNT_DOFADR); M.jnt_limited = I(DEXF_JNT_LIMITED); M.jnt_pos = F(DEXF_JNT_POS);
+  M.jnt_axis = F(DEXF_JNT_AXIS); M.jnt_range = F(DEXF_JNT_RANGE); M.jnt_margin = F(DEXF_JNT_MARGIN);
+  M.jnt_solref = F(DEXF_JNT_SOLREF); M.jnt_solimp = F(DEXF_JNT_SOLIMP); M.qpos0 = F(DEXF_QPOS0);
+  M.dof_body = I(DEXF_DOF_BODY); M.dof_jnt = I(DEXF_DOF_JNT); M.dof_parent = I(DEXF_DOF_PARENT);
+  M.dof_armature = F(DEXF_DOF_ARMATURE); M.dof_damping = F(DEXF_DOF_DAMPING); M.dof_frictionloss = F(DEXF_DOF_FRICTIONLOSS);
+  M.dof_invweight0 = F(DEXF_DOF_INVWEIGHT0); M.dof_solref = F(DEXF_DOF_SOLREF); M.dof_solimp = F(DEXF_DOF_SOLIMP);
+  M.ten_adr = I(DEXF_TEN_ADR); M.ten_num = I(DEXF_TEN_NUM); M.ten_limited = I(DEXF_TEN_LIMITED);
+  M.ten_range = F(DEXF_TEN_RANGE); M.ten_margin = F(DEXF_TEN_MARGIN); M.ten_invweight0 = F(DEXF_TEN_INVWEIGHT0);
+  M.ten_solref = F(DEXF_TEN_SOLREF); M.ten_solimp = F(DEXF_TEN_SOLIMP); M.wrap_jnt = I(DEXF_WRAP_JNT); M.wrap_coef = F(DEXF_WRAP_COEF);
+  M.act_trntype = I(DEXF_ACT_TRNTYPE); M.act_trnid = I(DEXF_ACT_TRNID); M.act_ctrllimited = I(DEXF_ACT_CTRLLIMITED);
+  M.act_forcelimited = I(DEXF_ACT_FORCELIMITED); M.act_gear = F(DEXF_ACT_GEAR); M.act_gainprm = F(DEXF_ACT_GAINPRM);
+  M.act_biasprm = F(DEXF_ACT_BIASPRM); M.act_ctrlrange = F(DEXF_ACT_CTRLRANGE); M.act_forcerange = F(DEXF_ACT_FORCERANGE);
+  M.geom_type = I(DEXF_GEOM_TYPE); M.geom_body = I(DEXF_GEOM_BODY); M.geom_pos = F(DEXF_GEOM_POS);
+  M.geom_size = F(DEXF_GEOM_SIZE); M.geom_rbound = F(DEXF_GEOM_RBOUND);
+  M.site_body = I(DEXF_SITE_BODY); M.site_pos = F(DEXF_SITE_POS);
+  for (int t = 0; t < M.ntendon; ++t) if (M.ten_limited[t]) return "limited tendons are not supported yet";
+  if (M.ntendon > DEX_MAXTEN) return "ntendon exceeds DEX_MAXTEN";
+
+  // ---- tree structure
+  const int nb = M.nbody, nv = M.nv;
+  M.body_depth.assign(nb, 0);
+  M.maxdepth = 0;
+  for (int b = 1; b < nb; ++b) { M.body_depth[b] = M.body_depth[M.body_parent[b]] + 1; M.maxdepth = std::max(M.maxdepth, M.body_depth[b]); }
+  std::vector<int> broot = I(DEXF_BODY_ROOT);
+  std::map<int, int> tree_of_root;
+  M.body_tree.assign(nb, 0);
+  tree_of_root[0] = 0;  // world
+  for (int b = 1; b < nb; ++b) {
+    if (!tree_of_root.count(broot[b])) { int t = (int)tree_of_root.size(); tree_of_root[broot[b]] = t; }
+    M.body_tree[b] = tree_of_root[broot[b]];
+  }
+  M.ntree = (int)tree_of_root.size();
+  if (M.ntree > 5) return "more than 5 kinematic trees";
+  M.dof_tree.assign(nv, 0);
+  for (int i = 0; i < nv; ++i) M.dof_tree[i] = M.body_tree[M.dof_body[i]];
+  M.body_dofmask.assign(nb, 0);
+  for (int b = 1; b < nb; ++b) {
+    unsigned mask = (unsigned)M.body_dofmask[M.body_parent[b]];
+    for (int i = 0; i < M.body_dofnum[b]; ++i) mask |= 1u << (M.body_dofadr[b] + i);
+    M.body_dofmask[b] = (int)mask;
+  }
+  // reference body of each tree: the moving body whose origin (at qpos0) minimises the mean squared
+  // distance to the tree's moving bodies -> small lever arms in FP32 (MuJoCo uses the subtree COM)
+  {
+    std::vector<double> xp(3 * nb, 0), xm(9 * nb, 0), xq(4 * nb, 0);
+    xq[0] = 1; q2m(&xq[0], &xm[0]);
+    for (int b = 1; b < nb; ++b) {
+      int p = M.body_parent[b];
+      const double* R = &xm[9 * p];
+      const double* bp = &M.body_pos[3 * b];
+      for (int k = 0; k < 3; ++k) xp[3 * b + k] = xp[3 * p + k] + R[3 * k] * bp[0] + R[3 * k + 1] * bp[1] + R[3 * k + 2] * bp[2];
+      const double* a = &xq[4 * p];
+      const double* q = &M.body_quat[4 * b];
+      double r[4] = {a[0] * q[0] - a[1] * q[1] - a[2] * q[2] - a[3] * q[3], a[0] * q[1] + a[1] * q[0] + a[2] * q[3] - a[3] * q[2],
+                     a[0] * q[2] - a[1] * q[3] + a[2] * q[0] + a[3] * q[1], a[0] * q[3] + a[1] * q[2] - a[2] * q[1] + a[3] * q[0]};
+      if (M.body_jntnum[b] > 0 && M.jnt_type[M.body_jntadr[b]] == DEX_JNT_FREE) {
+        int qa = M.jnt_qposadr[M.body_jntadr[b]];
+        for (int k = 0; k < 3; ++k) xp[3 * b + k] = M.qpos0[qa + k];
+        for (int k = 0; k < 4; ++k) r[k] = M.qpos0[qa + 3 + k];
+      }
+      std::memcpy(&xq[4 * b], r, sizeof(r));
+      q2m(r, &xm[9 * b]);
+    }
+    M.tree_refbody.assign(M.ntree, 0);
+    for (int t = 1; t < M.ntree; ++t) {
+      double best = 1e300; int bestb = 0;
+      for (int c = 1; c < nb; ++c) {
+        if (M.body_tree[c] != t) continue;
+        double s = 0; int n = 0;
+        for (int b = 1; b < nb; ++b) if (M.body_tree[b] == t && M.body_weld[b] != 0) {
+          double d2 = 0;
+          for (int k = 0; k < 3; ++k) d2 += (xp[3 * b + k] - xp[3 * c + k]) * (xp[3 * b + k] - xp[3 * c + k]);
+          s += d2; n++;
+        }
+        if (n == 0) { bestb = c; break; }
+        if (s < best) { best = s; bestb = c; }
+      }
+      M.tree_refbody[t] = bestb;
+    }
+  }
+  // ---- body-frame inertia matrices
+  {
+    std::vector<double> iq = F(DEXF_BODY_IQUAT), in = F(DEXF_BODY_INERTIA);
+    M.body_inertia6.assign(6 * nb, 0);
+    for (int b = 0; b < nb; ++b) {
+      double R[9], A[9];
+      q2m(&iq[4 * b], R);
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += R[3 * r + k] * in[3 * b + k] * R[3 * c + k];
+        A[3 * r + c] = s;
+      }
+      double* o = &M.body_inertia6[6 * b];
+      o[0] = A[0]; o[1] = A[4]; o[2] = A[8]; o[3] = A[1]; o[4] = A[2]; o[5] = A[5];
+    }
+  }
+  // ---- geoms: body-frame rotation matrices and hull vertices
+  {
+    std::vector<double> gq = F(DEXF_GEOM_QUAT), v = F(DEXF_VERT);
+    std::vector<int> va = I(DEXF_GEOM_VERTADR), vn = I(DEXF_GEOM_VERTNUM);
+    M.geom_mat.assign(9 * M.ngeom, 0);
+    M.geom_vertadr.assign(M.ngeom, -1);
+    M.geom_vertnum = vn;
+    M.vert.clear();
+    for (int g = 0; g < M.ngeom; ++g) {
+      double* G = &M.geom_mat[9 * g];
+      q2m(&gq[4 * g], G);
+      int t = M.geom_type[g];
+      if (t != DEX_GEOM_PLANE && t != DEX_GEOM_BOX && t != DEX_GEOM_MESH) return "unsupported geom type (plane/box/mesh only)";
+      if (t == DEX_GEOM_MESH) {
+        M.geom_vertadr[g] = (int)(M.vert.size() / 3);
+        for (int i = 0; i < vn[g]; ++i) {
+          const double* p = &v[3 * (va[g] + i)];
+          for (int k = 0; k < 3; ++k) M.vert.push_back(M.geom_pos[3 * g + k] + G[3 * k] * p[0] + G[3 * k + 1] * p[1] + G[3 * k + 2] * p[2]);
+        }
+      }
+    }
+    // body-frame AABB (centre, half extents) of every geom: tightens the broadphase (conservative)
+    M.geom_aabb.assign(6 * M.ngeom, 0);
+    for (int g = 0; g < M.ngeom; ++g) {
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      auto grow = [&](const double* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } };
+      if (M.geom_type[g] == DEX_GEOM_MESH) {
+        for (int i = 0; i < vn[g]; ++i) grow(&M.vert[3 * (M.geom_vertadr[g] + i)]);
+      } else if (M.geom_type[g] == DEX_GEOM_BOX) {
+        const double* G = &M.geom_mat[9 * g];
+        for (int c = 0; c < 8; ++c) {
+          double l[3] = {(c & 1 ? 1 : -1) * M.geom_size[3 * g], (c & 2 ? 1 : -1) * M.geom_size[3 * g + 1], (c & 4 ? 1 : -1) * M.geom_size[3 * g + 2]}, p[3];
+          for (int k = 0; k < 3; ++k) p[k] = M.geom_pos[3 * g + k] + G[3 * k] * l[0] + G[3 * k + 1] * l[1] + G[3 * k + 2] * l[2];
+          grow(p);
+        }
+      } else { for (int k = 0; k < 3; ++k) { lo[k] = -1e30; hi[k] = 1e30; } }
+      for (int k = 0; k < 3; ++k) { M.geom_aabb[6 * g + k] = 0.5 * (lo[k] + hi[k]); M.geom_aabb[6 * g + 3 + k] = 0.5 * (hi[k] - lo[k]); }
+    }
+    if (M.vert.empty()) M.vert.assign(3, 0.0);
+  }
+  // ---- body bounding spheres (body frame); radius < 0 marks a body that owns a plane
+  M.body_bsphere.assign(4 * nb, 0);
+  for (int b = 0; b < nb; ++b) {
+    double c[3] = {0, 0, 0}; int n = 0; bool plane = false;
+    for (int g = 0; g < M.ngeom; ++g) if (M.geom_body[g] == b) {
+      if (M.geom_type[g] == DEX_GEOM_PLANE) plane = true;
+      for (int k = 0; k < 3; ++k) c[k] += M.geom_pos[3 * g + k];
+      n++;
+    }
+    if (n) for (int k = 0; k < 3; ++k) c[k] /= n;
+    double r = 0;
+    for (int g = 0; g < M.ngeom; ++g) if (M.geom_body[g] == b) {
+      double d2 = 0;
+      for (int k = 0; k < 3; ++k) d2 += (M.geom_pos[3 * g + k] - c[k]) * (M.geom_pos[3 * g + k] - c[k]);
+      r = std::max(r, std::sqrt(d2) + M.geom_rbound[g]);
+    }
+    for (int k = 0; k < 3; ++k) M.body_bsphere[4 * b + k] = c[k];
+    M.body_bsphere[4 * b + 3] = plane ? -1.0 : r;
+  }
+  // ---- candidate pairs grouped by body pair (blob order is already grouped; verified here)
+  M.pair_geom1 = I(DEXF_PAIR_GEOM1); M.pair_geom2 = I(DEXF_PAIR_GEOM2); M.pair_condim = I(DEXF_PAIR_CONDIM);
+  M.pair_friction = F(DEXF_PAIR_FRICTION); M.pair_solref = F(DEXF_PAIR_SOLREF); M.pair_solimp = F(DEXF_PAIR_SOLIMP);
+  M.pair_margin = F(DEXF_PAIR_MARGIN); M.pair_gap = F(DEXF_PAIR_GAP);
+  {
+    double maxmargin = 0;
+    for (int p = 0; p < M.npair; ++p) {
+      if (M.pair_condim[p] != 3) return "only condim-3 contact pairs are supported yet";
+      int t1 = M.geom_type[M.pair_geom1[p]], t2 = M.geom_type[M.pair_geom2[p]];
+      bool okp = (t1 == DEX_GEOM_PLANE && (t2 == DEX_GEOM_BOX || t2 == DEX_GEOM_MESH)) ||
+                 ((t1 == DEX_GEOM_BOX || t1 == DEX_GEOM_MESH) && t2 == DEX_GEOM_MESH);
+      if (!okp) return "unsupported geom pair type";
+      maxmargin = std::max(maxmargin, M.pair_margin[p]);
+      int a = M.geom_body[M.pair_geom1[p]], b = M.geom_body[M.pair_geom2[p]];
+      if (M.bp_body1.empty() || M.bp_body1.back() != a || M.bp_body2.back() != b) {
+        for (size_t q = 0; q < M.bp_body1.size(); ++q)
+          if (M.bp_body1[q] == a && M.bp_body2[q] == b) return "candidate pairs are not grouped by body pair";
+        M.bp_body1.push_back(a); M.bp_body2.push_back(b); M.bp_pairadr.push_back(p); M.bp_pairnum.push_back(0);
+      }
+      M.bp_pairnum.back()++;
+    }
+    M.nbodypair = (int)M.bp_body1.size();
+    // fold the largest pair margin into the body spheres so the body-level cull stays conservative
+    for (int b = 0; b < nb; ++b) if (M.body_bsphere[4 * b + 3] >= 0) M.body_bsphere[4 * b + 3] += 0.5 * maxmargin;
+  }
+  if (M.bp_body1.empty()) { M.bp_body1.assign(1, 0); M.bp_body2.assign(1, 0); M.bp_pairadr.assign(1, 0); M.bp_pairnum.assign(1, 0); }
+  return "";
+}
+
+}  // namespace dex_host
+#endif  // DEX_HOST_MODEL_H_

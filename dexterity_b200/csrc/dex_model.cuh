@@ -1,0 +1,185 @@
+// dex_model.cuh — device-side model constants (one copy per GPU, shared by all envs) and
+// small vector/quaternion helpers.  Populated by dex_api.cu from the host blob
+// (include/dex_model_blob.h); arrays are converted to the batch scalar type T.
+#ifndef DEX_MODEL_CUH_
+#define DEX_MODEL_CUH_
+
+#include "dex_portable.cuh"
+
+#define DEX_MAXBODY 40
+#define DEX_MAXDOF 32
+#define DEX_MAXJNT 32
+#define DEX_MAXU 32
+#define DEX_MAXTEN 8
+#define DEX_MAXCON 24      // per-env contact capacity (overflow sets a status bit)
+#define DEX_MAXCAND 128    // per-env narrowphase candidate capacity
+#define DEX_CON_STRIDE 8   // words per stored contact: dist, pos(3), normal(3), pair id
+
+// per-env status bits (SURVEY.md §5 failure detection: mirrors upstream PhysicsError handling)
+#define DEX_STATUS_BADQACC 1u
+#define DEX_STATUS_CON_OVERFLOW 2u
+#define DEX_STATUS_CAND_OVERFLOW 4u
+#define DEX_STATUS_SOLVER_MAXITER 8u
+#define DEX_STATUS_CHOL_FAIL 16u
+
+enum { DEX_JNT_FREE = 0, DEX_JNT_BALL = 1, DEX_JNT_SLIDE = 2, DEX_JNT_HINGE = 3 };
+enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_BOX = 6, DEX_GEOM_MESH = 7 };
+
+// X(type, name): type 'I' = int32 array, 'R' = real array
+#define DEX_DEVMODEL_ARRAYS(X)                                                             \
+  X(I, body_parent) X(I, body_depth) X(I, body_jntadr) X(I, body_jntnum) X(I, body_dofadr) \
+  X(I, body_dofnum) X(I, body_tree) X(I, body_dofmask) X(I, body_weld)                     \
+  X(R, body_pos) X(R, body_quat) X(R, body_ipos) X(R, body_mass) X(R, body_inertia6)       \
+  X(R, body_xfrc) X(R, body_invweight0) X(R, body_bsphere)                                 \
+  X(I, tree_refbody)                                                                       \
+  X(I, jnt_type) X(I, jnt_body) X(I, jnt_qposadr) X(I, jnt_dofadr) X(I, jnt_limited)       \
+  X(R, jnt_pos) X(R, jnt_axis) X(R, jnt_range) X(R, jnt_margin) X(R, jnt_solref)           \
+  X(R, jnt_solimp) X(R, qpos0)                                                             \
+  X(I, dof_body) X(I, dof_jnt) X(I, dof_parent) X(I, dof_tree)                             \
+  X(R, dof_armature) X(R, dof_damping) X(R, dof_frictionloss) X(R, dof_invweight0)         \
+  X(R, dof_solref) X(R, dof_solimp)                                                        \
+  X(I, ten_adr) X(I, ten_num) X(I, ten_limited) X(R, ten_range) X(R, ten_margin)           \
+  X(R, ten_invweight0) X(R, ten_solref) X(R, ten_solimp) X(I, wrap_jnt) X(R, wrap_coef)    \
+  X(I, act_trntype) X(I, act_trnid) X(I, act_ctrllimited) X(I, act_forcelimited)           \
+  X(R, act_gear) X(R, act_gainprm) X(R, act_biasprm) X(R, act_ctrlrange) X(R, act_forcerange) \
+  X(I, geom_type) X(I, geom_body) X(I, geom_vertadr) X(I, geom_vertnum)                    \
+  X(R, geom_pos) X(R, geom_mat) X(R, geom_size) X(R, geom_rbound) X(R, geom_aabb) X(R, vert)               \
+  X(I, bp_body1) X(I, bp_body2) X(I, bp_pairadr) X(I, bp_pairnum)                          \
+  X(I, pair_geom1) X(I, pair_geom2) X(I, pair_condim) X(R, pair_friction) X(R, pair_solref) \
+  X(R, pair_solimp) X(R, pair_margin) X(R, pair_gap)                                       \
+  X(I, site_body) X(R, site_pos)
+
+template <typename T>
+struct DevModel {
+  int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
+  int nconmax, iterations, mpr_iterations;
+  T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia;
+#define DEX_X_I(name) const int* name;
+#define DEX_X_R(name) const T* name;
+#define DEX_X(t, name) DEX_X_##t(name)
+  DEX_DEVMODEL_ARRAYS(DEX_X)
+#undef DEX_X
+#undef DEX_X_I
+#undef DEX_X_R
+};
+
+// Per-batch state pointers (torch-owned storage bound through dex_bind).
+// Row-major [num_envs][stride]; strides are in elements.
+template <typename T>
+struct BatchState {
+  int nenv;
+  T* qpos; int qpos_stride;
+  T* qvel; int qvel_stride;
+  T* ctrl; int ctrl_stride;
+  T* warm; int warm_stride;       // qacc_warmstart
+  T* time;                        // [nenv]
+  unsigned* status;               // [nenv] DEX_STATUS_* bits (sticky until reset)
+  // batch-owned scratch
+  T* contact;                     // [nenv][DEX_MAXCON][DEX_CON_STRIDE]
+  int* ncon;                      // [nenv]
+  int* niter;                     // [nenv] solver iterations of the last mj_step
+};
+
+// ---------------------------------------------------------------------------------------
+// math helpers
+// ---------------------------------------------------------------------------------------
+template <typename T> struct Real;
+template <> struct Real<float> {
+  static DEX_HD float eps() { return 1.1920929e-7f; }
+  static DEX_HD float minval() { return 1e-15f; }
+  static DEX_HD float big() { return 3.0e38f; }
+};
+template <> struct Real<double> {
+  static DEX_HD double eps() { return 2.220446049250313e-16; }
+  static DEX_HD double minval() { return 1e-15; }
+  static DEX_HD double big() { return 1.0e300; }
+};
+
+template <typename T> DEX_DEV T dx_sqrt(T x) { return sqrt(x); }
+template <typename T> DEX_DEV T dx_abs(T x) { return x < 0 ? -x : x; }
+template <typename T> DEX_DEV T dx_min(T a, T b) { return a < b ? a : b; }
+template <typename T> DEX_DEV T dx_max(T a, T b) { return a > b ? a : b; }
+template <typename T> DEX_DEV T dx_clamp(T x, T lo, T hi) { return dx_min(dx_max(x, lo), hi); }
+
+template <typename T> DEX_DEV T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> DEX_DEV void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> DEX_DEV T normalize3(T* a) {
+  T n = dx_sqrt(dot3(a, a));
+  if (n < Real<T>::minval()) { a[0] = 1; a[1] = 0; a[2] = 0; }
+  else { T inv = T(1) / n; a[0] *= inv; a[1] *= inv; a[2] *= inv; }
+  return n;
+}
+template <typename T> DEX_DEV void quat_mul(T* r, const T* a, const T* b) {
+  T w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+template <typename T> DEX_DEV void quat_normalize(T* q) {
+  T n = dx_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < Real<T>::minval()) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+  else { T inv = T(1) / n; q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv; }
+}
+template <typename T> DEX_DEV void quat2mat(T* m, const T* q) {
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+template <typename T> DEX_DEV void rot_vec(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  T y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  T z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> DEX_DEV void rotT_vec(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2];
+  T y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2];
+  T z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> DEX_DEV void axisangle2quat(T* q, const T* axis, T ang) {
+  T s = sin(ang * T(0.5));
+  q[0] = cos(ang * T(0.5)); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+// mju_makeFrame: frame[0:3] given (normal); builds the two tangents
+template <typename T> DEX_DEV void make_frame(T* f) {
+  normalize3(f);
+  f[3] = 0; f[4] = 0; f[5] = 0;
+  if (f[1] < T(0.5) && f[1] > T(-0.5)) f[4] = 1; else f[5] = 1;
+  T dp = dot3(f, f + 3);
+  f[3] -= dp * f[0]; f[4] -= dp * f[1]; f[5] -= dp * f[2];
+  normalize3(f + 3);
+  cross3(f + 6, f, f + 3);
+}
+// spatial algebra on [ang(3); lin(3)] vectors and 10-float inertias (MuJoCo layout)
+template <typename T> DEX_DEV void mul_inert_vec(T* r, const T* c, const T* v) {
+  r[0] = c[0] * v[0] + c[3] * v[1] + c[4] * v[2] - c[8] * v[4] + c[7] * v[5];
+  r[1] = c[3] * v[0] + c[1] * v[1] + c[5] * v[2] + c[8] * v[3] - c[6] * v[5];
+  r[2] = c[4] * v[0] + c[5] * v[1] + c[2] * v[2] - c[7] * v[3] + c[6] * v[4];
+  r[3] = c[8] * v[1] - c[7] * v[2] + c[9] * v[3];
+  r[4] = c[6] * v[2] - c[8] * v[0] + c[9] * v[4];
+  r[5] = c[7] * v[0] - c[6] * v[1] + c[9] * v[5];
+}
+template <typename T> DEX_DEV void cross_motion(T* r, const T* v, const T* s) {
+  T a[3], b[3], c[3];
+  cross3(a, v, s);
+  cross3(b, v, s + 3);
+  cross3(c, v + 3, s);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2];
+  r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+template <typename T> DEX_DEV void cross_force(T* r, const T* v, const T* f) {
+  T a[3], b[3], c[3];
+  cross3(a, v, f);
+  cross3(b, v + 3, f + 3);
+  cross3(c, v, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2];
+  r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+
+#endif  // DEX_MODEL_CUH_

@@ -1,0 +1,90 @@
+// dex_portable.cuh — warp-level primitives used by every kernel body.
+//
+// Under nvcc these map 1:1 onto CUDA intrinsics (full-mask warp shuffles, ballots,
+// __syncwarp, shared-memory atomics, __ldg).  When the header is compiled by a host
+// compiler with DEX_WARP_EMU defined (tests/emu only — TEST INFRASTRUCTURE, never part of
+// the product library) the same names are provided by a cooperative-fiber warp emulator
+// so kernel bodies can be debugged without a GPU.  The product library
+// (libdexb200.so) is compiled by nvcc only and contains no host execution path.
+#ifndef DEX_PORTABLE_CUH_
+#define DEX_PORTABLE_CUH_
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define DEX_DEV __device__ __forceinline__
+#define DEX_DEV_NOINLINE __device__ __noinline__
+#define DEX_HD __host__ __device__ __forceinline__
+#define DEX_FULL 0xffffffffu
+
+DEX_DEV int dex_lane() { return threadIdx.x & 31; }
+template <typename T> DEX_DEV T dex_shfl(T v, int src) { return __shfl_sync(DEX_FULL, v, src); }
+template <typename T> DEX_DEV T dex_shfl_xor(T v, int m) { return __shfl_xor_sync(DEX_FULL, v, m); }
+DEX_DEV unsigned dex_ballot(bool p) { return __ballot_sync(DEX_FULL, p); }
+DEX_DEV void dex_syncwarp() { __syncwarp(); }
+template <typename T> DEX_DEV void dex_atomic_add(T* p, T v) { atomicAdd(p, v); }
+template <typename T> DEX_DEV T dex_ldg(const T* p) { return __ldg(p); }
+DEX_DEV int dex_popc(unsigned x) { return __popc(x); }
+DEX_DEV int dex_ffs(unsigned x) { return __ffs(x); }
+
+#elif defined(DEX_WARP_EMU)
+#include <cmath>
+#define DEX_DEV inline
+#define DEX_DEV_NOINLINE inline
+#define DEX_HD inline
+namespace dex_emu {
+int lane();
+uint64_t exchange(uint64_t v, int src);  // shuffle: every live lane contributes v, reads lane src
+unsigned ballot(bool p);
+void barrier();
+}  // namespace dex_emu
+inline int dex_lane() { return dex_emu::lane(); }
+template <typename T> inline T dex_shfl(T v, int src) {
+  uint64_t raw = 0;
+  __builtin_memcpy(&raw, &v, sizeof(T));
+  raw = dex_emu::exchange(raw, src & 31);
+  T out;
+  __builtin_memcpy(&out, &raw, sizeof(T));
+  return out;
+}
+template <typename T> inline T dex_shfl_xor(T v, int m) { return dex_shfl(v, dex_emu::lane() ^ m); }
+inline unsigned dex_ballot(bool p) { return dex_emu::ballot(p); }
+inline void dex_syncwarp() { dex_emu::barrier(); }
+template <typename T> inline void dex_atomic_add(T* p, T v) { *p += v; }  // fibers are serialised
+template <typename T> inline T dex_ldg(const T* p) { return *p; }
+inline int dex_popc(unsigned x) { return __builtin_popcount(x); }
+inline int dex_ffs(unsigned x) { return __builtin_ffs((int)x); }
+#else
+#error "dex_portable.cuh: compile with nvcc (product) or -DDEX_WARP_EMU (tests/emu only)"
+#endif
+
+// ---------------------------------------------------------------------------------------
+// warp reductions (all 32 lanes must call)
+// ---------------------------------------------------------------------------------------
+template <typename T> DEX_DEV T dex_warp_sum(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += dex_shfl_xor(v, m);
+  return v;
+}
+template <typename T> DEX_DEV T dex_warp_max(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) { T o = dex_shfl_xor(v, m); v = o > v ? o : v; }
+  return v;
+}
+template <typename T> DEX_DEV T dex_warp_min(T v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) { T o = dex_shfl_xor(v, m); v = o < v ? o : v; }
+  return v;
+}
+// argmax with lowest-index tie-break (matches a serial "first strict maximum" scan)
+template <typename T> DEX_DEV void dex_warp_argmax(T& v, int& idx) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    T ov = dex_shfl_xor(v, m);
+    int oi = dex_shfl_xor(idx, m);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+#endif  // DEX_PORTABLE_CUH_

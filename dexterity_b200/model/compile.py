@@ -30,7 +30,7 @@ _HEADER = os.path.join(os.path.dirname(__file__), "..", "..", "include", "dex_mo
 
 def _parse_header() -> Tuple[List[Tuple[str, str]], Dict[str, int], Dict[str, int]]:
     src = open(_HEADER).read()
-    fields = re.findall(r"X\((\w+),\s*DEX_(I32|F64),", src)
+    fields = re.findall(r"X\((\w+),\s*DEX_BLOB_(I32|F64),", src)
 
     def enum(name: str) -> Dict[str, int]:
         body = re.search(r"enum %s \{(.*?)\};" % name, src, re.S).group(1)

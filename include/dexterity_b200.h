@@ -1,0 +1,95 @@
+/* dexterity_b200.h — C ABI of the B200-native batched physics backend (libdexb200.so).
+ *
+ * The reference has no FFI layer of its own: its boundary to the physics engine is the
+ * `dm_control.mjcf.Physics` object handed to every composer hook plus module-level
+ * `mujoco.mj_*` calls.  Each entry point below names the reference call
+ * site(s) it replaces.  Conventions:
+ *   - every function returns 0 on success, a negative DEX_E_* code on failure; the message is
+ *     available from dex_last_error() (thread-local).  No C++ exception crosses the ABI.
+ *   - all tensors are caller-owned device memory (PyTorch storage), bound once with dex_bind
+ *     as raw pointers + row stride (in elements); the library never allocates per-env state.
+ *   - launches are asynchronous on the caller's CUDA stream (`stream` = cudaStream_t, 0 for
+ *     the legacy default stream); there is no hidden synchronisation.
+ *   - per-env physics failures never raise: they set bits in the bound STATUS tensor
+ *     (mirrors dm_control's PhysicsError → episode termination).
+ *   - there is NO CPU execution path: without a CUDA device every call fails with DEX_E_CUDA.
+ */
+#ifndef DEXTERITY_B200_H_
+#define DEXTERITY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct DexModel DexModel;
+typedef struct DexBatch DexBatch;
+
+enum DexError {
+  DEX_OK = 0,
+  DEX_E_ARG = -1,       /* bad argument / API misuse */
+  DEX_E_MODEL = -2,     /* model blob rejected (unsupported feature, capacity exceeded) */
+  DEX_E_CUDA = -3,      /* CUDA runtime error */
+  DEX_E_UNBOUND = -4    /* a tensor required by the call has not been bound */
+};
+
+enum DexDtype { DEX_F32 = 0, DEX_F64 = 1 }; /* F64 = validation build of the same kernels */
+
+/* Bindable tensors.  Shapes are [num_envs][width] row-major with the given row stride. */
+enum DexFieldId {
+  DEX_FIELD_QPOS = 0,          /* real [nenv][nq]   physics.bind(joints).qpos, data.qpos           */
+  DEX_FIELD_QVEL = 1,          /* real [nenv][nv]   data.qvel                                       */
+  DEX_FIELD_CTRL = 2,          /* real [nenv][nu]   physics.bind(actuators).ctrl (mujoco_actuation.py:33) */
+  DEX_FIELD_QACC_WARMSTART = 3,/* real [nenv][nv]   data.qacc_warmstart                             */
+  DEX_FIELD_TIME = 4,          /* real [nenv]       physics.data.time (task.py:149,161,184)         */
+  DEX_FIELD_STATUS = 5,        /* u32  [nenv]       DEX_STATUS_* bits                               */
+  DEX_FIELD_CONTACT = 6,       /* real [nenv][DEX_MAXCON][8] dist,pos3,normal3,pair  (data.contact) */
+  DEX_FIELD_NCON = 7,          /* i32  [nenv]       data.ncon                                       */
+  DEX_FIELD_NITER = 8,         /* i32  [nenv]       solver iterations of the last step              */
+  DEX_FIELD_DBG_M = 9,         /* real [nenv][nv*nv]      optional: data.qM (dense)                 */
+  DEX_FIELD_DBG_QFRC_SMOOTH = 10, /* real [nenv][nv]      optional                                  */
+  DEX_FIELD_DBG_QACC = 11,     /* real [nenv][nv]         optional: data.qacc                       */
+  DEX_FIELD_DBG_QFRC_CONSTRAINT = 12, /* real [nenv][nv]  optional                                  */
+  DEX_FIELD_DBG_EFC = 13,      /* real [nenv][DEX_MAXCON][8] optional: per-contact D, aref[4], mu, imp, R */
+  DEX_FIELD_COUNT = 32
+};
+
+/* Compiled-capacity constants (also exported through dex_capacity for ctypes users). */
+enum DexCapacity { DEX_CAP_MAXCON = 0, DEX_CAP_CON_STRIDE = 1, DEX_CAP_MAXDOF = 2, DEX_CAP_MAXBODY = 3 };
+int dex_capacity(int which);
+
+/* Model: replaces mj_loadXML/mj_compile reached through composer.Environment.__init__
+ * (reference dexterity/manipulation/__init__.py:81).  `blob` is the host blob of
+ * include/dex_model_blob.h; it is copied to `device`. */
+int dex_model_create(const void* blob, uint64_t nbytes, int device, DexModel** out);
+void dex_model_destroy(DexModel* model);
+
+/* Batch of independent environments (the leading env dimension; replaces MjData). */
+int dex_batch_create(DexModel* model, int num_envs, int dtype, DexBatch** out);
+void dex_batch_destroy(DexBatch* batch);
+int dex_bind(DexBatch* batch, int field, void* dev_ptr, int64_t row_stride);
+
+/* nsub x mj_step on every env: replaces the `n_sub_steps x physics.step()` loop inside
+ * composer.Environment.step (reached from dexterity/environment.py:25-29) and
+ * physics.step() in goals/fingertip_position.py:97. */
+int dex_mj_step(DexBatch* batch, int nsub, void* stream);
+
+/* mj_forward without integration: refreshes contacts (+ optional DBG tensors).  Replaces
+ * physics.forward() (goals/fingertip_position.py:89,110; models/hands/dexterous_hand.py:165)
+ * and the trailing mj_step1 of dm_control's legacy step that post-step hooks read
+ * (utils/mujoco_collisions.py:106 iterates data.contact). */
+int dex_mj_forward(DexBatch* batch, void* stream);
+
+/* Collision only (position stage): contacts + ncon. */
+int dex_mj_collide(DexBatch* batch, void* stream);
+
+/* Number of this library's kernels launched since batch creation (bench `gpu_launches`). */
+int64_t dex_launch_count(const DexBatch* batch);
+
+const char* dex_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEXTERITY_B200_H_ */

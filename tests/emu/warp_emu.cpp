@@ -1,0 +1,172 @@
+// warp_emu.cpp — TEST INFRASTRUCTURE ONLY.
+// A cooperative-fiber emulator of one CUDA warp so that the kernel bodies in
+// dexterity_b200/csrc/*.cuh can be executed (slowly) on a host without a GPU, for debugging
+// and for the CPU-only part of the test-suite.  It is NOT a fallback: the product library
+// libdexb200.so is compiled by nvcc only, and nothing in the dexterity_b200 package loads
+// this file.  32 ucontext fibers stand for the 32 lanes; every warp-synchronous primitive
+// (shuffle, ballot, __syncwarp) is a fiber barrier.
+#define DEX_WARP_EMU 1
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#include "../../dexterity_b200/csrc/dex_collide.cuh"
+#include "../../dexterity_b200/csrc/dex_dynamics.cuh"
+#include "../../dexterity_b200/csrc/dex_host_model.h"
+
+namespace dex_emu {
+struct Warp {
+  ucontext_t main_ctx, ctx[32];
+  std::vector<char> stacks;
+  int cur = 0;
+  bool done[32];
+  uint64_t xchg[32];
+  bool pred[32];
+  std::function<void()> fn;
+};
+static thread_local Warp* W = nullptr;
+static const size_t kStack = 512 * 1024;
+
+int lane() { return W->cur; }
+void barrier() {
+  int me = W->cur;
+  swapcontext(&W->ctx[me], &W->main_ctx);
+}
+uint64_t exchange(uint64_t v, int src) {
+  W->xchg[W->cur] = v;
+  barrier();
+  uint64_t r = W->xchg[src];
+  barrier();
+  return r;
+}
+unsigned ballot(bool p) {
+  W->pred[W->cur] = p;
+  barrier();
+  unsigned r = 0;
+  for (int l = 0; l < 32; ++l) if (!W->done[l] && W->pred[l]) r |= 1u << l;
+  barrier();
+  return r;
+}
+static void trampoline() {
+  Warp* w = W;
+  int me = w->cur;
+  w->fn();
+  w->done[me] = true;
+  w->pred[me] = false;
+  swapcontext(&w->ctx[me], &w->main_ctx);
+}
+void run_warp(const std::function<void()>& fn) {
+  Warp* w = new Warp;
+  W = w;
+  w->fn = fn;
+  w->stacks.resize(32 * kStack);
+  for (int l = 0; l < 32; ++l) {
+    w->done[l] = false; w->pred[l] = false; w->xchg[l] = 0;
+    getcontext(&w->ctx[l]);
+    w->ctx[l].uc_stack.ss_sp = w->stacks.data() + l * kStack;
+    w->ctx[l].uc_stack.ss_size = kStack;
+    w->ctx[l].uc_link = &w->main_ctx;
+    makecontext(&w->ctx[l], trampoline, 0);
+  }
+  for (;;) {
+    bool any = false;
+    for (int l = 0; l < 32; ++l) {
+      if (w->done[l]) continue;
+      any = true;
+      w->cur = l;
+      swapcontext(&w->main_ctx, &w->ctx[l]);
+    }
+    if (!any) break;
+  }
+  W = nullptr;
+  delete w;
+}
+}  // namespace dex_emu
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct EmuModelT {
+  DevModel<T> dev;
+#define DEX_X_I(name) std::vector<int> v_##name;
+#define DEX_X_R(name) std::vector<T> v_##name;
+#define DEX_X(t, name) DEX_X_##t(name)
+  DEX_DEVMODEL_ARRAYS(DEX_X)
+#undef DEX_X
+#undef DEX_X_I
+#undef DEX_X_R
+  void init(const HostModel& h) {
+    dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
+    dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
+    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations;
+    dev.timestep = (T)h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
+    dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia;
+#define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
+#define DEX_X_R(name) v_##name.assign(h.name.begin(), h.name.end()); dev.name = v_##name.data();
+#define DEX_X(t, name) DEX_X_##t(name)
+    DEX_DEVMODEL_ARRAYS(DEX_X)
+#undef DEX_X
+#undef DEX_X_I
+#undef DEX_X_R
+  }
+};
+struct EmuModel {
+  HostModel host;
+  EmuModelT<float> f;
+  EmuModelT<double> d;
+};
+
+template <typename T>
+static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int nsub, int integrate, int do_collide,
+                    int do_dynamics, int nthreads) {
+  auto work = [&](int lo, int hi) {
+    std::vector<T> smem(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T) + 64);
+    for (int env = lo; env < hi; ++env) {
+      for (int s = 0; s < nsub; ++s) {
+        if (do_collide) dex_emu::run_warp([&]() { dex_collide_env<T>(m, st, env, smem.data()); });
+        if (do_dynamics) dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem.data(), integrate); });
+      }
+    }
+  };
+  if (nthreads <= 1) { work(0, st.nenv); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work, st.nenv * t / nthreads, st.nenv * (t + 1) / nthreads);
+  for (auto& t : th) t.join();
+}
+
+extern "C" {
+void* emu_model_create(const void* blob, uint64_t nbytes, char* err, int errlen) {
+  EmuModel* m = new EmuModel;
+  std::string e = dex_host::build(blob, nbytes, m->host);
+  if (!e.empty()) { snprintf(err, errlen, "%s", e.c_str()); delete m; return nullptr; }
+  m->f.init(m->host);
+  m->d.init(m->host);
+  return m;
+}
+void emu_model_destroy(void* m) { delete (EmuModel*)m; }
+int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
+
+// dtype: 0 = float32, 1 = float64.  All arrays are host arrays of that dtype, row-major with the
+// given strides.  dbg_* may be null.
+int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, void* qvel, int qvel_stride, void* ctrl,
+                  int ctrl_stride, void* warm, int warm_stride, void* time, unsigned* status, void* contact, int* ncon,
+                  int* niter, int nsub, int integrate, int do_collide, int do_dynamics, void* dbg_M, void* dbg_fs,
+                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, int nthreads) {
+  EmuModel* m = (EmuModel*)mp;
+  if (dtype == 0) {
+    BatchState<float> st = {nenv, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
+                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter};
+    DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
+    emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
+  } else {
+    BatchState<double> st = {nenv, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
+                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter};
+    DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
+    emu_run<double>(m->d.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
+  }
+  return 0;
+}
+}

@@ -1,0 +1,84 @@
+"""Seeded state generation shared by the parity tests, smoke() and bench.py's cpu_baseline.
+
+States are produced by rolling the FP64 oracle from the task's reset distribution with uniform
+random controls (the recipe of reference manipulation_test.py:44-45), so they contain the
+contact configurations the task actually visits.  TEST INFRASTRUCTURE.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+from oracle import oracle as orc
+
+
+def reorient_reset(compiled, rng: np.random.RandomState) -> np.ndarray:
+    """qpos at episode start (reference reorient.py:72-78,143-151): hand at qpos0, cube placed
+    uniformly in the 5 cm box above the palm with a uniform random orientation."""
+    q = compiled.QPOS0.copy()
+    nq = compiled.nq
+    if nq >= 31:
+        q[nq - 7:nq - 4] = [rng.uniform(-0.025, 0.025), rng.uniform(-0.155, -0.105), 0.16]
+        quat = rng.randn(4)
+        q[nq - 4:] = quat / np.linalg.norm(quat)
+    return q
+
+
+def rollout_states(compiled, seed: int, nstates: int, every: int = 10, nsub: int = 1,
+                   episodes: int = 1) -> Dict[str, np.ndarray]:
+    """Rolls the oracle and snapshots (qpos, qvel, ctrl, qacc_warmstart) every `every` steps."""
+    rng = np.random.RandomState(seed)
+    om = orc.OracleModel(compiled)
+    d = orc.OracleData(om)
+    lo, hi = compiled.ACT_CTRLRANGE[:, 0], compiled.ACT_CTRLRANGE[:, 1]
+    out = dict(qpos=[], qvel=[], ctrl=[], warm=[])
+    per_ep = (nstates + episodes - 1) // episodes
+    for _ in range(episodes):
+        d.set_state(reorient_reset(compiled, rng), np.zeros(compiled.nv), np.zeros(compiled.nu), np.zeros(compiled.nv))
+        ctrl = rng.uniform(lo, hi)
+        for i in range(per_ep * every):
+            if i % 5 == 0:
+                ctrl = rng.uniform(lo, hi)
+                q, v, w, _ = d.get_state()
+                d.set_state(q, v, ctrl, w)
+            d.step()
+            if i % every == every - 1 and len(out["qpos"]) < nstates:
+                q, v, w, _ = d.get_state()
+                out["qpos"].append(q); out["qvel"].append(v); out["ctrl"].append(ctrl.copy()); out["warm"].append(w)
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def oracle_step(compiled, states: Dict[str, np.ndarray], nsub: int = 1, forward_only: bool = False):
+    """Oracle result for every state: next state, contacts (as sets), qacc."""
+    om = orc.OracleModel(compiled)
+    d = orc.OracleData(om)
+    n = len(states["qpos"])
+    res = dict(qpos=[], qvel=[], warm=[], ncon=[], pairs=[], dist=[], qacc=[], niter=[], normal=[], pos=[])
+    for e in range(n):
+        d.set_state(states["qpos"][e], states["qvel"][e], states["ctrl"][e], states["warm"][e])
+        d.forward()
+        c = d.contacts()
+        res["ncon"].append(len(c["dist"]))
+        res["pairs"].append([tuple(g) for g in c["geom"]])
+        res["dist"].append(c["dist"]); res["normal"].append(c["frame"][:, 0] if len(c["dist"]) else np.zeros((0, 3)))
+        res["pos"].append(c["pos"])
+        res["qacc"].append(d.get("qacc")); res["niter"].append(d.solver_niter)
+        if not forward_only:
+            d.set_state(states["qpos"][e], states["qvel"][e], states["ctrl"][e], states["warm"][e])
+            for _ in range(nsub):
+                d.step()
+        q, v, w, _ = d.get_state()
+        res["qpos"].append(q); res["qvel"].append(v); res["warm"].append(w)
+    for k in ("qpos", "qvel", "warm", "qacc"):
+        res[k] = np.array(res[k])
+    res["ncon"] = np.array(res["ncon"])
+    return res
+
+
+def upload(batch, states: Dict[str, np.ndarray]) -> None:
+    import torch
+    t = lambda a: torch.as_tensor(a, dtype=batch.dtype, device=batch.device)
+    batch.qpos.copy_(t(states["qpos"])); batch.qvel.copy_(t(states["qvel"]))
+    batch.ctrl.copy_(t(states["ctrl"])); batch.qacc_warmstart.copy_(t(states["warm"]))
+    batch.time.zero_(); batch.status.zero_()
