@@ -12,6 +12,7 @@
 #include "dex_collide.cuh"
 #include "dex_dynamics.cuh"
 #include "dex_host_model.h"
+#include "dex_task.cuh"
 
 namespace {
 
@@ -44,6 +45,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_dynamics(DevModel<T> m,
   if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_task_pre(DevModel<T> m, BatchState<T> st, TaskState<T> ts,
+                                                                   DexTaskParams p, int force_reset) {
+  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (env >= st.nenv) return;
+  dex_task_pre_env<T>(m, st, ts, p, env, force_reset);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_task_post(DevModel<T> m, BatchState<T> st, TaskState<T> ts,
+                                                                    DexTaskParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * kWarpsPerBlock + warp;
+  if (env >= st.nenv) return;
+  T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K3_SMEM_T;
+  dex_task_post_env<T>(m, st, ts, p, env, smem);
 }
 
 template <typename T>
@@ -107,12 +127,31 @@ struct DexBatch {
   int64_t stride[DEX_FIELD_COUNT];
   int64_t launches = 0;
   bool attrs_set = false;
+  DexTaskParams task;
+  bool task_set = false;
+  // optional per-kernel-class timing (cudaEvent pairs recorded on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev[4];   // class: 0 pre, 1 collide, 2 dynamics, 3 post; pairs (start, stop)
+  double ms[4] = {0, 0, 0, 0};
+  int64_t count[4] = {0, 0, 0, 0};
 };
 
 namespace {
 
+struct ProfScope {  // records an event pair around one launch when profiling is on
+  DexBatch* b; int cls; cudaStream_t s;
+  ProfScope(DexBatch* b_, int cls_, cudaStream_t s_) : b(b_), cls(cls_), s(s_) {
+    if (!b->profiling) return;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    b->ev[cls].push_back(e0); b->ev[cls].push_back(e1);
+    cudaEventRecord(e0, s);
+  }
+  ~ProfScope() { if (b->profiling) cudaEventRecord(b->ev[cls].back(), s); }
+};
+
 template <typename T>
-int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn) {
+int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, bool use_skip = false) {
   static const int req_col[] = {DEX_FIELD_QPOS, DEX_FIELD_STATUS, DEX_FIELD_CONTACT, DEX_FIELD_NCON};
   static const int req_dyn[] = {DEX_FIELD_QVEL, DEX_FIELD_CTRL, DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER};
   for (int f : req_col) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
@@ -127,6 +166,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn) 
   st.contact = (T*)b->ptr[DEX_FIELD_CONTACT];
   st.ncon = (int*)b->ptr[DEX_FIELD_NCON];
   st.niter = (int*)b->ptr[DEX_FIELD_NITER];
+  st.skip = use_skip ? (const unsigned char*)b->ptr[DEX_FIELD_SKIP] : nullptr;
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
   dbg.qacc = (T*)b->ptr[DEX_FIELD_DBG_QACC];
@@ -151,11 +191,59 @@ int run(DexBatch* b, const DevModel<T>& m, int nsub, bool collide, bool dynamics
   }
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
   for (int i = 0; i < nsub; ++i) {
-    if (collide) { k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, s>>>(m, st); b->launches++; }
-    if (dynamics) { k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, s>>>(m, st, dbg, integrate); b->launches++; }
+    if (collide) { ProfScope ps(b, 1, s); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, s>>>(m, st); b->launches++; }
+    if (dynamics) { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, s>>>(m, st, dbg, integrate); b->launches++; }
   }
   DEX_CUDA(cudaGetLastError());
   return DEX_OK;
+}
+
+template <typename T>
+int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaStream_t s) {
+  if (!b->task_set) return fail(DEX_E_ARG, "dex_task_configure has not been called");
+  static const int req[] = {DEX_FIELD_OBS, DEX_FIELD_REWARD, DEX_FIELD_DISCOUNT, DEX_FIELD_GOAL, DEX_FIELD_TASK_I,
+                            DEX_FIELD_TASK_F, DEX_FIELD_RNG, DEX_FIELD_ACTION, DEX_FIELD_SKIP};
+  for (int f : req) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required task tensor not bound: field " + std::to_string(f));
+  BatchState<T> st;
+  DynDebug<T> dbg;
+  int rc = make_state<T>(b, st, dbg, true, true);
+  if (rc) return rc;
+  TaskState<T> ts;
+  ts.action = (const T*)b->ptr[DEX_FIELD_ACTION]; ts.action_stride = (int)b->stride[DEX_FIELD_ACTION];
+  ts.obs = (T*)b->ptr[DEX_FIELD_OBS]; ts.reward = (T*)b->ptr[DEX_FIELD_REWARD]; ts.discount = (T*)b->ptr[DEX_FIELD_DISCOUNT];
+  ts.goal = (T*)b->ptr[DEX_FIELD_GOAL]; ts.task_i = (int*)b->ptr[DEX_FIELD_TASK_I]; ts.task_f = (T*)b->ptr[DEX_FIELD_TASK_F];
+  ts.rng = (unsigned*)b->ptr[DEX_FIELD_RNG]; ts.skip = (unsigned char*)b->ptr[DEX_FIELD_SKIP];
+  ts.reset_mask = (const unsigned char*)b->ptr[DEX_FIELD_RESET_MASK];
+  ts.stats = (double*)b->ptr[DEX_FIELD_EPISODE_STATS];
+  DEX_CUDA(cudaSetDevice(b->model->device));
+  const size_t smem1 = (size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T);
+  const size_t smem2 = (size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T);
+  const size_t smem3 = (size_t)kWarpsPerBlock * DEX_K3_SMEM_T * sizeof(T);
+  if (!b->attrs_set) {
+    DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    b->attrs_set = true;
+  }
+  const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int block = kWarpsPerBlock * 32;
+  { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
+  if (!force_reset) {
+    for (int i = 0; i < nsub; ++i) {
+      { ProfScope ps(b, 1, s); k_collide<T><<<grid, block, smem1, s>>>(m, st); b->launches++; }
+      { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, block, smem2, s>>>(m, st, dbg, 1); b->launches++; }
+    }
+  }
+  { ProfScope ps(b, 3, s); k_task_post<T><<<grid, block, smem3, s>>>(m, st, ts, b->task); b->launches++; }
+  DEX_CUDA(cudaGetLastError());
+  return DEX_OK;
+}
+
+int dispatch_env(DexBatch* b, int nsub, int force_reset, void* stream) {
+  if (!b) return fail(DEX_E_ARG, "null batch");
+  if (nsub < 1) return fail(DEX_E_ARG, "nsub must be >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (b->dtype == DEX_F32) return run_env<float>(b, b->model->f32.dev, nsub, force_reset, s);
+  return run_env<double>(b, b->model->f64.dev, nsub, force_reset, s);
 }
 
 int dispatch(DexBatch* b, int nsub, bool collide, bool dynamics, int integrate, void* stream) {
@@ -235,5 +323,46 @@ int dex_mj_step(DexBatch* b, int nsub, void* stream) { return dispatch(b, nsub, 
 int dex_mj_forward(DexBatch* b, void* stream) { return dispatch(b, 1, true, true, 0, stream); }
 int dex_mj_collide(DexBatch* b, void* stream) { return dispatch(b, 1, true, false, 0, stream); }
 int64_t dex_launch_count(const DexBatch* b) { return b ? b->launches : 0; }
+
+int dex_task_configure(DexBatch* b, const DexTaskParams* p) {
+  if (!b || !p) return fail(DEX_E_ARG, "null argument");
+  const HostModel& h = b->model->host;
+  if (p->task != DEX_TASK_REORIENT && p->task != DEX_TASK_REACH) return fail(DEX_E_ARG, "unknown task");
+  if (p->nsite < 0 || p->nsite > 5 || p->nhand < 0 || p->nhand > h.nv) return fail(DEX_E_ARG, "bad nsite/nhand");
+  for (int s = 0; s < p->nsite; ++s) if (p->site_id[s] < 0 || p->site_id[s] >= h.nsite) return fail(DEX_E_ARG, "bad site id");
+  if (p->task == DEX_TASK_REORIENT) {
+    if (p->prop_body <= 0 || p->prop_body >= h.nbody || p->prop_geom < 0 || p->prop_geom >= h.ngeom ||
+        p->ground_geom < 0 || p->ground_geom >= h.ngeom) return fail(DEX_E_ARG, "bad prop/ground ids");
+    if (3 * p->nhand + 6 * p->nsite + 21 > DEX_OBS_STRIDE) return fail(DEX_E_ARG, "observation does not fit");
+  }
+  b->task = *p;
+  b->task_set = true;
+  return DEX_OK;
+}
+int dex_set_profiling(DexBatch* b, int on) {
+  if (!b) return fail(DEX_E_ARG, "null batch");
+  b->profiling = on != 0;
+  return DEX_OK;
+}
+// Synchronises the device, folds the recorded event pairs into per-class totals and returns
+// ms[4] (total milliseconds) and count[4] (launches) for pre / collide / dynamics / post.
+int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
+  if (!b || !ms || !count) return fail(DEX_E_ARG, "null argument");
+  DEX_CUDA(cudaSetDevice(b->model->device));
+  DEX_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < 4; ++c) {
+    for (size_t i = 0; i + 1 < b->ev[c].size(); i += 2) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, b->ev[c][i], b->ev[c][i + 1]) == cudaSuccess) { b->ms[c] += t; b->count[c]++; }
+      cudaEventDestroy(b->ev[c][i]); cudaEventDestroy(b->ev[c][i + 1]);
+    }
+    b->ev[c].clear();
+    ms[c] = b->ms[c]; count[c] = b->count[c];
+    if (reset) { b->ms[c] = 0; b->count[c] = 0; }
+  }
+  return DEX_OK;
+}
+int dex_env_reset(DexBatch* b, void* stream) { return dispatch_env(b, 1, 1, stream); }
+int dex_env_step(DexBatch* b, int nsub, void* stream) { return dispatch_env(b, nsub, 0, stream); }
 
 }  // extern "C"

@@ -271,6 +271,7 @@ DEX_DEV void dex_store_contact(T* dst, T dist, const T* pos, const T* normal, in
 
 template <typename T>
 DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
+  if (st.skip && st.skip[env]) return;  // warp-uniform
   const int lane = dex_lane();
   T* xpos = smem;
   T* xquat = xpos + DEX_MAXBODY * 3;

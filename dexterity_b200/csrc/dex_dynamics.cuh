@@ -154,6 +154,7 @@ DEX_DEV void dex_contact_dots(const T* Jc, const T* x, int nrows, int nv, T* out
 template <typename T>
 DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int env,
                               T* smem, int integrate) {
+  if (st.skip && st.skip[env]) return;  // warp-uniform
   const int lane = dex_lane();
   const int nv = m.nv, nb = m.nbody;
   T* xpos = smem + DEX_K2_OFF_XPOS;
@@ -200,31 +201,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   dex_syncwarp();
 
   // ------------------------------------------------------------------ cdof (lane = dof), cinert (lane = body)
-  T cd[6] = {0, 0, 0, 0, 0, 0};
-  int dbody = 0, dpar = -1;
-  if (isdof) {
-    const int j = dex_ldg(m.dof_jnt + lane);
-    dbody = dex_ldg(m.dof_body + lane);
-    dpar = dex_ldg(m.dof_parent + lane);
-    const T* rp = ref + 3 * dex_ldg(m.dof_tree + lane);
-    if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
-      const int k = lane - dex_ldg(m.jnt_dofadr + j);
-      if (k < 3) cd[3 + k] = 1;
-      else {
-        const T* R = xmat + 9 * dbody;
-        T ax[3] = {R[k - 3], R[3 + k - 3], R[6 + k - 3]};
-        T off[3] = {rp[0] - xpos[3 * dbody], rp[1] - xpos[3 * dbody + 1], rp[2] - xpos[3 * dbody + 2]};
-        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
-        cross3(cd + 3, ax, off);
-      }
-    } else {
-      T ax[3] = {xaxis[3 * j], xaxis[3 * j + 1], xaxis[3 * j + 2]};
-      T off[3] = {rp[0] - xanchor[3 * j], rp[1] - xanchor[3 * j + 1], rp[2] - xanchor[3 * j + 2]};
-      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
-      cross3(cd + 3, ax, off);
-    }
-    for (int k = 0; k < 6; ++k) cdof[6 * lane + k] = cd[k];
-  }
+  T cd[6];
+  dex_cdof_lane(m, lane, xpos, xmat, xanchor, xaxis, ref, cd);
+  const int dbody = isdof ? dex_ldg(m.dof_body + lane) : 0;
+  if (isdof) for (int k = 0; k < 6; ++k) cdof[6 * lane + k] = cd[k];
   for (int b = lane; b < nb; b += 32) {
     T c[10];
     const T mass = dex_ldg(m.body_mass + b);

@@ -76,4 +76,32 @@ DEX_DEV void dex_fk(const DevModel<T>& m, const T* qpos, const KinBuf<T>& k) {
   }
 }
 
+// cdof of dof `lane` (mj_comPos): [angular(3); linear(3)] about the reference point of its tree.
+// hinge: [axis; axis x (ref - anchor)];  free: 3 world translations then 3 body-frame rotations.
+template <typename T>
+DEX_DEV void dex_cdof_lane(const DevModel<T>& m, int lane, const T* xpos, const T* xmat, const T* xanchor,
+                           const T* xaxis, const T* ref, T* cd) {
+  for (int k = 0; k < 6; ++k) cd[k] = 0;
+  if (lane >= m.nv) return;
+  const int j = dex_ldg(m.dof_jnt + lane);
+  const int b = dex_ldg(m.dof_body + lane);
+  const T* rp = ref + 3 * dex_ldg(m.dof_tree + lane);
+  if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+    const int k = lane - dex_ldg(m.jnt_dofadr + j);
+    if (k < 3) cd[3 + k] = 1;
+    else {
+      const T* R = xmat + 9 * b;
+      T ax[3] = {R[k - 3], R[3 + k - 3], R[6 + k - 3]};
+      T off[3] = {rp[0] - xpos[3 * b], rp[1] - xpos[3 * b + 1], rp[2] - xpos[3 * b + 2]};
+      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+      cross3(cd + 3, ax, off);
+    }
+  } else {
+    T ax[3] = {xaxis[3 * j], xaxis[3 * j + 1], xaxis[3 * j + 2]};
+    T off[3] = {rp[0] - xanchor[3 * j], rp[1] - xanchor[3 * j + 1], rp[2] - xanchor[3 * j + 2]};
+    cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+    cross3(cd + 3, ax, off);
+  }
+}
+
 #endif  // DEX_KIN_CUH_

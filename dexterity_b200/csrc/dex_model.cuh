@@ -78,6 +78,7 @@ struct BatchState {
   T* contact;                     // [nenv][DEX_MAXCON][DEX_CON_STRIDE]
   int* ncon;                      // [nenv]
   int* niter;                     // [nenv] solver iterations of the last mj_step
+  const unsigned char* skip;      // optional [nenv]: 1 = leave this env untouched (it was just reset)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,271 @@
+"""Batched, composer-compatible environments (leading env dimension on every array).
+
+Mirrors the reference's public surface for the hot path:
+  * `load(domain_name, task_name, seed, ..., num_envs=...)`   ← dexterity/manipulation/__init__.py:56-86
+  * `GoalEnvironment.reset() / step(action)`                  ← dexterity/environment.py:14-34
+  * `action_spec()` (bounds = ctrlrange where ctrllimited)    ← effectors/mujoco_actuation.py:48-67
+  * `observation_spec()` / observation dict keys              ← composer observables enabled by
+    shared/observations.py:96-103, reorient.py:81-86, task.py:206-216
+
+dm_env semantics are kept per env: the TimeStep after a terminal step has step_type LAST; the
+next `step` call ignores that env's action and returns the FIRST TimeStep of a new episode.
+"""
+from __future__ import annotations
+
+import collections
+import ctypes
+import dataclasses
+import math
+from typing import Dict, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from dexterity_b200 import backend
+from dexterity_b200.model import scenes
+
+FIRST, MID, LAST = 0, 1, 2
+OBS_STRIDE, GOAL_STRIDE = 128, 16
+
+# reference manipulation/tasks/reorient.py:41-78
+REORIENT = dict(
+    success_threshold=0.1, successes_needed=1, steps_before_changing_goal=5,
+    max_time_per_goal=300 * 0.025, control_timestep=0.025, physics_timestep=0.005,
+    spawn_lo=(-0.025, -0.13 - 0.025, 0.16), spawn_hi=(0.025, -0.13 + 0.025, 0.16),
+    w_orientation=1.0, w_success_bonus=800.0, w_action_smoothing=-0.1, orientation_eps=0.1, bonus_threshold=0.1)
+# reference manipulation/tasks/reach.py:47-66
+REACH = dict(
+    success_threshold=0.01, successes_needed=50, steps_before_changing_goal=5,
+    max_time_per_goal=150 * 0.02, control_timestep=0.02, physics_timestep=0.02)
+
+
+class TaskParams(ctypes.Structure):
+    """struct DexTaskParams (include/dexterity_b200.h)."""
+    _fields_ = [
+        ("task", ctypes.c_int), ("successes_needed", ctypes.c_int), ("steps_before_changing_goal", ctypes.c_int),
+        ("fall_termination", ctypes.c_int), ("has_max_time", ctypes.c_int),
+        ("prop_body", ctypes.c_int), ("prop_qposadr", ctypes.c_int), ("prop_dofadr", ctypes.c_int),
+        ("prop_geom", ctypes.c_int), ("ground_geom", ctypes.c_int),
+        ("nhand", ctypes.c_int), ("nsite", ctypes.c_int), ("site_id", ctypes.c_int * 5),
+        ("dense_reward", ctypes.c_int), ("pad0", ctypes.c_int),
+        ("success_threshold", ctypes.c_double), ("max_time_per_goal", ctypes.c_double), ("time_limit", ctypes.c_double),
+        ("spawn_lo", ctypes.c_double * 3), ("spawn_hi", ctypes.c_double * 3),
+        ("w_orientation", ctypes.c_double), ("w_success_bonus", ctypes.c_double), ("w_action_smoothing", ctypes.c_double),
+        ("orientation_eps", ctypes.c_double), ("bonus_threshold", ctypes.c_double),
+        ("seed", ctypes.c_ulonglong),
+    ]
+
+
+@dataclasses.dataclass(frozen=True)
+class BoundedArraySpec:
+    """Stand-in for dm_env.specs.BoundedArray (dm_env is not a dependency of this build)."""
+    shape: tuple
+    dtype: np.dtype
+    minimum: np.ndarray
+    maximum: np.ndarray
+    name: str
+
+
+@dataclasses.dataclass(frozen=True)
+class ArraySpec:
+    shape: tuple
+    dtype: np.dtype
+    name: str
+
+
+class TimeStep(NamedTuple):
+    step_type: torch.Tensor   # int32 [num_envs]: 0 FIRST, 1 MID, 2 LAST
+    reward: torch.Tensor      # [num_envs] (0 where step_type == FIRST; dm_env uses None)
+    discount: torch.Tensor    # [num_envs] (1 where step_type == FIRST)
+    observation: Dict[str, torch.Tensor]
+
+    def first(self): return self.step_type == FIRST
+    def mid(self): return self.step_type == MID
+    def last(self): return self.step_type == LAST
+
+
+def _reorient_layout(prefix: str, nhand: int, nsite: int) -> "collections.OrderedDict[str, slice]":
+    o = collections.OrderedDict()
+    o[f"{prefix}/joint_positions_sin_cos"] = slice(0, 2 * nhand)
+    o[f"{prefix}/joint_velocities"] = slice(2 * nhand, 3 * nhand)
+    a = 3 * nhand
+    o[f"{prefix}/fingertip_positions"] = slice(a, a + 3 * nsite)
+    o[f"{prefix}/fingertip_linear_velocities"] = slice(a + 3 * nsite, a + 6 * nsite)
+    return o
+
+
+class BatchedGoalEnvironment:
+    """`num_envs` independent copies of a GoalTask environment on one GPU."""
+
+    def __init__(self, task_name: str, num_envs: int, seed: Optional[int] = None, device: int = 0,
+                 dtype: torch.dtype = torch.float32, time_limit: Optional[float] = None,
+                 fall_termination: bool = True, dense_reward: bool = True) -> None:
+        if task_name not in ("reorient", "reach"):
+            raise ValueError(f"Unknown task: {task_name}")
+        self.task_name = task_name
+        self.compiled = scenes.load_compiled("reorient_shadow" if task_name == "reorient" else "reach_shadow")
+        c = self.compiled
+        self.model = backend.PhysicsModel(c, device)
+        self.physics = backend.PhysicsBatch(self.model, num_envs, dtype)
+        self.num_envs, self.dtype, self.device = num_envs, dtype, self.physics.device
+        cfg = REORIENT if task_name == "reorient" else REACH
+        self.control_timestep, self.physics_timestep = cfg["control_timestep"], cfg["physics_timestep"]
+        self.n_sub_steps = int(round(self.control_timestep / self.physics_timestep))
+        seed = int(seed if seed is not None else np.random.randint(0, 2 ** 31 - 1))
+        self.seed = seed
+
+        n, dev = num_envs, self.device
+        z = lambda *s, dt=dtype: torch.zeros(*s, dtype=dt, device=dev)
+        self._obs = z(n, OBS_STRIDE)
+        self._reward, self._discount = z(n), z(n)
+        self._goal = z(n, GOAL_STRIDE)
+        self._task_i = z(n, 8, dt=torch.int32)
+        self._task_f = z(n, 8)
+        self._rng = z(n, 4, dt=torch.int32)
+        self._rng[:, 0] = seed & 0x7FFFFFFF
+        self._rng[:, 1] = (seed >> 31) & 0x7FFFFFFF
+        self._action = z(n, backend.PhysicsBatch.ROW)
+        self._skip = z(n, dt=torch.uint8)
+        self._reset_mask = z(n, dt=torch.uint8)
+        self.episode_stats = z(8, dt=torch.float64)
+        for name, t in (("OBS", self._obs), ("REWARD", self._reward), ("DISCOUNT", self._discount), ("GOAL", self._goal),
+                        ("TASK_I", self._task_i), ("TASK_F", self._task_f), ("RNG", self._rng), ("ACTION", self._action),
+                        ("EPISODE_STATS", self.episode_stats), ("RESET_MASK", self._reset_mask)):
+            self.physics.bind(name, t)
+        backend._check(backend.lib().dex_bind(self.physics.ptr, 26, ctypes.c_void_p(self._skip.data_ptr()), 1))
+
+        # task description
+        hand_prefix = "shadow_hand_e"
+        sites = [c.site_names.index(f"{hand_prefix}/{t}_site") for t in scenes.SHADOW_FINGERTIPS]
+        nhand = sum(1 for j in c.joint_names if j.startswith(hand_prefix + "/"))
+        p = TaskParams()
+        p.task = 0 if task_name == "reorient" else 1
+        p.successes_needed = cfg["successes_needed"]
+        p.steps_before_changing_goal = cfg["steps_before_changing_goal"]
+        p.fall_termination = int(fall_termination)
+        p.has_max_time = 1
+        p.nhand, p.nsite = nhand, len(sites)
+        for i, s in enumerate(sites):
+            p.site_id[i] = s
+        p.dense_reward = int(dense_reward)
+        p.success_threshold = cfg["success_threshold"]
+        p.max_time_per_goal = cfg["max_time_per_goal"]
+        p.time_limit = float(time_limit) if time_limit else math.inf
+        p.seed = seed
+        layout = _reorient_layout(hand_prefix, nhand, len(sites))
+        o = 3 * nhand + 6 * len(sites)
+        if task_name == "reorient":
+            pb = c.body_names.index("prop/")
+            j = c.joint_names.index("prop/")
+            p.prop_body, p.prop_qposadr, p.prop_dofadr = pb, int(c.JNT_QPOSADR[j]), int(c.JNT_DOFADR[j])
+            p.prop_geom, p.ground_geom = c.geom_names.index("prop/geom"), c.geom_names.index("ground")
+            for k in range(3):
+                p.spawn_lo[k], p.spawn_hi[k] = cfg["spawn_lo"][k], cfg["spawn_hi"][k]
+            for k in ("w_orientation", "w_success_bonus", "w_action_smoothing", "orientation_eps", "bonus_threshold"):
+                setattr(p, k, cfg[k])
+            layout["prop/position"] = slice(o, o + 3)
+            layout["prop/orientation"] = slice(o + 3, o + 7)
+            layout["prop/linear_velocity"] = slice(o + 7, o + 10)
+            layout["prop/angular_velocity"] = slice(o + 10, o + 13)
+            layout["target_prop/orientation"] = slice(o + 13, o + 17)
+            layout["goal_state"] = slice(o + 17, o + 21)
+            self.obs_dim = o + 21
+        else:
+            layout["goal_state"] = slice(o, o + 3 * len(sites))
+            self.obs_dim = o + 3 * len(sites)
+        self._params = p
+        self.obs_layout = layout
+        lib = backend.lib()
+        lib.dex_task_configure.argtypes = [ctypes.c_void_p, ctypes.POINTER(TaskParams)]
+        lib.dex_env_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.dex_env_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        backend._check(lib.dex_task_configure(self.physics.ptr, ctypes.byref(p)))
+
+        is_lim = c.ACT_CTRLLIMITED.astype(bool)
+        lo = np.full(c.nu, -np.inf, np.float32)
+        hi = np.full(c.nu, np.inf, np.float32)
+        lo[is_lim], hi[is_lim] = c.ACT_CTRLRANGE[is_lim, 0], c.ACT_CTRLRANGE[is_lim, 1]
+        self._action_spec = BoundedArraySpec((c.nu,), np.dtype(np.float32), lo, hi,
+                                             "\t".join(f"{hand_prefix}_joint{i}" for i in range(c.nu)))
+
+    # ------------------------------------------------------------------ specs
+    def action_spec(self) -> BoundedArraySpec:
+        return self._action_spec
+
+    def observation_spec(self) -> "collections.OrderedDict[str, ArraySpec]":
+        return collections.OrderedDict(
+            (k, ArraySpec((s.stop - s.start,), np.dtype(np.float64), k)) for k, s in self.obs_layout.items())
+
+    def reward_spec(self) -> ArraySpec:
+        return ArraySpec((), np.dtype(np.float64), "reward")
+
+    def discount_spec(self) -> BoundedArraySpec:
+        return BoundedArraySpec((), np.dtype(np.float64), np.array(0.0), np.array(1.0), "discount")
+
+    # ------------------------------------------------------------------ dm_env API (batched)
+    def _timestep(self) -> TimeStep:
+        obs = collections.OrderedDict((k, self._obs[:, s]) for k, s in self.obs_layout.items())
+        return TimeStep(self._task_i[:, 6], self._reward, self._discount, obs)
+
+    def reset(self) -> TimeStep:
+        backend._check(backend.lib().dex_env_reset(self.physics.ptr, backend.PhysicsBatch._stream()))
+        return self._timestep()
+
+    def step(self, action: torch.Tensor) -> TimeStep:
+        """`action`: [num_envs, nu] tensor on this env's device (float32 or the batch dtype)."""
+        self._action[:, :action.shape[1]].copy_(action)
+        return self.step_bound()
+
+    def step_bound(self) -> TimeStep:
+        """Steps with whatever is already stored in `self.action_buffer` (zero-copy path)."""
+        backend._check(backend.lib().dex_env_step(self.physics.ptr, self.n_sub_steps, backend.PhysicsBatch._stream()))
+        return self._timestep()
+
+    @property
+    def action_buffer(self) -> torch.Tensor:
+        return self._action[:, :self.compiled.nu]
+
+    @property
+    def observation_buffer(self) -> torch.Tensor:
+        return self._obs[:, :self.obs_dim]
+
+    @property
+    def goal(self) -> torch.Tensor:
+        return self._goal
+
+    @property
+    def goal_distance(self) -> torch.Tensor:
+        return self._task_f[:, 2:7]
+
+    @property
+    def successes(self) -> torch.Tensor:
+        return self._task_i[:, 0]
+
+    def request_reset(self, mask: torch.Tensor) -> None:
+        """Marks envs to be re-initialised at the next `step` (their action is ignored)."""
+        self._reset_mask.copy_(mask.to(torch.uint8))
+
+    def reduce_episode_stats(self) -> Dict[str, float]:
+        """Episode statistics summed over all ranks (the ONLY collective on this path: one
+        all-reduce of an 8-element float64 vector over NCCL / NVLink per logging interval)."""
+        stats = self.episode_stats.clone()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM)
+        s = stats.cpu().numpy()
+        n = max(s[2], 1.0)
+        return dict(episodes=s[2], mean_return=s[0] / n, mean_length=s[1] / n, successes=s[3], falls=s[4],
+                    timeouts=s[5], physics_errors=s[6])
+
+
+def load(domain_name: str, task_name: str = "state_dense", seed: Optional[int] = None,
+         strip_singleton_obs_buffer_dim: bool = True, time_limit: Optional[float] = None,
+         num_envs: int = 1, device: int = 0, dtype: torch.dtype = torch.float32) -> BatchedGoalEnvironment:
+    """Batched counterpart of reference `manipulation.load` (same leading arguments)."""
+    del strip_singleton_obs_buffer_dim
+    tasks = {"reorient": ("state_dense",), "reach": ("state_dense", "state_sparse")}
+    if domain_name not in tasks:
+        raise ValueError(f"Unknown domain: {domain_name}")
+    if task_name not in tasks[domain_name]:
+        raise ValueError(f"Unknown task: {task_name}")
+    return BatchedGoalEnvironment(domain_name, num_envs, seed, device, dtype, time_limit,
+                                  dense_reward=(task_name == "state_dense"))

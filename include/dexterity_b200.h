@@ -87,6 +87,66 @@ int dex_mj_collide(DexBatch* batch, void* stream);
 /* Number of this library's kernels launched since batch creation (bench `gpu_launches`). */
 int64_t dex_launch_count(const DexBatch* batch);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Task layer: the reference's composer hooks fused into pre-/post-step kernels.
+ * ------------------------------------------------------------------------------------------- */
+// Plain-data task description (mirrors the module-level constants of the reference tasks).
+typedef struct DexTaskParams {
+  int task;                       // DEX_TASK_REORIENT = 0, DEX_TASK_REACH = 1
+  int successes_needed;           // reorient.py:64 / reach.py:62
+  int steps_before_changing_goal; // reorient.py:70
+  int fall_termination;           // reorient.py:103
+  int has_max_time;               // max_time_per_goal is not None
+  int prop_body, prop_qposadr, prop_dofadr, prop_geom, ground_geom;
+  int nhand;                      // number of hand joints (qpos/qvel 0..nhand-1)
+  int nsite;                      // fingertip sites (<= 5)
+  int site_id[5];
+  int dense_reward;               // reach only
+  int pad0;
+  double success_threshold;       // reorient.py:52 / reach.py:50
+  double max_time_per_goal;       // reorient.py:68
+  double time_limit;              // manipulation/__init__.py:83 (inf if None)
+  double spawn_lo[3], spawn_hi[3];// reorient.py:72-78
+  double w_orientation, w_success_bonus, w_action_smoothing, orientation_eps, bonus_threshold;  // reorient.py:49-56
+  unsigned long long seed;
+} DexTaskParams;
+
+
+/* Additional bindable tensors for the task layer (DexFieldId continues). */
+enum DexTaskFieldId {
+  DEX_FIELD_OBS = 14,          /* real [nenv][128]   observation vector (layout: dexterity_b200/envs.py)       */
+  DEX_FIELD_REWARD = 15,       /* real [nenv]        Task.get_reward                                            */
+  DEX_FIELD_DISCOUNT = 16,     /* real [nenv]        Task.get_discount                                          */
+  DEX_FIELD_GOAL = 18,         /* real [nenv][16]    GoalTask._goal                                             */
+  DEX_FIELD_TASK_I = 19,       /* i32  [nenv][8]     successes, change counter, registered, exceeded, goal_changed, failure, step_type, episode_len */
+  DEX_FIELD_TASK_F = 20,       /* real [nenv][8]     solve_start_time, episode_return, goal_distance[<=5]       */
+  DEX_FIELD_RNG = 21,          /* u32  [nenv][4]     Philox key0,key1,counter,-                                 */
+  DEX_FIELD_ACTION = 22,       /* real [nenv][nu]    the action passed to Environment.step                      */
+  DEX_FIELD_EPISODE_STATS = 24,/* f64  [8]           sum return, sum length, episodes, successes, falls, timeouts, physics errors */
+  DEX_FIELD_RESET_MASK = 25,   /* u8   [nenv]        optional: envs to reset on the next dex_env_step           */
+  DEX_FIELD_SKIP = 26          /* u8   [nenv]        scratch: envs reset during the current call                */
+};
+
+/* Installs the task description (copied).  Replaces the task constructors
+ * (reference manipulation/tasks/reorient.py:94-168, reach.py:74-139). */
+int dex_task_configure(DexBatch* batch, const DexTaskParams* params);
+
+/* Resets every env and writes the FIRST TimeStep (obs, reward=0, discount=1, step_type=FIRST):
+ * GoalEnvironment.reset (reference dexterity/environment.py:14-23). */
+int dex_env_reset(DexBatch* batch, void* stream);
+
+/* One control step on every env: pre-step (auto-reset of envs whose last TimeStep was LAST, goal
+ * switch, action -> ctrl), nsub x mj_step, position/velocity refresh + post-step (reward,
+ * discount, termination, observations): GoalEnvironment.step (reference environment.py:25-34). */
+int dex_env_step(DexBatch* batch, int nsub, void* stream);
+
+/* Per-kernel-class device timing for the benchmark's roofline block: when enabled every launch is
+ * bracketed by a cudaEvent pair on the launching stream.  dex_get_kernel_times synchronises and
+ * returns total milliseconds and launch counts for {pre-step, collide, dynamics, post-step}. */
+int dex_set_profiling(DexBatch* batch, int on);
+int dex_get_kernel_times(DexBatch* batch, double* ms4, int64_t* count4, int reset);
+
 const char* dex_last_error(void);
 
 #ifdef __cplusplus

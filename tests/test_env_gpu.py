@@ -1,0 +1,125 @@
+"""GPU tests of the batched environment (task pre/post kernels) against the numpy restatement of
+the reference's task logic (oracle/task_oracle.py) and the oracle's kinematics."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from oracle import task_oracle as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from dexterity_b200 import envs
+    return envs.load("reorient", "state_dense", seed=12345, num_envs=256)
+
+
+def test_spec_coherence_like_manipulation_test(env):
+    """reference manipulation/manipulation_test.py:23-61, batched."""
+    spec = env.action_spec()
+    assert np.isfinite(spec.minimum).all() and np.isfinite(spec.maximum).all() and spec.shape == (20,)
+    obs_spec = env.observation_spec()
+    ts = env.reset()
+    assert set(ts.observation.keys()) == set(obs_spec.keys())
+    assert (ts.step_type == 0).all() and (ts.reward == 0).all() and (ts.discount == 1).all()
+    assert sum(s.shape[0] for s in obs_spec.values()) == 123
+    lo = torch.as_tensor(spec.minimum, device=env.device); hi = torch.as_tensor(spec.maximum, device=env.device)
+    for _ in range(10):
+        ts = env.step(lo + (hi - lo) * torch.rand(env.num_envs, 20, device=env.device))
+        for k, v in ts.observation.items():
+            assert v.shape == (env.num_envs,) + obs_spec[k].shape and torch.isfinite(v).all(), k
+        assert ((ts.discount >= 0) & (ts.discount <= 1)).all()
+
+
+def test_observations_and_reward_match_restatement(env, reorient_model):
+    c = reorient_model
+    ts = env.reset()
+    om = orc.OracleModel(c)
+    d = orc.OracleData(om)
+    lo = torch.as_tensor(env.action_spec().minimum, device=env.device)
+    hi = torch.as_tensor(env.action_spec().maximum, device=env.device)
+    sites = [c.site_names.index(f"shadow_hand_e/{t}_site") for t in ("fftip", "mftip", "rftip", "lftip", "thtip")]
+    pb = c.body_names.index("prop/")
+    for it in range(6):
+        a = lo + (hi - lo) * torch.rand(env.num_envs, 20, device=env.device)
+        ts = env.step(a)
+        torch.cuda.synchronize()
+        qpos = env.physics.qpos.cpu().numpy().astype(np.float64)
+        qvel = env.physics.qvel.cpu().numpy().astype(np.float64)
+        ctrl = env.physics.ctrl.cpu().numpy().astype(np.float64)
+        goal = env.goal.cpu().numpy().astype(np.float64)[:, :4]
+        obs = {k: v.cpu().numpy().astype(np.float64) for k, v in ts.observation.items()}
+        rew = ts.reward.cpu().numpy().astype(np.float64)
+        stype = ts.step_type.cpu().numpy()
+        for e in range(0, env.num_envs, 17):
+            d.set_state(qpos[e], qvel[e], ctrl[e], np.zeros(c.nv))
+            d.step1()
+            ho = T.hand_observations(c, d, 24, sites)
+            for k, v in ho.items():
+                np.testing.assert_allclose(obs["shadow_hand_e/" + k][e], v, atol=2e-5, rtol=1e-4, err_msg=k)
+            po = T.prop_observations(c, d, pb, 24)
+            for k, v in po.items():
+                np.testing.assert_allclose(obs["prop/" + k][e], v, atol=2e-5, rtol=1e-4, err_msg=k)
+            np.testing.assert_allclose(obs["goal_state"][e], goal[e], atol=1e-6)
+            np.testing.assert_allclose(obs["target_prop/orientation"][e], goal[e], atol=1e-6)
+            if stype[e] != 0:
+                dist = T.prop_orientation_goal_distance(goal[e], po["orientation"])[0]
+                expect = T.weighted_average(T.reorient_reward_terms(dist, ctrl[e]))
+                np.testing.assert_allclose(rew[e], expect, rtol=2e-4, atol=1e-3)
+
+
+def test_reward_kat_at_goal(env):
+    """reference manipulation/tasks/reorient_test.py:13-50: cube at the goal orientation gives
+    orientation reward 1/0.1, success bonus 1.0 and smoothing ||ctrl||^2; first success ends the
+    episode with discount 0 (successes_needed = 1)."""
+    env.reset()
+    torch.cuda.synchronize()
+    env.physics.qpos[:, 27:31] = env.goal[:, :4]
+    a = torch.zeros(env.num_envs, 20, device=env.device)
+    a[:, 3] = 0.5
+    ts = env.step(a)
+    torch.cuda.synchronize()
+    d = env.goal_distance[:, 0]
+    ok = d <= 0.1          # five physics substeps may rotate the cube a little; most stay inside
+    assert ok.float().mean() > 0.9
+    expect = 1.0 / (d[ok] + 0.1) + 800.0 - 0.1 * 0.25
+    torch.testing.assert_close(ts.reward[ok], expect.to(ts.reward.dtype), rtol=1e-4, atol=1e-2)
+    assert (ts.discount[ok] == 0).all() and (ts.step_type[ok] == 2).all() and (env.successes[ok] == 1).all()
+
+
+def test_dm_env_auto_reset_semantics(env):
+    env.reset()
+    mask = torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
+    mask[::2] = True
+    env.request_reset(mask)
+    a = torch.zeros(env.num_envs, 20, device=env.device)
+    ts = env.step(a)
+    torch.cuda.synchronize()
+    assert (ts.step_type[::2] == 0).all() and (ts.step_type[1::2] != 0).all()
+    assert (env.physics.time[::2] == 0).all() and (env.physics.time[1::2] > 0).all()
+    env.request_reset(torch.zeros_like(mask))
+    # drive envs until some terminate (cube falls with random actions), then check LAST -> FIRST
+    lo = torch.as_tensor(env.action_spec().minimum, device=env.device)
+    hi = torch.as_tensor(env.action_spec().maximum, device=env.device)
+    seen_last = torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
+    for _ in range(120):
+        prev_last = ts.step_type.clone() == 2
+        ts = env.step(lo + (hi - lo) * torch.rand(env.num_envs, 20, device=env.device))
+        assert (ts.step_type[prev_last] == 0).all(), "the step after LAST must be FIRST"
+        seen_last |= prev_last
+    assert seen_last.any(), "no episode terminated in 120 random-action steps"
+    stats = env.reduce_episode_stats()
+    assert stats["episodes"] >= seen_last.sum().item()
+
+
+def test_fall_termination_has_discount_one(env):
+    """reference reorient.py:222-225: failure termination returns discount 1.0."""
+    env.reset()
+    torch.cuda.synchronize()
+    env.physics.qpos[:, 24:27] = torch.tensor([0.3, 0.3, 0.0195], device=env.device)  # cube on the ground
+    env.physics.qpos[:, 27:31] = torch.tensor([1.0, 0, 0, 0], device=env.device)
+    ts = env.step(torch.zeros(env.num_envs, 20, device=env.device))
+    torch.cuda.synchronize()
+    assert (ts.step_type == 2).all() and (ts.discount == 1).all()

@@ -1,0 +1,165 @@
+"""CPU checks that pin the FP64 oracle itself (it has no MuJoCo golden vectors to lean on, so it
+is validated against definitions and physical invariants, plus a committed regression fixture)."""
+import os
+
+import numpy as np
+import pytest
+
+from dexterity_b200.model import compile as C
+from oracle import oracle as orc
+from tests import statelib
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reorient_oracle_steps.npz")
+
+
+@pytest.fixture(scope="module")
+def om(reorient_model):
+    return orc.OracleModel(reorient_model)
+
+
+def _random_state(c, rng, vel=0.5):
+    q = statelib.reorient_reset(c, rng)
+    q[:24] = rng.uniform(c.JNT_RANGE[:24, 0], c.JNT_RANGE[:24, 1])
+    return q, rng.randn(c.nv) * vel
+
+
+def test_model_counts_match_survey(reorient_model):
+    c = reorient_model
+    assert (c.nbody, c.nq, c.nv, c.nu, c.ngeom, c.nsite) == (34, 31, 30, 20, 206, 5)
+    assert abs(c.BODY_MASS[2:32].sum() - 3.794) < 1e-9                 # SURVEY §8 model facts
+    assert abs(c.BODY_MASS[32] - 0.064) < 1e-12 and np.allclose(c.BODY_INERTIA[32], 1.7066666e-5, rtol=1e-6)
+    assert c.GEOM_VERTNUM.max() == 407 and len(c.VERT) == 5899
+
+
+def test_kinematics_and_mass_matrix_match_definitions(reorient_model, om):
+    c = reorient_model
+    rng = np.random.RandomState(0)
+    d = orc.OracleData(om)
+    for _ in range(5):
+        q, v = _random_state(c, rng)
+        d.set_state(q, v, np.zeros(c.nu), np.zeros(c.nv))
+        d.forward()
+        kin = C.kinematics(c.arrays, q)
+        assert np.abs(d.get("xpos").reshape(-1, 3) - kin["xpos"]).max() < 1e-14
+        M = d.get("M").reshape(c.nv, c.nv)
+        Mdef = C.mass_matrix(c.arrays, kin)          # sum_b m Jp^T Jp + Jr^T I Jr + armature
+        assert np.abs(M - Mdef).max() < 1e-13
+        assert np.abs(M - M.T).max() == 0 and np.linalg.eigvalsh(M).min() > 0
+
+
+def test_bias_force_matches_lagrangian_finite_difference(reorient_model, om):
+    """qfrc_bias = C(q,v) v + g(q): compare with d/dt(dT/dv) - dT/dq + dV/dq by finite differences
+    on the hinge dofs (the free joint's quaternion coordinates are left out)."""
+    c = reorient_model
+    rng = np.random.RandomState(1)
+    d = orc.OracleData(om)
+    q, v = _random_state(c, rng, vel=1.0)
+    v[24:] = 0
+    d.set_state(q, v, np.zeros(c.nu), np.zeros(c.nv)); d.forward()
+    bias = d.get("qfrc_bias")[:24]
+    applied = d.get("qfrc_applied")[:24]
+
+    def M_of(qq):
+        return C.mass_matrix(c.arrays, C.kinematics(c.arrays, qq))[:24, :24]
+
+    def V_of(qq):
+        kin = C.kinematics(c.arrays, qq)
+        return 9.81 * (c.BODY_MASS * kin["xipos"][:, 2]).sum()
+
+    eps = 1e-6
+    vh = v[:24]
+    dM = np.zeros((24, 24, 24)); dV = np.zeros(24)
+    for k in range(24):
+        qp, qm = q.copy(), q.copy(); qp[k] += eps; qm[k] -= eps
+        dM[k] = (M_of(qp) - M_of(qm)) / (2 * eps)
+        dV[k] = (V_of(qp) - V_of(qm)) / (2 * eps)
+    coriolis = np.einsum("kij,k,j->i", dM, vh, vh) - 0.5 * np.einsum("iab,a,b->i", dM, vh, vh)
+    assert np.abs(bias - (coriolis + dV)).max() < 1e-5
+    # gravity compensation (reference utils/mujoco_utils.py:91-99) cancels gravity on the hand dofs
+    assert np.abs(applied - dV).max() < 1e-9
+
+
+def test_free_fall_and_energy(reorient_model, om):
+    c = reorient_model
+    d = orc.OracleData(om)
+    q = c.QPOS0.copy(); q[24:27] = [0.3, 0.3, 0.5]
+    d.set_state(q, np.zeros(c.nv), np.zeros(c.nu), np.zeros(c.nv))
+    d.forward()
+    assert np.allclose(d.get("qacc")[24:27], [0, 0, -9.81], atol=1e-9) and np.allclose(d.get("qacc")[27:], 0, atol=1e-9)
+    for _ in range(20):
+        d.step()
+    qq, vv, _, t = d.get_state()
+    assert abs(vv[26] + 9.81 * t) < 1e-9                       # semi-implicit Euler: v = -g t exactly
+    assert abs(qq[26] - (0.5 - 9.81 * 0.005 ** 2 * 20 * 21 / 2)) < 1e-9
+
+
+def test_solver_kkt_and_cone(reorient_model, om):
+    """At the Newton solution the gradient M a - qfrc_smooth - J^T f vanishes and every force is
+    consistent with its row's regime (contact/limit rows push only; friction rows are boxed)."""
+    c = reorient_model
+    states = statelib.rollout_states(c, seed=3, nstates=24, every=10, episodes=3)
+    d = orc.OracleData(om)
+    seen_contact = 0
+    for e in range(24):
+        d.set_state(states["qpos"][e], states["qvel"][e], states["ctrl"][e], states["warm"][e]); d.forward()
+        n = d.nefc
+        J = d.get("efc_J").reshape(n, c.nv); f = d.get("efc_force"); M = d.get("M").reshape(c.nv, c.nv)
+        grad = M @ d.get("qacc") - d.get("qfrc_smooth") - J.T @ f
+        assert np.abs(grad).max() < 1e-6 * max(1.0, np.abs(d.get("qfrc_smooth")).max())
+        types, _ = d.efc_types()
+        jar = J @ d.get("qacc") - d.get("efc_aref")
+        assert (f[types != 0] >= 0).all()
+        assert (np.abs(f[types == 0]) <= d.get("efc_floss")[types == 0] + 1e-12).all()
+        assert (f[(types != 0) & (jar > 0)] == 0).all()
+        seen_contact += int((types == 3).any())
+    assert seen_contact > 3
+
+
+def test_cube_rests_on_palm(reorient_model, om):
+    """Soft-contact equilibrium: a cube dropped on the open palm comes to rest, supported by
+    contact forces that balance its weight."""
+    c = reorient_model
+    d = orc.OracleData(om)
+    q = c.QPOS0.copy(); q[24:27] = [0.0, -0.13, 0.14]
+    d.set_state(q, np.zeros(c.nv), np.zeros(c.nu), np.zeros(c.nv))
+    for _ in range(300):
+        d.step()
+    qq, vv, _, _ = d.get_state()
+    assert np.abs(vv[24:]).max() < 1e-3 and 0.11 < qq[26] < 0.14
+    d.forward()
+    con = d.contacts()
+    assert len(con["dist"]) >= 3 and (con["dist"] < 0).all() and con["dist"].min() > -1e-3
+    assert abs(d.get("qfrc_constraint")[26] - 0.064 * 9.81) < 1e-3
+
+
+def test_mpr_depth_against_support_function_search(reorient_model, om):
+    """For intersecting pairs MPR reports the distance from the origin to a portal triangle lying
+    on the boundary of the Minkowski difference, so along its direction the hulls overlap by at
+    least that much: support gap along n <= dist <= 0."""
+    c = reorient_model
+    states = statelib.rollout_states(c, seed=11, nstates=40, every=8, episodes=4)
+    d = orc.OracleData(om)
+    checked = 0
+    for e in range(40):
+        d.set_state(states["qpos"][e], states["qvel"][e], states["ctrl"][e], states["warm"][e]); d.forward()
+        con = d.contacts()
+        for (g1, g2), dist, frame in zip(con["geom"], con["dist"], con["frame"]):
+            if c.GEOM_TYPE[g1] == 0:
+                continue
+            n = frame[0]
+            gap = np.dot(d.support(g2, -n), n) - np.dot(d.support(g1, n), n)   # signed gap along n (<0: overlap)
+            assert dist <= 0 and gap <= dist + 1e-6, (gap, dist)
+            checked += 1
+    assert checked > 10
+
+
+def test_golden_regression_fixture(reorient_model, om):
+    """Committed oracle outputs (tests/golden/, generated by tools/make_golden.py).  NOT MuJoCo
+    vectors: a regression pin so that oracle edits that change numerics are noticed."""
+    z = np.load(GOLDEN)
+    c = reorient_model
+    states = {k: z[k] for k in ("qpos", "qvel", "ctrl", "warm")}
+    ref = statelib.oracle_step(c, states, nsub=1)
+    assert np.abs(ref["qpos"] - z["next_qpos"]).max() < 1e-12
+    assert np.abs(ref["qvel"] - z["next_qvel"]).max() < 1e-9
+    assert (ref["ncon"] == z["ncon"]).all()
