@@ -248,13 +248,8 @@ class BatchedGoalEnvironment:
     def reduce_episode_stats(self) -> Dict[str, float]:
         """Episode statistics summed over all ranks (the ONLY collective on this path: one
         all-reduce of an 8-element float64 vector over NCCL / NVLink per logging interval)."""
-        stats = self.episode_stats.clone()
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.SUM)
-        s = stats.cpu().numpy()
-        n = max(s[2], 1.0)
-        return dict(episodes=s[2], mean_return=s[0] / n, mean_length=s[1] / n, successes=s[3], falls=s[4],
-                    timeouts=s[5], physics_errors=s[6])
+        from dexterity_b200 import sharding
+        return sharding.reduce_episode_stats(self.episode_stats)
 
 
 def load(domain_name: str, task_name: str = "state_dense", seed: Optional[int] = None,

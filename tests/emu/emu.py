@@ -64,3 +64,37 @@ class EmuModel:
                    time=time, status=status, contact=contact.astype(np.float64), ncon=ncon, niter=niter)
         out.update({k: v.astype(np.float64) for k, v in dbg.items()})
         return out
+
+
+class EmuEnv:
+    """Host emulation of dex_env_reset / dex_env_step (kernel bodies run by the fiber emulator)."""
+
+    FIELD = dict(QPOS=0, QVEL=1, CTRL=2, QACC_WARMSTART=3, TIME=4, STATUS=5, CONTACT=6, NCON=7, NITER=8, OBS=14, REWARD=15,
+                 DISCOUNT=16, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22, EPISODE_STATS=24, RESET_MASK=25, SKIP=26)
+
+    def __init__(self, model: EmuModel, params, nenv: int, dtype=np.float32, seed: int = 1):
+        self.m, self.p, self.n, self.dtype = model, params, nenv, dtype
+        z = lambda *s, dt=dtype: np.zeros(s, dt)
+        self.a = dict(QPOS=z(nenv, 32), QVEL=z(nenv, 32), CTRL=z(nenv, 32), QACC_WARMSTART=z(nenv, 32), TIME=z(nenv),
+                      STATUS=z(nenv, dt=np.uint32), CONTACT=z(nenv, MAXCON, CON_STRIDE), NCON=z(nenv, dt=np.int32),
+                      NITER=z(nenv, dt=np.int32), OBS=z(nenv, 128), REWARD=z(nenv), DISCOUNT=z(nenv), GOAL=z(nenv, 16),
+                      TASK_I=z(nenv, 8, dt=np.int32), TASK_F=z(nenv, 8), RNG=z(nenv, 4, dt=np.uint32), ACTION=z(nenv, 32),
+                      EPISODE_STATS=z(8, dt=np.float64), RESET_MASK=z(nenv, dt=np.uint8), SKIP=z(nenv, dt=np.uint8))
+        self.a["RNG"][:, 0] = seed
+        self.ptrs = (ctypes.c_void_p * 32)()
+        self.strides = (ctypes.c_int64 * 32)()
+        for k, arr in self.a.items():
+            self.ptrs[self.FIELD[k]] = arr.ctypes.data
+            self.strides[self.FIELD[k]] = arr.strides[0] // arr.itemsize if arr.ndim > 1 else 1
+        self.m.lib.emu_env_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+
+    def _call(self, nsub, force_reset, nthreads=1):
+        self.m.lib.emu_env_step(self.m.ptr, 0 if self.dtype == np.float32 else 1, self.n, self.ptrs, self.strides,
+                                ctypes.byref(self.p), nsub, force_reset, nthreads)
+
+    def reset(self): self._call(1, 1)
+
+    def step(self, action, nsub):
+        self.a["ACTION"][:, :action.shape[1]] = action
+        self._call(nsub, 0, nthreads=4)

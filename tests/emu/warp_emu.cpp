@@ -17,6 +17,7 @@
 #include "../../dexterity_b200/csrc/dex_collide.cuh"
 #include "../../dexterity_b200/csrc/dex_dynamics.cuh"
 #include "../../dexterity_b200/csrc/dex_host_model.h"
+#include "../../dexterity_b200/csrc/dex_task.cuh"
 
 namespace dex_emu {
 struct Warp {
@@ -158,15 +159,52 @@ int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, vo
   EmuModel* m = (EmuModel*)mp;
   if (dtype == 0) {
     BatchState<float> st = {nenv, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
-                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter};
+                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr};
     DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
     emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   } else {
     BatchState<double> st = {nenv, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
-                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter};
+                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr};
     DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
     emu_run<double>(m->d.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   }
+  return 0;
+}
+
+// One batched control step (or a forced reset when force_reset != 0) through the task kernels.
+// Pointers follow DexFieldId; `f` is an array of DEX_FIELD_COUNT host pointers, `stride` likewise.
+int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride, const DexTaskParams* p, int nsub,
+                 int force_reset, int nthreads) {
+  EmuModel* m = (EmuModel*)mp;
+  auto go = [&](auto tag, const auto& dev) {
+    using T = decltype(tag);
+    BatchState<T> st = {nenv, (T*)f[DEX_FIELD_QPOS], (int)stride[DEX_FIELD_QPOS], (T*)f[DEX_FIELD_QVEL], (int)stride[DEX_FIELD_QVEL],
+                        (T*)f[DEX_FIELD_CTRL], (int)stride[DEX_FIELD_CTRL], (T*)f[DEX_FIELD_QACC_WARMSTART],
+                        (int)stride[DEX_FIELD_QACC_WARMSTART], (T*)f[DEX_FIELD_TIME], (unsigned*)f[DEX_FIELD_STATUS],
+                        (T*)f[DEX_FIELD_CONTACT], (int*)f[DEX_FIELD_NCON], (int*)f[DEX_FIELD_NITER],
+                        (const unsigned char*)f[DEX_FIELD_SKIP]};
+    TaskState<T> ts = {(const T*)f[DEX_FIELD_ACTION], (int)stride[DEX_FIELD_ACTION], (T*)f[DEX_FIELD_OBS], (T*)f[DEX_FIELD_REWARD],
+                       (T*)f[DEX_FIELD_DISCOUNT], (T*)f[DEX_FIELD_GOAL], (int*)f[DEX_FIELD_TASK_I], (T*)f[DEX_FIELD_TASK_F],
+                       (unsigned*)f[DEX_FIELD_RNG], (unsigned char*)f[DEX_FIELD_SKIP], (const unsigned char*)f[DEX_FIELD_RESET_MASK],
+                       (double*)f[DEX_FIELD_EPISODE_STATS]};
+    DynDebug<T> dbg = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto work = [&](int lo, int hi) {
+      std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T) + 64);
+      for (int env = lo; env < hi; ++env) {
+        dex_emu::run_warp([&]() { dex_task_pre_env<T>(dev, st, ts, *p, env, force_reset); });
+        if (!force_reset) for (int s = 0; s < nsub; ++s) {
+          dex_emu::run_warp([&]() { dex_collide_env<T>(dev, st, env, smem.data()); });
+          dex_emu::run_warp([&]() { dex_dynamics_env<T>(dev, st, dbg, env, smem.data(), 1); });
+        }
+        dex_emu::run_warp([&]() { dex_task_post_env<T>(dev, st, ts, *p, env, smem.data()); });
+      }
+    };
+    if (nthreads <= 1) { work(0, nenv); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, nenv * t / nthreads, nenv * (t + 1) / nthreads);
+    for (auto& t : th) t.join();
+  };
+  if (dtype == 0) go(float(0), m->f.dev); else go(double(0), m->d.dev);
   return 0;
 }
 }

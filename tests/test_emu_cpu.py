@@ -1,0 +1,103 @@
+"""CPU-only execution of the CUDA kernel BODIES under the test-only warp emulator
+(tests/emu/warp_emu.cpp) against the oracle.  This guards kernel logic between GPU runs; the GPU
+parity proper is tests/test_physics_gpu.py.  The emulator is test infrastructure, not a fallback."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import task_oracle as T
+from tests import statelib
+from tests.emu import emu as E
+
+
+@pytest.fixture(scope="module")
+def emu_model(reorient_model):
+    return E.EmuModel(reorient_model)
+
+
+@pytest.fixture(scope="module")
+def states(reorient_model):
+    return statelib.rollout_states(reorient_model, seed=77, nstates=12, every=11, episodes=3)
+
+
+def test_kernel_bodies_fp64_match_oracle(reorient_model, emu_model, states):
+    ref = statelib.oracle_step(reorient_model, states, nsub=1)
+    out = emu_model.run(states["qpos"], states["qvel"], states["ctrl"], states["warm"], nsub=1, dtype=np.float64, debug=True)
+    assert (out["ncon"] == ref["ncon"]).all() and (out["status"] == 0).all()
+    assert np.abs(out["qacc"] - ref["qacc"]).max() < 1e-6 * max(1.0, np.abs(ref["qacc"]).max())
+    assert np.abs(out["qpos"] - ref["qpos"]).max() < 1e-10 and np.abs(out["qvel"] - ref["qvel"]).max() < 1e-7
+
+
+def test_kernel_bodies_fp32_match_oracle(reorient_model, emu_model, states):
+    ref = statelib.oracle_step(reorient_model, states, nsub=1)
+    out = emu_model.run(states["qpos"], states["qvel"], states["ctrl"], states["warm"], nsub=1, dtype=np.float32)
+    assert (out["ncon"] == ref["ncon"]).all()
+    rel = np.abs(out["qvel"] - ref["qvel"]).max(axis=1) / np.maximum(1, np.abs(ref["qvel"]).max(axis=1))
+    assert np.median(rel) < 1e-5 and (rel < 1e-4).mean() >= 0.8
+
+
+def _params(c):
+    from dexterity_b200 import envs
+    p = envs.TaskParams()
+    cfg = envs.REORIENT
+    p.task, p.successes_needed, p.steps_before_changing_goal, p.fall_termination, p.has_max_time = 0, 1, 5, 1, 1
+    p.prop_body = c.body_names.index("prop/"); j = c.joint_names.index("prop/")
+    p.prop_qposadr, p.prop_dofadr = int(c.JNT_QPOSADR[j]), int(c.JNT_DOFADR[j])
+    p.prop_geom, p.ground_geom = c.geom_names.index("prop/geom"), c.geom_names.index("ground")
+    p.nhand, p.nsite = 24, 5
+    for i, t in enumerate(("fftip", "mftip", "rftip", "lftip", "thtip")):
+        p.site_id[i] = c.site_names.index(f"shadow_hand_e/{t}_site")
+    p.success_threshold, p.max_time_per_goal, p.time_limit = 0.1, 7.5, float("inf")
+    for k in range(3):
+        p.spawn_lo[k], p.spawn_hi[k] = cfg["spawn_lo"][k], cfg["spawn_hi"][k]
+    p.w_orientation, p.w_success_bonus, p.w_action_smoothing, p.orientation_eps, p.bonus_threshold = 1.0, 800.0, -0.1, 0.1, 0.1
+    return p
+
+
+def test_task_kernels_against_restatement(reorient_model, emu_model):
+    c = reorient_model
+    env = E.EmuEnv(emu_model, _params(c), nenv=6, dtype=np.float64, seed=9)
+    env.reset()
+    a = env.a
+    assert (a["TASK_I"][:, 6] == 0).all() and (a["REWARD"] == 0).all() and (a["DISCOUNT"] == 1).all()
+    q = a["QPOS"][:, :31]
+    assert np.allclose(np.linalg.norm(q[:, 27:31], axis=1), 1) and np.allclose(np.linalg.norm(a["GOAL"][:, :4], axis=1), 1)
+    assert (np.abs(q[:, 24]) <= 0.025).all() and (np.abs(q[:, 25] + 0.13) <= 0.025).all() and np.allclose(q[:, 26], 0.16)
+    assert len({tuple(np.round(x, 6)) for x in q[:, 24:31]}) == 6, "per-env RNG streams must differ"
+    rng = np.random.RandomState(0)
+    lo, hi = c.ACT_CTRLRANGE[:, 0], c.ACT_CTRLRANGE[:, 1]
+    om = orc.OracleModel(c); d = orc.OracleData(om)
+    sites = [c.site_names.index(f"shadow_hand_e/{t}_site") for t in ("fftip", "mftip", "rftip", "lftip", "thtip")]
+    machines = [T.GoalTaskState(0.1, 1, 5, 7.5) for _ in range(6)]
+    for m_ in machines:
+        m_.initialize_episode(0.0)
+    for it in range(3):
+        act = rng.uniform(lo, hi, size=(6, 20))
+        env.step(act, nsub=5)
+        for e in range(6):
+            assert a["TASK_I"][e, 6] in (1, 2)
+            d.set_state(a["QPOS"][e, :31], a["QVEL"][e, :30], a["CTRL"][e, :20], np.zeros(30)); d.step1()
+            ho = T.hand_observations(c, d, 24, sites)
+            np.testing.assert_allclose(a["OBS"][e, :48], ho["joint_positions_sin_cos"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 48:72], ho["joint_velocities"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 72:87], ho["fingertip_positions"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 87:102], ho["fingertip_linear_velocities"], atol=1e-10)
+            po = T.prop_observations(c, d, 32, 24)
+            np.testing.assert_allclose(a["OBS"][e, 102:105], po["position"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 105:109], po["orientation"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 109:112], po["linear_velocity"], atol=1e-10)
+            np.testing.assert_allclose(a["OBS"][e, 112:115], po["angular_velocity"], atol=1e-10)
+            goal = a["GOAL"][e, :4]
+            dist = T.prop_orientation_goal_distance(goal, po["orientation"])[0]
+            np.testing.assert_allclose(a["TASK_F"][e, 2], dist, atol=1e-7)
+            np.testing.assert_allclose(a["REWARD"][e], T.weighted_average(T.reorient_reward_terms(dist, a["CTRL"][e, :20])), rtol=1e-9)
+            np.testing.assert_allclose(a["CTRL"][e, :20], act[e], atol=0)      # stored unclipped
+            m_ = machines[e]
+            m_.before_step(a["TIME"][e] - 0.025)
+            m_.after_step(np.array([dist]), a["TIME"][e])
+            assert a["TASK_I"][e, 0] == m_.successes and a["TASK_I"][e, 1] == m_.success_change_counter
+            fallen = bool((d.contacts()["geom"] == [c.geom_names.index("ground"), c.geom_names.index("prop/geom")]).all(axis=1).any()) \
+                if len(d.contacts()["dist"]) else False
+            assert (a["TASK_I"][e, 6] == 2) == (m_.should_terminate_episode() or fallen)
