@@ -2,13 +2,19 @@
 // suite's geom pairs).
 //
 //   broadphase  : static candidate pairs grouped by body pair (compile-time filters already
-//                 applied: same weld, parent-child, <exclude>, contype/conaffinity), culled at
-//                 run time by body bounding spheres then geom bounding spheres, 32 tests per
-//                 warp instruction, survivors compacted with ballots.
+//                 applied: same weld, parent-child, <exclude>, contype/conaffinity).  Run-time
+//                 culls are conservative and therefore do not change the contact set:
+//                 body bounding spheres (plane: half-space test), then per geom pair, in the
+//                 frame of body A so that no per-geom world transform is needed: bounding
+//                 spheres, then each sphere against the other geom's body-frame AABB.  32 tests
+//                 per warp instruction; survivors are compacted with ballots.
 //   narrowphase : plane-box (mjc_PlaneBox), plane-mesh (mjc_PlaneConvex) and convex-convex
-//                 through libccd's MPR (ccdMPRPenetration) with mpr_tolerance/mpr_iterations.
-//                 The portal state is warp-uniform; the mesh support function is the parallel
-//                 part (lanes scan hull vertices, warp argmax with lowest-index tie-break).
+//                 through libccd's MPR (ccdMPRPenetration) with mpr_tolerance/mpr_iterations,
+//                 carried out in the frame of body A.  The portal state is warp-uniform; the mesh
+//                 support function is the parallel part (lanes scan hull vertices, warp argmax
+//                 with lowest-index tie-break).  The support function is a real (non-inlined)
+//                 call: the r01a profile showed 54 % of K1's stall samples were instruction-cache
+//                 misses with everything inlined (111 KB of SASS).
 // Contacts are written compactly to global memory [env][DEX_MAXCON][8] for K2.
 #ifndef DEX_COLLIDE_CUH_
 #define DEX_COLLIDE_CUH_
@@ -17,72 +23,64 @@
 
 // per-warp shared-memory footprint of K1, in units of T
 #define DEX_K1_SMEM_T (DEX_MAXBODY * 16 + 48 + DEX_MAXCAND + 8 * 4)
+#define DEX_GPACK 12  // geom_pack: centre(3) rbound | aabb centre(3) aabb half.x | aabb half.y half.z pad pad
 
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> struct Xf { T R[9]; T t[3]; };  // pose of frame B expressed in frame A
+
+// Everything the support function needs about one geom, resolved by the caller from the kernel's
+// constant-bank model so that the non-inlined callees never take the model's address.
 template <typename T>
-struct CollideCtx {
-  const DevModel<T>* m;
-  const T* xpos;
-  const T* xmat;
-  T half_margin;  // mjc_Convex inflates both shapes by margin/2 along the query direction
+struct GeomRef {
+  const T* vert;   // body-frame hull vertices (mesh)
+  int n;           // vertex count
+  int type;        // DEX_GEOM_*
+  const T* mat;    // geom rotation in the body frame (box)
+  const T* size;   // half sizes (box)
+  const T* pack;   // geom_pack record (centre, rbound, aabb)
 };
-
-// world-frame support point of geom g in unit direction dir (mjccd_support, margin 0)
 template <typename T>
-DEX_DEV void dex_support(const CollideCtx<T>& c, int g, int gtype, const T* dir, T* out) {
-  const DevModel<T>& m = *c.m;
-  const int b = dex_ldg(m.geom_body + g);
-  const T* R = c.xmat + 9 * b;
-  T ld[3], loc[3];
-  rotT_vec(ld, R, dir);
+DEX_DEV GeomRef<T> dex_geom_ref(const DevModel<T>& m, int g, int type) {
+  GeomRef<T> r;
+  r.vert = m.vert + 3 * dex_ldg(m.geom_vertadr + g);
+  r.n = dex_ldg(m.geom_vertnum + g);
+  r.type = type;
+  r.mat = m.geom_mat + 9 * g;
+  r.size = m.geom_size + 3 * g;
+  r.pack = m.geom_pack + DEX_GPACK * g;
+  return r;
+}
+
+// Body-frame support point for the body-frame unit direction (lx,ly,lz): mjccd_support.
+// All 32 lanes call this together (warp shuffles inside).
+template <typename T>
+DEX_DEV_NOINLINE V3<T> dex_support_local(const T* vert, int n, int gtype, const T* mat, const T* size, const T* pack,
+                                         T lx, T ly, T lz) {
+  V3<T> out;
   if (gtype == DEX_GEOM_MESH) {
-    const int adr = dex_ldg(m.geom_vertadr + g), n = dex_ldg(m.geom_vertnum + g);
-    const T* v = m.vert + 3 * adr;
     T best = -Real<T>::big();
     int bi = 0x7fffffff;
     for (int i = dex_lane(); i < n; i += 32) {
-      T t = dex_ldg(v + 3 * i) * ld[0] + dex_ldg(v + 3 * i + 1) * ld[1] + dex_ldg(v + 3 * i + 2) * ld[2];
+      const T t = dex_ldg(vert + 3 * i) * lx + dex_ldg(vert + 3 * i + 1) * ly + dex_ldg(vert + 3 * i + 2) * lz;
       if (t > best) { best = t; bi = i; }
     }
     dex_warp_argmax(best, bi);
-    loc[0] = dex_ldg(v + 3 * bi); loc[1] = dex_ldg(v + 3 * bi + 1); loc[2] = dex_ldg(v + 3 * bi + 2);
+    out.x = dex_ldg(vert + 3 * bi); out.y = dex_ldg(vert + 3 * bi + 1); out.z = dex_ldg(vert + 3 * bi + 2);
   } else {  // box
-    const T* gm = m.geom_mat + 9 * g;
-    T G[9];
-    for (int i = 0; i < 9; ++i) G[i] = dex_ldg(gm + i);
-    T l2[3], cn[3];
+    T G[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
+    for (int i = 0; i < 9; ++i) G[i] = dex_ldg(mat + i);
     rotT_vec(l2, G, ld);
-    cn[0] = l2[0] > 0 ? dex_ldg(m.geom_size + 3 * g) : -dex_ldg(m.geom_size + 3 * g);
-    cn[1] = l2[1] > 0 ? dex_ldg(m.geom_size + 3 * g + 1) : -dex_ldg(m.geom_size + 3 * g + 1);
-    cn[2] = l2[2] > 0 ? dex_ldg(m.geom_size + 3 * g + 2) : -dex_ldg(m.geom_size + 3 * g + 2);
+    cn[0] = l2[0] > 0 ? dex_ldg(size) : -dex_ldg(size);
+    cn[1] = l2[1] > 0 ? dex_ldg(size + 1) : -dex_ldg(size + 1);
+    cn[2] = l2[2] > 0 ? dex_ldg(size + 2) : -dex_ldg(size + 2);
     rot_vec(loc, G, cn);
-    loc[0] += dex_ldg(m.geom_pos + 3 * g); loc[1] += dex_ldg(m.geom_pos + 3 * g + 1); loc[2] += dex_ldg(m.geom_pos + 3 * g + 2);
+    out.x = loc[0] + dex_ldg(pack); out.y = loc[1] + dex_ldg(pack + 1); out.z = loc[2] + dex_ldg(pack + 2);
   }
-  rot_vec(out, R, loc);
-  out[0] += c.xpos[3 * b]; out[1] += c.xpos[3 * b + 1]; out[2] += c.xpos[3 * b + 2];
+  return out;
 }
-
 template <typename T>
-DEX_DEV void dex_geom_center(const CollideCtx<T>& c, int g, T* out) {
-  const DevModel<T>& m = *c.m;
-  const int b = dex_ldg(m.geom_body + g);
-  T gp[3] = {dex_ldg(m.geom_pos + 3 * g), dex_ldg(m.geom_pos + 3 * g + 1), dex_ldg(m.geom_pos + 3 * g + 2)};
-  rot_vec(out, c.xmat + 9 * b, gp);
-  out[0] += c.xpos[3 * b]; out[1] += c.xpos[3 * b + 1]; out[2] += c.xpos[3 * b + 2];
-}
-
-// true if the sphere (world centre c, radius r) may touch the body-frame AABB of geom g
-template <typename T>
-DEX_DEV bool dex_sphere_vs_aabb(const CollideCtx<T>& cx, const T* c, T r, int g) {
-  const DevModel<T>& m = *cx.m;
-  const int b = dex_ldg(m.geom_body + g);
-  T d[3] = {c[0] - cx.xpos[3 * b], c[1] - cx.xpos[3 * b + 1], c[2] - cx.xpos[3 * b + 2]}, l[3];
-  rotT_vec(l, cx.xmat + 9 * b, d);
-  T s = 0;
-  for (int k = 0; k < 3; ++k) {
-    T e = dx_abs(l[k] - dex_ldg(m.geom_aabb + 6 * g + k)) - dex_ldg(m.geom_aabb + 6 * g + 3 + k);
-    if (e > 0) s += e * e;
-  }
-  return s <= r * r;
+DEX_DEV V3<T> dex_support_ref(const GeomRef<T>& g, T lx, T ly, T lz) {
+  return dex_support_local(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
 }
 
 // ---- libccd helpers ---------------------------------------------------------------------
@@ -97,15 +95,30 @@ template <typename T> DEX_DEV bool ccd_eq(T a, T b) {
   T fa = dx_abs(a), fb = dx_abs(b);
   return fb > fa ? ab < Real<T>::eps() * fb : ab < Real<T>::eps() * fa;
 }
-template <typename T> struct SupPt { T v[3], v1[3], v2[3]; };
+// Minkowski-difference support point: v = v1 - v2, v1 on geom A, v2 on geom B (both in frame A)
+template <typename T> struct SupPt { T v[3], v1[3]; };
 
 template <typename T>
-DEX_DEV void dex_mink(const CollideCtx<T>& c, int g1, int t1, int g2, int t2, const T* dir, SupPt<T>& p) {
-  T nd[3] = {-dir[0], -dir[1], -dir[2]};
-  dex_support(c, g1, t1, dir, p.v1);
-  dex_support(c, g2, t2, nd, p.v2);
-  for (int k = 0; k < 3; ++k) { p.v1[k] += dir[k] * c.half_margin; p.v2[k] -= dir[k] * c.half_margin; }
-  p.v[0] = p.v1[0] - p.v2[0]; p.v[1] = p.v1[1] - p.v2[1]; p.v[2] = p.v1[2] - p.v2[2];
+struct MprCtx {
+  GeomRef<T> A, B;
+  Xf<T> rel;
+  T half_margin;  // mjc_Convex inflates both shapes by margin/2 along the query direction
+  T tolerance;    // opt.mpr_tolerance
+  int iterations; // opt.mpr_iterations
+};
+
+template <typename T>
+DEX_DEV_NOINLINE void dex_mink(const MprCtx<T>& c, const T* dir, SupPt<T>& p) {
+  const V3<T> a = dex_support_ref(c.A, dir[0], dir[1], dir[2]);
+  T nd[3] = {-dir[0], -dir[1], -dir[2]}, lb[3];
+  rotT_vec(lb, c.rel.R, nd);
+  const V3<T> b = dex_support_ref(c.B, lb[0], lb[1], lb[2]);
+  T bl[3] = {b.x, b.y, b.z}, bw[3];
+  rot_vec(bw, c.rel.R, bl);
+  p.v1[0] = a.x + dir[0] * c.half_margin; p.v1[1] = a.y + dir[1] * c.half_margin; p.v1[2] = a.z + dir[2] * c.half_margin;
+  p.v[0] = p.v1[0] - (bw[0] + c.rel.t[0] - dir[0] * c.half_margin);
+  p.v[1] = p.v1[1] - (bw[1] + c.rel.t[1] - dir[1] * c.half_margin);
+  p.v[2] = p.v1[2] - (bw[2] + c.rel.t[2] - dir[2] * c.half_margin);
 }
 template <typename T> DEX_DEV T point_seg_dist2(const T* x0, const T* b, T* wit) {  // P = origin
   T dd[3] = {b[0] - x0[0], b[1] - x0[1], b[2] - x0[2]};
@@ -157,20 +170,24 @@ template <typename T> DEX_DEV void expand_portal(SupPt<T>* s, const SupPt<T>& v4
   }
 }
 
-// ccdMPRPenetration.  All lanes run this with identical (warp-uniform) state.
-// returns true on intersection; depth/dir/pos as libccd.
+// ccdMPRPenetration in the frame of body A.  All lanes run this with identical (warp-uniform)
+// state.  Returns true on intersection; depth / dir / pos as libccd (pos = midpoint of the witness
+// points on A and B).
 template <typename T>
-DEX_DEV bool dex_mpr(const CollideCtx<T>& c, int g1, int t1, int g2, int t2, T* depth, T* pdir, T* pos) {
-  const DevModel<T>& m = *c.m;
+DEX_DEV_NOINLINE bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
   SupPt<T> s[4], v4;
   T dir[3], va[3], vb[3];
-  dex_geom_center(c, g1, s[0].v1);
-  dex_geom_center(c, g2, s[0].v2);
-  for (int k = 0; k < 3; ++k) s[0].v[k] = s[0].v1[k] - s[0].v2[k];
+  {
+    const T* pa = c.A.pack;
+    const T* pb = c.B.pack;
+    T cb[3] = {dex_ldg(pb), dex_ldg(pb + 1), dex_ldg(pb + 2)}, cbw[3];
+    rot_vec(cbw, c.rel.R, cb);
+    for (int k = 0; k < 3; ++k) { s[0].v1[k] = dex_ldg(pa + k); s[0].v[k] = s[0].v1[k] - (cbw[k] + c.rel.t[k]); }
+  }
   if (ccd_zero(s[0].v[0]) && ccd_zero(s[0].v[1]) && ccd_zero(s[0].v[2])) s[0].v[0] += T(2.220446049250313e-15);
   dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
   normalize3(dir);
-  dex_mink(c, g1, t1, g2, t2, dir, s[1]);
+  dex_mink(c, dir, s[1]);
   T dt = dot3(s[1].v, dir);
   if (ccd_zero(dt) || dt < 0) return false;
   cross3(dir, s[0].v, s[1].v);
@@ -182,11 +199,11 @@ DEX_DEV bool dex_mpr(const CollideCtx<T>& c, int g1, int t1, int g2, int t2, T* 
       pdir[0] = s[1].v[0]; pdir[1] = s[1].v[1]; pdir[2] = s[1].v[2];
       normalize3(pdir);
     }
-    for (int k = 0; k < 3; ++k) pos[k] = T(0.5) * (s[1].v1[k] + s[1].v2[k]);
+    for (int k = 0; k < 3; ++k) pos[k] = s[1].v1[k] - T(0.5) * s[1].v[k];  // (v1 + v2) / 2
     return true;
   }
   normalize3(dir);
-  dex_mink(c, g1, t1, g2, t2, dir, s[2]);
+  dex_mink(c, dir, s[2]);
   dt = dot3(s[2].v, dir);
   if (ccd_zero(dt) || dt < 0) return false;
   for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
@@ -198,7 +215,7 @@ DEX_DEV bool dex_mpr(const CollideCtx<T>& c, int g1, int t1, int g2, int t2, T* 
   }
   for (int guard = 0;; ++guard) {  // discoverPortal: find v3
     if (guard > 100) return false;
-    dex_mink(c, g1, t1, g2, t2, dir, s[3]);
+    dex_mink(c, dir, s[3]);
     dt = dot3(s[3].v, dir);
     if (ccd_zero(dt) || dt < 0) return false;
     bool cont = false;
@@ -220,15 +237,15 @@ DEX_DEV bool dex_mpr(const CollideCtx<T>& c, int g1, int t1, int g2, int t2, T* 
     portal_dir(s, dir);
     dt = dot3(dir, s[1].v);
     if (ccd_zero(dt) || dt > 0) break;
-    dex_mink(c, g1, t1, g2, t2, dir, v4);
+    dex_mink(c, dir, v4);
     dt = dot3(v4.v, dir);
-    if (!(ccd_zero(dt) || dt > 0) || portal_reach_tol(s, v4, dir, m.mpr_tolerance)) return false;
+    if (!(ccd_zero(dt) || dt > 0) || portal_reach_tol(s, v4, dir, c.tolerance)) return false;
     expand_portal(s, v4);
   }
   for (int it = 0;; ++it) {  // findPenetr
     portal_dir(s, dir);
-    dex_mink(c, g1, t1, g2, t2, dir, v4);
-    if (portal_reach_tol(s, v4, dir, m.mpr_tolerance) || it > m.mpr_iterations) {
+    dex_mink(c, dir, v4);
+    if (portal_reach_tol(s, v4, dir, c.tolerance) || it > c.iterations) {
       T d2 = point_tri_dist2(s[1].v, s[2].v, s[3].v, pdir);
       *depth = dx_sqrt(d2);
       if (ccd_zero(pdir[0]) && ccd_zero(pdir[1]) && ccd_zero(pdir[2])) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; }
@@ -249,14 +266,36 @@ DEX_DEV bool dex_mpr(const CollideCtx<T>& c, int g1, int t1, int g2, int t2, T* 
       }
       T inv = T(1) / sum;
       for (int k = 0; k < 3; ++k) {
+        // p1 = sum b_i v1_i, p2 = sum b_i v2_i with v2 = v1 - v;  pos = (p1 + p2) / 2
         T p1 = b[0] * s[0].v1[k] + b[1] * s[1].v1[k] + b[2] * s[2].v1[k] + b[3] * s[3].v1[k];
-        T p2 = b[0] * s[0].v2[k] + b[1] * s[1].v2[k] + b[2] * s[2].v2[k] + b[3] * s[3].v2[k];
-        pos[k] = T(0.5) * (p1 + p2) * inv;
+        T pv = b[0] * s[0].v[k] + b[1] * s[1].v[k] + b[2] * s[2].v[k] + b[3] * s[3].v[k];
+        pos[k] = (p1 - T(0.5) * pv) * inv;
       }
       return true;
     }
     expand_portal(s, v4);
   }
+}
+
+// pose of body b2 in the frame of body b1
+template <typename T>
+DEX_DEV void dex_relative(const T* xpos, const T* xmat, int b1, int b2, Xf<T>& x) {
+  const T* R1 = xmat + 9 * b1;
+  const T* R2 = xmat + 9 * b2;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+    x.R[3 * r + c] = R1[r] * R2[c] + R1[3 + r] * R2[3 + c] + R1[6 + r] * R2[6 + c];
+  T d[3] = {xpos[3 * b2] - xpos[3 * b1], xpos[3 * b2 + 1] - xpos[3 * b1 + 1], xpos[3 * b2 + 2] - xpos[3 * b1 + 2]};
+  rotT_vec(x.t, R1, d);
+}
+
+template <typename T>
+DEX_DEV bool dex_sphere_aabb(const T* c, T r, const T* pack) {  // pack + 4: aabb centre(3), half(3)
+  T s = 0;
+  for (int k = 0; k < 3; ++k) {
+    T e = dx_abs(c[k] - dex_ldg(pack + 4 + k)) - dex_ldg(pack + 7 + k);
+    if (e > 0) s += e * e;
+  }
+  return s <= r * r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -282,7 +321,6 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   dex_syncwarp();
   KinBuf<T> kb = {xpos, xquat, xmat, nullptr, nullptr};
   dex_fk(m, qpos, kb);
-  CollideCtx<T> cx = {&m, xpos, xmat, T(0)};
 
   // ---- broadphase
   int ncand = 0;
@@ -292,15 +330,24 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     if (bp < m.nbodypair) {
       const int b1 = dex_ldg(m.bp_body1 + bp), b2 = dex_ldg(m.bp_body2 + bp);
       const T r1 = dex_ldg(m.body_bsphere + 4 * b1 + 3), r2 = dex_ldg(m.body_bsphere + 4 * b2 + 3);
-      if (r1 < 0 || r2 < 0) pass = true;  // body holds a plane: resolved per geom
-      else {
-        T c1[3], c2[3];
+      T c2[3];
+      T l2[3] = {dex_ldg(m.body_bsphere + 4 * b2), dex_ldg(m.body_bsphere + 4 * b2 + 1), dex_ldg(m.body_bsphere + 4 * b2 + 2)};
+      rot_vec(c2, xmat + 9 * b2, l2);
+      c2[0] += xpos[3 * b2]; c2[1] += xpos[3 * b2 + 1]; c2[2] += xpos[3 * b2 + 2];
+      if (r1 < 0) {  // body 1 owns a plane (planes sort first in a pair): half-space test of body 2's sphere
+        const int gp = dex_ldg(m.pair_geom1 + dex_ldg(m.bp_pairadr + bp));
+        const T* G = m.geom_mat + 9 * gp;
+        T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3], pl[3], pw[3];
+        rot_vec(n, xmat + 9 * b1, nl);
+        pl[0] = dex_ldg(m.geom_pack + DEX_GPACK * gp); pl[1] = dex_ldg(m.geom_pack + DEX_GPACK * gp + 1); pl[2] = dex_ldg(m.geom_pack + DEX_GPACK * gp + 2);
+        rot_vec(pw, xmat + 9 * b1, pl);
+        T d[3] = {c2[0] - pw[0] - xpos[3 * b1], c2[1] - pw[1] - xpos[3 * b1 + 1], c2[2] - pw[2] - xpos[3 * b1 + 2]};
+        pass = dot3(d, n) <= r2;
+      } else {
+        T c1[3];
         T l1[3] = {dex_ldg(m.body_bsphere + 4 * b1), dex_ldg(m.body_bsphere + 4 * b1 + 1), dex_ldg(m.body_bsphere + 4 * b1 + 2)};
-        T l2[3] = {dex_ldg(m.body_bsphere + 4 * b2), dex_ldg(m.body_bsphere + 4 * b2 + 1), dex_ldg(m.body_bsphere + 4 * b2 + 2)};
         rot_vec(c1, xmat + 9 * b1, l1);
-        rot_vec(c2, xmat + 9 * b2, l2);
-        T d[3] = {c2[0] + xpos[3 * b2] - c1[0] - xpos[3 * b1], c2[1] + xpos[3 * b2 + 1] - c1[1] - xpos[3 * b1 + 1],
-                  c2[2] + xpos[3 * b2 + 2] - c1[2] - xpos[3 * b1 + 2]};
+        T d[3] = {c2[0] - c1[0] - xpos[3 * b1], c2[1] - c1[1] - xpos[3 * b1 + 1], c2[2] - c1[2] - xpos[3 * b1 + 2]};
         T bound = r1 + r2;
         pass = dot3(d, d) <= bound * bound;
       }
@@ -311,30 +358,38 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
       mask &= mask - 1;
       const int bpk = bp0 + kk;
       const int adr = dex_ldg(m.bp_pairadr + bpk), num = dex_ldg(m.bp_pairnum + bpk);
+      const int b1 = dex_ldg(m.bp_body1 + bpk), b2 = dex_ldg(m.bp_body2 + bpk);
+      Xf<T> rel;
+      dex_relative(xpos, xmat, b1, b2, rel);
       for (int p0 = 0; p0 < num; p0 += 32) {
         const int p = adr + p0 + lane;
         bool ok = false;
         if (p0 + lane < num) {
           const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
           const T margin = dex_ldg(m.pair_margin + p);
-          T c1[3], c2[3];
-          dex_geom_center(cx, g1, c1);
-          dex_geom_center(cx, g2, c2);
-          T d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+          const T* pk1 = m.geom_pack + DEX_GPACK * g1;
+          const T* pk2 = m.geom_pack + DEX_GPACK * g2;
+          T c2l[3] = {dex_ldg(pk2), dex_ldg(pk2 + 1), dex_ldg(pk2 + 2)}, c2[3];
+          rot_vec(c2, rel.R, c2l);
+          c2[0] += rel.t[0]; c2[1] += rel.t[1]; c2[2] += rel.t[2];            // centre of geom 2 in frame 1
+          const T r2 = dex_ldg(pk2 + 3);
           if (dex_ldg(m.geom_type + g1) == DEX_GEOM_PLANE) {
-            const int b1 = dex_ldg(m.geom_body + g1);
-            const T* R = xmat + 9 * b1;
             const T* G = m.geom_mat + 9 * g1;
-            T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
-            rot_vec(n, R, nl);
-            ok = dot3(d, n) <= margin + dex_ldg(m.geom_rbound + g2);
+            T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)};
+            T d[3] = {c2[0] - dex_ldg(pk1), c2[1] - dex_ldg(pk1 + 1), c2[2] - dex_ldg(pk1 + 2)};
+            ok = dot3(d, nl) <= margin + r2;
           } else {
-            const T r1 = dex_ldg(m.geom_rbound + g1), r2 = dex_ldg(m.geom_rbound + g2);
-            T bound = margin + r1 + r2;
+            const T r1 = dex_ldg(pk1 + 3);
+            T c1[3] = {dex_ldg(pk1), dex_ldg(pk1 + 1), dex_ldg(pk1 + 2)};
+            T d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+            const T bound = margin + r1 + r2;
             ok = dot3(d, d) <= bound * bound;
-            // conservative refinements: bounding sphere of one geom against the body-frame AABB of the other
-            if (ok) ok = dex_sphere_vs_aabb(cx, c2, r2 + margin, g1);
-            if (ok) ok = dex_sphere_vs_aabb(cx, c1, r1 + margin, g2);
+            if (ok) ok = dex_sphere_aabb(c2, r2 + margin, pk1);               // sphere 2 vs AABB 1 (frame 1)
+            if (ok) {
+              T e[3] = {c1[0] - rel.t[0], c1[1] - rel.t[1], c1[2] - rel.t[2]}, c1in2[3];
+              rotT_vec(c1in2, rel.R, e);
+              ok = dex_sphere_aabb(c1in2, r1 + margin, pk2);                  // sphere 1 vs AABB 2 (frame 2)
+            }
           }
         }
         const unsigned m2 = dex_ballot(ok);
@@ -357,16 +412,19 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     const int p = cand[ci];
     const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
     const int t1 = dex_ldg(m.geom_type + g1), t2 = dex_ldg(m.geom_type + g2);
+    const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
     const T margin = dex_ldg(m.pair_margin + p);
     if (t1 == DEX_GEOM_PLANE) {
-      const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
       const T* G1 = m.geom_mat + 9 * g1;
       T nl[3] = {dex_ldg(G1 + 2), dex_ldg(G1 + 5), dex_ldg(G1 + 8)}, n[3], p1[3];
       rot_vec(n, xmat + 9 * b1, nl);
-      dex_geom_center(cx, g1, p1);
+      T pl[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 2)};
+      rot_vec(p1, xmat + 9 * b1, pl);
+      p1[0] += xpos[3 * b1]; p1[1] += xpos[3 * b1 + 1]; p1[2] += xpos[3 * b1 + 2];
       if (t2 == DEX_GEOM_BOX) {  // mjc_PlaneBox: lanes 0..7 test the corners, first 4 hits kept
-        T c2[3];
-        dex_geom_center(cx, g2, c2);
+        T cl[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g2), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 2)}, c2[3];
+        rot_vec(c2, xmat + 9 * b2, cl);
+        c2[0] += xpos[3 * b2]; c2[1] += xpos[3 * b2 + 1]; c2[2] += xpos[3 * b2 + 2];
         T dif[3] = {c2[0] - p1[0], c2[1] - p1[1], c2[2] - p1[2]};
         const T dist = dot3(dif, n);
         T corner[3] = {0, 0, 0};
@@ -395,9 +453,13 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
         int add = dex_popc(hm); if (add > 4) add = 4;
         if (ncon + add > DEX_MAXCON) { status |= DEX_STATUS_CON_OVERFLOW; add = DEX_MAXCON - ncon; }
         ncon += add;
-      } else if (t2 == DEX_GEOM_MESH) {  // mjc_PlaneConvex: deepest vertex (+ up to 3 hull neighbours: TODO round 2)
-        T nn[3] = {-n[0], -n[1], -n[2]}, w[3];
-        dex_support(cx, g2, t2, nn, w);
+      } else if (t2 == DEX_GEOM_MESH) {  // mjc_PlaneConvex: deepest vertex (hull-neighbour extras: next round)
+        T nn[3] = {-n[0], -n[1], -n[2]}, ld[3], w[3];
+        rotT_vec(ld, xmat + 9 * b2, nn);
+        const V3<T> sp = dex_support_ref(dex_geom_ref(m, g2, t2), ld[0], ld[1], ld[2]);
+        T sl[3] = {sp.x, sp.y, sp.z};
+        rot_vec(w, xmat + 9 * b2, sl);
+        w[0] += xpos[3 * b2]; w[1] += xpos[3 * b2 + 1]; w[2] += xpos[3 * b2 + 2];
         T dif[3] = {w[0] - p1[0], w[1] - p1[1], w[2] - p1[2]};
         const T dist = dot3(dif, n);
         if (dist <= margin) {
@@ -409,11 +471,20 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
         }
       }
     } else {
+      MprCtx<T> mc;
+      mc.A = dex_geom_ref(m, g1, t1); mc.B = dex_geom_ref(m, g2, t2); mc.half_margin = T(0.5) * margin;
+      mc.tolerance = m.mpr_tolerance; mc.iterations = m.mpr_iterations;
+      dex_relative(xpos, xmat, b1, b2, mc.rel);
       T depth, dir[3], pos[3];
-      cx.half_margin = T(0.5) * margin;
-      if (dex_mpr(cx, g1, t1, g2, t2, &depth, dir, pos) && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0)) {
+      if (dex_mpr(mc, &depth, dir, pos) && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0)) {
         if (ncon < DEX_MAXCON) {
-          if (lane == 0) dex_store_contact(cout + ncon * DEX_CON_STRIDE, margin - depth, pos, dir, p);
+          if (lane == 0) {
+            T pw[3], nw[3];
+            rot_vec(pw, xmat + 9 * b1, pos);
+            rot_vec(nw, xmat + 9 * b1, dir);
+            pw[0] += xpos[3 * b1]; pw[1] += xpos[3 * b1 + 1]; pw[2] += xpos[3 * b1 + 2];
+            dex_store_contact(cout + ncon * DEX_CON_STRIDE, margin - depth, pw, nw, p);
+          }
           ncon++;
         } else status |= DEX_STATUS_CON_OVERFLOW;
       }

@@ -202,6 +202,13 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       } else { for (int k = 0; k < 3; ++k) { lo[k] = -1e30; hi[k] = 1e30; } }
       for (int k = 0; k < 3; ++k) { M.geom_aabb[6 * g + k] = 0.5 * (lo[k] + hi[k]); M.geom_aabb[6 * g + 3 + k] = 0.5 * (hi[k] - lo[k]); }
     }
+    // packed per-geom broadphase record (DEX_GPACK = 12): centre(3) rbound | aabb centre(3) half(3) | pad(2)
+    M.geom_pack.assign(12 * M.ngeom, 0);
+    for (int g = 0; g < M.ngeom; ++g) {
+      double* pk = &M.geom_pack[12 * g];
+      for (int k = 0; k < 3; ++k) { pk[k] = M.geom_pos[3 * g + k]; pk[4 + k] = M.geom_aabb[6 * g + k]; pk[7 + k] = M.geom_aabb[6 * g + 3 + k]; }
+      pk[3] = M.geom_rbound[g];
+    }
     if (M.vert.empty()) M.vert.assign(3, 0.0);
   }
   // ---- body bounding spheres (body frame); radius < 0 marks a body that owns a plane
@@ -221,7 +228,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       r = std::max(r, std::sqrt(d2) + M.geom_rbound[g]);
     }
     for (int k = 0; k < 3; ++k) M.body_bsphere[4 * b + k] = c[k];
-    M.body_bsphere[4 * b + 3] = plane ? -1.0 : r;
+    M.body_bsphere[4 * b + 3] = plane ? (n == 1 ? -1.0 : 1e30) : r;
   }
   // ---- candidate pairs grouped by body pair (blob order is already grouped; verified here)
   M.pair_geom1 = I(DEXF_PAIR_GEOM1); M.pair_geom2 = I(DEXF_PAIR_GEOM2); M.pair_condim = I(DEXF_PAIR_CONDIM);

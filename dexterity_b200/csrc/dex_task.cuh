@@ -222,10 +222,10 @@ DEX_DEV void dex_task_post_env(const DevModel<T>& m, const BatchState<T>& st, co
       const int gbody = dex_ldg(m.geom_body + gg);
       T nl[3] = {dex_ldg(m.geom_mat + 9 * gg + 2), dex_ldg(m.geom_mat + 9 * gg + 5), dex_ldg(m.geom_mat + 9 * gg + 8)}, n[3], pp[3], gp[3];
       rot_vec(n, xmat + 9 * gbody, nl);
-      T gl[3] = {dex_ldg(m.geom_pos + 3 * gg), dex_ldg(m.geom_pos + 3 * gg + 1), dex_ldg(m.geom_pos + 3 * gg + 2)};
+      T gl[3] = {dex_ldg(m.geom_pack + 12 * gg), dex_ldg(m.geom_pack + 12 * gg + 1), dex_ldg(m.geom_pack + 12 * gg + 2)};
       rot_vec(gp, xmat + 9 * gbody, gl);
       gp[0] += xpos[3 * gbody]; gp[1] += xpos[3 * gbody + 1]; gp[2] += xpos[3 * gbody + 2];
-      T pl[3] = {dex_ldg(m.geom_pos + 3 * pg), dex_ldg(m.geom_pos + 3 * pg + 1), dex_ldg(m.geom_pos + 3 * pg + 2)};
+      T pl[3] = {dex_ldg(m.geom_pack + 12 * pg), dex_ldg(m.geom_pack + 12 * pg + 1), dex_ldg(m.geom_pack + 12 * pg + 2)};
       rot_vec(pp, xmat + 9 * pb, pl);
       T dif[3] = {pp[0] + xpos[3 * pb] - gp[0], pp[1] + xpos[3 * pb + 1] - gp[1], pp[2] + xpos[3 * pb + 2] - gp[2]};
       const T dc = dot3(dif, n);
