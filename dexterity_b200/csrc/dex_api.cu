@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_collide(DevModel<T> m, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
                                                                    int integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -153,7 +153,7 @@ struct ProfScope {  // records an event pair around one launch when profiling is
 template <typename T>
 int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, bool use_skip = false) {
   static const int req_col[] = {DEX_FIELD_QPOS, DEX_FIELD_STATUS, DEX_FIELD_CONTACT, DEX_FIELD_NCON};
-  static const int req_dyn[] = {DEX_FIELD_QVEL, DEX_FIELD_CTRL, DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER};
+  static const int req_dyn[] = {DEX_FIELD_QVEL, DEX_FIELD_CTRL, DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER, DEX_FIELD_JC};
   for (int f : req_col) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   if (need_dyn) for (int f : req_dyn) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   st.nenv = b->nenv;
@@ -167,6 +167,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.ncon = (int*)b->ptr[DEX_FIELD_NCON];
   st.niter = (int*)b->ptr[DEX_FIELD_NITER];
   st.skip = use_skip ? (const unsigned char*)b->ptr[DEX_FIELD_SKIP] : nullptr;
+  st.jc = (T*)b->ptr[DEX_FIELD_JC];
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
   dbg.qacc = (T*)b->ptr[DEX_FIELD_DBG_QACC];

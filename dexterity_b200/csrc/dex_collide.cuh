@@ -298,6 +298,38 @@ DEX_DEV bool dex_sphere_aabb(const T* c, T r, const T* pack) {  // pack + 4: aab
   return s <= r * r;
 }
 
+// Separating-axis test between the body-frame AABB of geom 1 (frame A) and that of geom 2 (frame B,
+// pose `rel` in A), both inflated by `margin`/2.  Conservative (the boxes enclose the hulls), so a
+// "separated" verdict can never remove a real contact.  Gottschalk's 15-axis OBB test.
+template <typename T>
+DEX_DEV bool dex_obb_overlap(const Xf<T>& rel, const T* pk1, const T* pk2, T margin) {
+  T ha[3], hb[3], cb[3], t[3], AR[9];
+  for (int k = 0; k < 3; ++k) {
+    ha[k] = dex_ldg(pk1 + 7 + k) + T(0.5) * margin;
+    hb[k] = dex_ldg(pk2 + 7 + k) + T(0.5) * margin;
+    cb[k] = dex_ldg(pk2 + 4 + k);
+  }
+  rot_vec(t, rel.R, cb);
+  for (int k = 0; k < 3; ++k) t[k] += rel.t[k] - dex_ldg(pk1 + 4 + k);
+  const T eps = T(1e-6);
+  for (int k = 0; k < 9; ++k) AR[k] = dx_abs(rel.R[k]) + eps;
+  const T* R = rel.R;
+  for (int i = 0; i < 3; ++i)
+    if (dx_abs(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2]) return false;
+  for (int j = 0; j < 3; ++j)
+    if (dx_abs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j]) return false;
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const T ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j];
+      const T rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+      if (dx_abs(t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j]) > ra + rb) return false;
+    }
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1 body.  smem: [xpos | xquat | xmat | qpos | cand(int)]
 // ------------------------------------------------------------------------------------------
@@ -390,6 +422,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
               rotT_vec(c1in2, rel.R, e);
               ok = dex_sphere_aabb(c1in2, r1 + margin, pk2);                  // sphere 1 vs AABB 2 (frame 2)
             }
+            if (ok) ok = dex_obb_overlap(rel, pk1, pk2, margin);              // AABB 1 vs AABB 2 as OBBs
           }
         }
         const unsigned m2 = dex_ballot(ok);

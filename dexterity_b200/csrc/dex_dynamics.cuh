@@ -16,39 +16,40 @@
 
 #include "dex_kin.cuh"
 
-#define DEX_MSTRIDE 33
-#define DEX_JSTRIDE 33
-// shared memory per warp (units of T)
+#define DEX_MSTRIDE 36   // rows 16-byte aligned; LDS.128 of 8 consecutive rows is bank-conflict free
+// shared memory per warp (units of T).  The Hessian / contact scratch (union B) aliases the tree-pass
+// temporaries (union A), which are dead once qfrc_smooth is known; the contact-frame Jacobian lives
+// in an L2-resident global scratch (BatchState::jc), not in shared memory -> ~15 KB per warp (FP32).
 #define DEX_K2_OFF_XPOS 0
 #define DEX_K2_OFF_XQUAT (DEX_K2_OFF_XPOS + DEX_MAXBODY * 3)
 #define DEX_K2_OFF_XMAT (DEX_K2_OFF_XQUAT + DEX_MAXBODY * 4)
-#define DEX_K2_OFF_XANCHOR (DEX_K2_OFF_XMAT + DEX_MAXBODY * 9)
-#define DEX_K2_OFF_XAXIS (DEX_K2_OFF_XANCHOR + DEX_MAXJNT * 3)
-#define DEX_K2_OFF_REF (DEX_K2_OFF_XAXIS + DEX_MAXJNT * 3)
-#define DEX_K2_OFF_CDOF (DEX_K2_OFF_REF + 16)
-#define DEX_K2_OFF_QPOS (DEX_K2_OFF_CDOF + DEX_MAXDOF * 6)
+#define DEX_K2_OFF_REF (DEX_K2_OFF_XMAT + DEX_MAXBODY * 9)
+#define DEX_K2_OFF_QPOS (DEX_K2_OFF_REF + 16)
 #define DEX_K2_OFF_QVEL (DEX_K2_OFF_QPOS + 48)
 #define DEX_K2_OFF_VECA (DEX_K2_OFF_QVEL + 32)
 #define DEX_K2_OFF_VECB (DEX_K2_OFF_VECA + 32)
-#define DEX_K2_OFF_DINV (DEX_K2_OFF_VECB + 32)
-#define DEX_K2_OFF_M (DEX_K2_OFF_DINV + 32)
-#define DEX_K2_OFF_H (DEX_K2_OFF_M + 32 * DEX_MSTRIDE)
-#define DEX_K2_OFF_UNION (DEX_K2_OFF_H + 32 * DEX_MSTRIDE)
+#define DEX_K2_OFF_M (DEX_K2_OFF_VECB + 32)
+#define DEX_K2_OFF_UNION (DEX_K2_OFF_M + 32 * DEX_MSTRIDE)
 //   union A (tree passes)
-#define DEX_K2_OFF_CINERT DEX_K2_OFF_UNION
+#define DEX_K2_OFF_XANCHOR DEX_K2_OFF_UNION
+#define DEX_K2_OFF_XAXIS (DEX_K2_OFF_XANCHOR + DEX_MAXJNT * 3)
+#define DEX_K2_OFF_CDOF (DEX_K2_OFF_XAXIS + DEX_MAXJNT * 3)
+#define DEX_K2_OFF_CINERT (DEX_K2_OFF_CDOF + DEX_MAXDOF * 6)
 #define DEX_K2_OFF_CRB (DEX_K2_OFF_CINERT + DEX_MAXBODY * 10)
 #define DEX_K2_OFF_CVEL (DEX_K2_OFF_CRB + DEX_MAXBODY * 10)
 #define DEX_K2_OFF_CDOFDOT (DEX_K2_OFF_CVEL + DEX_MAXBODY * 6)
 #define DEX_K2_OFF_CACC (DEX_K2_OFF_CDOFDOT + DEX_MAXDOF * 6)
 #define DEX_K2_OFF_CFRC (DEX_K2_OFF_CACC + DEX_MAXBODY * 6)
-#define DEX_K2_UNION_A (DEX_MAXBODY * 38 + DEX_MAXDOF * 6)
-//   union B (constraints)
-#define DEX_K2_OFF_JC DEX_K2_OFF_UNION
-#define DEX_K2_OFF_CDAT (DEX_K2_OFF_JC + DEX_MAXCON * 3 * DEX_JSTRIDE)
+#define DEX_K2_UNION_A (DEX_MAXJNT * 6 + DEX_MAXDOF * 12 + DEX_MAXBODY * 38)
+//   union B (constraints + solver)
+#define DEX_K2_OFF_H DEX_K2_OFF_UNION
+#define DEX_K2_OFF_CDAT (DEX_K2_OFF_H + 32 * DEX_MSTRIDE)
 #define DEX_CDAT_STRIDE 24
 #define DEX_K2_OFF_CDOT (DEX_K2_OFF_CDAT + DEX_MAXCON * DEX_CDAT_STRIDE)
-#define DEX_K2_UNION_B (DEX_MAXCON * 3 * DEX_JSTRIDE + DEX_MAXCON * DEX_CDAT_STRIDE + 96)
+#define DEX_K2_UNION_B (32 * DEX_MSTRIDE + DEX_MAXCON * DEX_CDAT_STRIDE + 96)
 #define DEX_K2_SMEM_T (DEX_K2_OFF_UNION + (DEX_K2_UNION_A > DEX_K2_UNION_B ? DEX_K2_UNION_A : DEX_K2_UNION_B))
+#define DEX_JC_ROW 32                         // global Jc scratch: [env][3 * DEX_MAXCON][DEX_JC_ROW]
+#define DEX_JC_ENV (3 * DEX_MAXCON * DEX_JC_ROW)
 
 // cdat layout per contact
 enum { CD_MU = 0, CD_D = 1, CD_AREF = 2 /*4*/, CD_JAR = 6 /*4*/, CD_JV = 10 /*4*/, CD_F = 14 /*3 frame-space force*/,
@@ -94,40 +95,53 @@ DEX_DEV void dex_kb(const T* solref, const T* solimp, T timestep, T* K, T* B) {
   }
 }
 
-// In-place lower Cholesky of the nv x nv matrix A (smem, stride DEX_MSTRIDE), lane = row.
-// dinv[k] = 1 / L[k][k].  Returns false (warp-uniform) if a pivot is not positive.
+// sum_{j<k4} a[j] b[j] for 16-byte aligned rows, k4 a multiple of 4: two 128-bit shared loads per 4 terms
+template <typename T> struct alignas(16) DexVec4 { T x, y, z, w; };
 template <typename T>
-DEX_DEV bool dex_cholesky(T* A, T* dinv, int nv) {
+DEX_DEV T dex_dot4(const T* a, const T* b, int k4) {
+  T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int j = 0; j < k4; j += 4) {
+    const DexVec4<T> va = *reinterpret_cast<const DexVec4<T>*>(a + j);
+    const DexVec4<T> vb = *reinterpret_cast<const DexVec4<T>*>(b + j);
+    s0 += va.x * vb.x; s1 += va.y * vb.y; s2 += va.z * vb.z; s3 += va.w * vb.w;
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+// Solves H x = b for the SPD nv x nv matrix H (smem, stride DEX_MSTRIDE, lower triangle read and
+// overwritten by L; the strictly upper part of every row is zeroed so the dot products can run over
+// whole 4-element groups).  Left-looking Cholesky, lane = row, tiny code (the r01b profile showed a
+// fully unrolled register version losing to instruction-cache misses).  Lane i holds b_i / returns x_i.
+template <typename T>
+DEX_DEV_NOINLINE T dex_chol_solve(T* H, int nv, T b, int* fail) {
   const int i = dex_lane();
-  bool ok = true;
+  T* rowi = H + i * DEX_MSTRIDE;
+  for (int j = i + 1; j < DEX_MSTRIDE; ++j) rowi[j] = 0;       // zero the upper part (and the padding)
+  if (i >= nv) { for (int j = 0; j <= i; ++j) rowi[j] = (j == i) ? T(1) : T(0); }
+  dex_syncwarp();
+  bool bad = false;
+  T inv_mine = 1;
   for (int k = 0; k < nv; ++k) {
-    T s = (i >= k && i < nv) ? A[i * DEX_MSTRIDE + k] : T(0);
-    const T* rowi = A + (i < nv ? i : 0) * DEX_MSTRIDE;
-    const T* rowk = A + k * DEX_MSTRIDE;
-    for (int j = 0; j < k; ++j) s -= rowi[j] * rowk[j];
+    const T* rowk = H + k * DEX_MSTRIDE;
+    const int k4 = k & ~3;
+    T s = rowi[k] - dex_dot4(rowi, rowk, k4);
+    for (int j = k4; j < k; ++j) s -= rowi[j] * rowk[j];
     T dkk = dex_shfl(s, k);
-    if (!(dkk > Real<T>::minval())) { ok = false; dkk = Real<T>::minval(); }
-    T inv = T(1) / dx_sqrt(dkk);
-    if (i >= k && i < nv) A[i * DEX_MSTRIDE + k] = s * inv;
-    if (i == k) dinv[k] = inv;
+    if (!(dkk > Real<T>::minval())) { bad = true; dkk = Real<T>::minval(); }
+    const T inv = T(1) / dx_sqrt(dkk);
+    if (i == k) inv_mine = inv;
+    if (i >= k && i < nv) rowi[k] = s * inv;
     dex_syncwarp();
   }
-  return ok;
-}
-// Solves L L^T x = b; lane i holds b_i on entry and x_i on return.
-template <typename T>
-DEX_DEV T dex_chol_solve(const T* L, const T* dinv, int nv, T b) {
-  const int i = dex_lane();
-  for (int k = 0; k < nv; ++k) {
-    T yk = dex_shfl(b, k) * dinv[k];
-    if (i == k) b = yk;
-    else if (i > k && i < nv) b -= L[i * DEX_MSTRIDE + k] * yk;
+  if (bad) *fail = 1;
+  for (int k = 0; k < nv; ++k) {                                 // L y = b
+    const T yk = dex_shfl(b * inv_mine, k);
+    if (i == k) b = yk; else if (i > k && i < nv) b -= rowi[k] * yk;
   }
-  for (int k = nv - 1; k >= 0; --k) {
-    T xk = dex_shfl(b, k) * dinv[k];
-    if (i == k) b = xk;
-    else if (i < k) b -= L[k * DEX_MSTRIDE + i] * xk;
+  for (int k = nv - 1; k >= 0; --k) {                            // L^T x = y
+    const T xk = dex_shfl(b * inv_mine, k);
+    if (i == k) b = xk; else if (i < k) b -= H[k * DEX_MSTRIDE + i] * xk;
   }
+  dex_syncwarp();
   return b;
 }
 // y_i = sum_j M[i][j] x_j with x in smem (nv entries), lane = row
@@ -139,14 +153,14 @@ DEX_DEV T dex_matvec(const T* M, const T* x, int nv) {
   for (int j = 0; j < nv; ++j) s += row[j] * x[j];
   return i < nv ? s : T(0);
 }
-// out[t] = Jc[t] . x  for the 3*ncon contact-frame Jacobian rows (one row per lane per round)
+// out[t] = Jc[t] . x for the 3*ncon contact-frame Jacobian rows.  Jc is the env's global (L2) scratch,
+// read coalesced with lane = dof; xi is this lane's component of x.
 template <typename T>
-DEX_DEV void dex_contact_dots(const T* Jc, const T* x, int nrows, int nv, T* out) {
-  for (int t = dex_lane(); t < nrows; t += 32) {
-    const T* row = Jc + t * DEX_JSTRIDE;
-    T s = 0;
-    for (int j = 0; j < nv; ++j) s += row[j] * x[j];
-    out[t] = s;
+DEX_DEV void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
+  const int lane = dex_lane();
+  for (int t = 0; t < nrows; ++t) {
+    const T s = dex_warp_sum(Jc[t * DEX_JC_ROW + lane] * xi);
+    if (lane == 0) out[t] = s;
   }
   dex_syncwarp();
 }
@@ -168,7 +182,6 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   T* qvel = smem + DEX_K2_OFF_QVEL;
   T* vecA = smem + DEX_K2_OFF_VECA;
   T* vecB = smem + DEX_K2_OFF_VECB;
-  T* dinv = smem + DEX_K2_OFF_DINV;
   T* M = smem + DEX_K2_OFF_M;
   T* H = smem + DEX_K2_OFF_H;
   T* cinert = smem + DEX_K2_OFF_CINERT;
@@ -177,7 +190,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   T* cdofdot = smem + DEX_K2_OFF_CDOFDOT;
   T* cacc = smem + DEX_K2_OFF_CACC;
   T* cfrc = smem + DEX_K2_OFF_CFRC;
-  T* Jc = smem + DEX_K2_OFF_JC;
+  T* Jc = st.jc + (size_t)env * DEX_JC_ENV;  // global scratch (L2 resident)
   T* cdat = smem + DEX_K2_OFF_CDAT;
   T* cdot = smem + DEX_K2_OFF_CDOT;
   const T h = m.timestep;
@@ -427,13 +440,13 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
         j0 = sgn * dot3(frame, v); j1 = sgn * dot3(frame + 3, v); j2 = sgn * dot3(frame + 6, v);
       }
     }
-    Jc[(3 * c) * DEX_JSTRIDE + lane] = j0;
-    Jc[(3 * c + 1) * DEX_JSTRIDE + lane] = j1;
-    Jc[(3 * c + 2) * DEX_JSTRIDE + lane] = j2;
+    Jc[(3 * c) * DEX_JC_ROW + lane] = j0;
+    Jc[(3 * c + 1) * DEX_JC_ROW + lane] = j1;
+    Jc[(3 * c + 2) * DEX_JC_ROW + lane] = j2;
     if (lane == 0) *(int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK) = (int)(m1 | m2);
   }
   dex_syncwarp();
-  dex_contact_dots(Jc, qvel, 3 * ncon, nv, cdot);  // contact-frame velocities
+  dex_contact_dots(Jc, qv, 3 * ncon, cdot);  // contact-frame velocities
   if (lane < ncon) {  // lane = contact: impedance, R, aref of the 4 pyramid rows
     const int c = lane;
     const T* cc = cin + c * DEX_CON_STRIDE;
@@ -472,7 +485,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   vecA[lane] = qacc;
   dex_syncwarp();
   T Ma = dex_matvec(M, vecA, nv);
-  dex_contact_dots(Jc, vecA, 3 * ncon, nv, cdot);
+  dex_contact_dots(Jc, qacc, 3 * ncon, cdot);
   if (lane < ncon) {
     T* cdt = cdat + lane * DEX_CDAT_STRIDE;
     const T mu = cdt[CD_MU], an = cdot[3 * lane], a1 = cdot[3 * lane + 1], a2 = cdot[3 * lane + 2];
@@ -525,8 +538,8 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     if (isdof) {
       for (int c = 0; c < ncon; ++c) {
         const T* cdt = cdat + c * DEX_CDAT_STRIDE;
-        jtf += Jc[(3 * c) * DEX_JSTRIDE + lane] * cdt[CD_F] + Jc[(3 * c + 1) * DEX_JSTRIDE + lane] * cdt[CD_F + 1] +
-               Jc[(3 * c + 2) * DEX_JSTRIDE + lane] * cdt[CD_F + 2];
+        jtf += Jc[(3 * c) * DEX_JC_ROW + lane] * cdt[CD_F] + Jc[(3 * c + 1) * DEX_JC_ROW + lane] * cdt[CD_F + 1] +
+               Jc[(3 * c + 2) * DEX_JC_ROW + lane] * cdt[CD_F + 2];
       }
     }
     grad = isdof ? (Ma - fs - jtf) : T(0);
@@ -551,27 +564,26 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
       if (w00 == 0) continue;  // no active row (warp-uniform)
       unsigned mask = (unsigned)*(const int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK);
-      const T* J0 = Jc + (3 * c) * DEX_JSTRIDE;
-      const T* J1 = J0 + DEX_JSTRIDE;
-      const T* J2 = J1 + DEX_JSTRIDE;
-      const T a0 = J0[lane], a1 = J1[lane], a2 = J2[lane];
+      const T a0 = Jc[(3 * c) * DEX_JC_ROW + lane], a1 = Jc[(3 * c + 1) * DEX_JC_ROW + lane], a2 = Jc[(3 * c + 2) * DEX_JC_ROW + lane];
       const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
       const bool mine = isdof && ((mask >> lane) & 1u);
       while (mask) {
         const int j = dex_ffs(mask) - 1;
         mask &= mask - 1;
-        if (mine) H[lane * DEX_MSTRIDE + j] += t0 * J0[j] + t1 * J1[j] + t2 * J2[j];
+        const T b0 = dex_shfl(a0, j), b1 = dex_shfl(a1, j), b2 = dex_shfl(a2, j);
+        if (mine) H[lane * DEX_MSTRIDE + j] += t0 * b0 + t1 * b1 + t2 * b2;
       }
     }
     dex_syncwarp();
-    if (!dex_cholesky(H, dinv, nv)) status |= DEX_STATUS_CHOL_FAIL;
-    const T search = dex_chol_solve(H, dinv, nv, isdof ? -grad : T(0));
+    int cfail = 0;
+    const T search = dex_chol_solve(H, nv, isdof ? -grad : T(0), &cfail);
+    if (cfail) status |= DEX_STATUS_CHOL_FAIL;
 
     // ---- exact line search along `search` (PrimalSearch)
     vecB[lane] = isdof ? search : T(0);
     dex_syncwarp();
     const T Mv = dex_matvec(M, vecB, nv);
-    dex_contact_dots(Jc, vecB, 3 * ncon, nv, cdot);
+    dex_contact_dots(Jc, isdof ? search : T(0), 3 * ncon, cdot);
     if (lane < ncon) {
       T* cdt = cdat + lane * DEX_CDAT_STRIDE;
       const T mu = cdt[CD_MU], sn = cdot[3 * lane], s1 = cdot[3 * lane + 1], s2 = cdot[3 * lane + 2];
@@ -645,8 +657,8 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     H[lane * DEX_MSTRIDE + lane] += h * damping;
   }
   dex_syncwarp();
-  dex_cholesky(H, dinv, nv);
-  const T qacc_e = dex_chol_solve(H, dinv, nv, isdof ? (fs + qfrc_constraint) : T(0));
+  int efail = 0;
+  const T qacc_e = dex_chol_solve(H, nv, isdof ? (fs + qfrc_constraint) : T(0), &efail);
   const T qv_new = qv + h * qacc_e;
   dex_syncwarp();
   qvel[lane] = qv_new;

@@ -79,6 +79,7 @@ struct BatchState {
   int* ncon;                      // [nenv]
   int* niter;                     // [nenv] solver iterations of the last mj_step
   const unsigned char* skip;      // optional [nenv]: 1 = leave this env untouched (it was just reset)
+  T* jc;                          // [nenv][3*DEX_MAXCON][32] contact-frame Jacobian scratch (L2 resident)
 };
 
 // ---------------------------------------------------------------------------------------
