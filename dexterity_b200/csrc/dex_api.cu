@@ -73,7 +73,7 @@ struct DeviceArrays {
   int upload(const HostModel& h) {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
-    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations;
+    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep;
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia;
@@ -153,7 +153,7 @@ struct ProfScope {  // records an event pair around one launch when profiling is
 template <typename T>
 int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, bool use_skip = false) {
   static const int req_col[] = {DEX_FIELD_QPOS, DEX_FIELD_STATUS, DEX_FIELD_CONTACT, DEX_FIELD_NCON};
-  static const int req_dyn[] = {DEX_FIELD_QVEL, DEX_FIELD_CTRL, DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER, DEX_FIELD_JC};
+  static const int req_dyn[] = {DEX_FIELD_QVEL, DEX_FIELD_CTRL, DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER, DEX_FIELD_JC, DEX_FIELD_MSCR};
   for (int f : req_col) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   if (need_dyn) for (int f : req_dyn) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   st.nenv = b->nenv;
@@ -168,6 +168,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.niter = (int*)b->ptr[DEX_FIELD_NITER];
   st.skip = use_skip ? (const unsigned char*)b->ptr[DEX_FIELD_SKIP] : nullptr;
   st.jc = (T*)b->ptr[DEX_FIELD_JC];
+  st.mscr = (T*)b->ptr[DEX_FIELD_MSCR];
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
   dbg.qacc = (T*)b->ptr[DEX_FIELD_DBG_QACC];

@@ -28,19 +28,17 @@
 #define DEX_K2_OFF_QVEL (DEX_K2_OFF_QPOS + 48)
 #define DEX_K2_OFF_VECA (DEX_K2_OFF_QVEL + 32)
 #define DEX_K2_OFF_VECB (DEX_K2_OFF_VECA + 32)
-#define DEX_K2_OFF_M (DEX_K2_OFF_VECB + 32)
-#define DEX_K2_OFF_UNION (DEX_K2_OFF_M + 32 * DEX_MSTRIDE)
+#define DEX_K2_OFF_UNION (DEX_K2_OFF_VECB + 32)
 //   union A (tree passes)
 #define DEX_K2_OFF_XANCHOR DEX_K2_OFF_UNION
 #define DEX_K2_OFF_XAXIS (DEX_K2_OFF_XANCHOR + DEX_MAXJNT * 3)
 #define DEX_K2_OFF_CDOF (DEX_K2_OFF_XAXIS + DEX_MAXJNT * 3)
 #define DEX_K2_OFF_CINERT (DEX_K2_OFF_CDOF + DEX_MAXDOF * 6)
-#define DEX_K2_OFF_CRB (DEX_K2_OFF_CINERT + DEX_MAXBODY * 10)
-#define DEX_K2_OFF_CVEL (DEX_K2_OFF_CRB + DEX_MAXBODY * 10)
+#define DEX_K2_OFF_CVEL (DEX_K2_OFF_CINERT + DEX_MAXBODY * 10)
 #define DEX_K2_OFF_CDOFDOT (DEX_K2_OFF_CVEL + DEX_MAXBODY * 6)
 #define DEX_K2_OFF_CACC (DEX_K2_OFF_CDOFDOT + DEX_MAXDOF * 6)
 #define DEX_K2_OFF_CFRC (DEX_K2_OFF_CACC + DEX_MAXBODY * 6)
-#define DEX_K2_UNION_A (DEX_MAXJNT * 6 + DEX_MAXDOF * 12 + DEX_MAXBODY * 38)
+#define DEX_K2_UNION_A (DEX_MAXJNT * 6 + DEX_MAXDOF * 12 + DEX_MAXBODY * 28)
 //   union B (constraints + solver)
 #define DEX_K2_OFF_H DEX_K2_OFF_UNION
 #define DEX_K2_OFF_CDAT (DEX_K2_OFF_H + 32 * DEX_MSTRIDE)
@@ -50,6 +48,7 @@
 #define DEX_K2_SMEM_T (DEX_K2_OFF_UNION + (DEX_K2_UNION_A > DEX_K2_UNION_B ? DEX_K2_UNION_A : DEX_K2_UNION_B))
 #define DEX_JC_ROW 32                         // global Jc scratch: [env][3 * DEX_MAXCON][DEX_JC_ROW]
 #define DEX_JC_ENV (3 * DEX_MAXCON * DEX_JC_ROW)
+#define DEX_MG_ENV (32 * 32)                  // global M scratch: [env][32][32] (symmetric, row j = M[j][:])
 
 // cdat layout per contact
 enum { CD_MU = 0, CD_D = 1, CD_AREF = 2 /*4*/, CD_JAR = 6 /*4*/, CD_JV = 10 /*4*/, CD_F = 14 /*3 frame-space force*/,
@@ -107,20 +106,21 @@ DEX_DEV T dex_dot4(const T* a, const T* b, int k4) {
   }
   return (s0 + s1) + (s2 + s3);
 }
-// Solves H x = b for the SPD nv x nv matrix H (smem, stride DEX_MSTRIDE, lower triangle read and
-// overwritten by L; the strictly upper part of every row is zeroed so the dot products can run over
-// whole 4-element groups).  Left-looking Cholesky, lane = row, tiny code (the r01b profile showed a
-// fully unrolled register version losing to instruction-cache misses).  Lane i holds b_i / returns x_i.
+// Cholesky of the SPD n x n matrix H (smem, stride DEX_MSTRIDE, lower triangle read and overwritten
+// by L; the strictly upper part of every row is zeroed so the dot products can run over whole
+// 4-element groups; rows >= n are padded with the identity).  Left-looking, lane = row, tiny code
+// (the r01b profile showed a fully unrolled register version losing to instruction-cache misses).
+// Returns 1 / L[i][i] for lane i.
 template <typename T>
-DEX_DEV_NOINLINE T dex_chol_solve(T* H, int nv, T b, int* fail) {
+DEX_DEV_NOINLINE T dex_chol_factor(T* H, int n, int* fail) {
   const int i = dex_lane();
   T* rowi = H + i * DEX_MSTRIDE;
-  for (int j = i + 1; j < DEX_MSTRIDE; ++j) rowi[j] = 0;       // zero the upper part (and the padding)
-  if (i >= nv) { for (int j = 0; j <= i; ++j) rowi[j] = (j == i) ? T(1) : T(0); }
+  for (int j = i + 1; j < DEX_MSTRIDE; ++j) rowi[j] = 0;
+  if (i >= n) { for (int j = 0; j <= i; ++j) rowi[j] = (j == i) ? T(1) : T(0); }
   dex_syncwarp();
   bool bad = false;
   T inv_mine = 1;
-  for (int k = 0; k < nv; ++k) {
+  for (int k = 0; k < n; ++k) {
     const T* rowk = H + k * DEX_MSTRIDE;
     const int k4 = k & ~3;
     T s = rowi[k] - dex_dot4(rowi, rowk, k4);
@@ -129,29 +129,37 @@ DEX_DEV_NOINLINE T dex_chol_solve(T* H, int nv, T b, int* fail) {
     if (!(dkk > Real<T>::minval())) { bad = true; dkk = Real<T>::minval(); }
     const T inv = T(1) / dx_sqrt(dkk);
     if (i == k) inv_mine = inv;
-    if (i >= k && i < nv) rowi[k] = s * inv;
+    if (i >= k && i < n) rowi[k] = s * inv;
     dex_syncwarp();
   }
   if (bad) *fail = 1;
-  for (int k = 0; k < nv; ++k) {                                 // L y = b
+  return inv_mine;
+}
+// Solves L L^T x = b with the factor left in H by dex_chol_factor; lane i holds b_i / returns x_i.
+template <typename T>
+DEX_DEV_NOINLINE T dex_chol_apply(const T* H, int n, T inv_mine, T b) {
+  const int i = dex_lane();
+  const T* rowi = H + i * DEX_MSTRIDE;
+  for (int k = 0; k < n; ++k) {
     const T yk = dex_shfl(b * inv_mine, k);
-    if (i == k) b = yk; else if (i > k && i < nv) b -= rowi[k] * yk;
+    if (i == k) b = yk; else if (i > k && i < n) b -= rowi[k] * yk;
   }
-  for (int k = nv - 1; k >= 0; --k) {                            // L^T x = y
+  for (int k = n - 1; k >= 0; --k) {
     const T xk = dex_shfl(b * inv_mine, k);
     if (i == k) b = xk; else if (i < k) b -= H[k * DEX_MSTRIDE + i] * xk;
   }
-  dex_syncwarp();
   return b;
 }
-// y_i = sum_j M[i][j] x_j with x in smem (nv entries), lane = row
+// y_i = sum_j M[j][i] x_j (M symmetric) with M in the env's global scratch (rows of 32, read coalesced
+// with lane = column) and x in shared memory.
 template <typename T>
-DEX_DEV T dex_matvec(const T* M, const T* x, int nv) {
+DEX_DEV T dex_matvec(const T* Mg, const T* x, int nv) {
   const int i = dex_lane();
-  const T* row = M + (i < nv ? i : 0) * DEX_MSTRIDE;
-  T s = 0;
-  for (int j = 0; j < nv; ++j) s += row[j] * x[j];
-  return i < nv ? s : T(0);
+  T s0 = 0, s1 = 0;
+  int j = 0;
+  for (; j + 1 < nv; j += 2) { s0 += Mg[j * 32 + i] * x[j]; s1 += Mg[(j + 1) * 32 + i] * x[j + 1]; }
+  if (j < nv) s0 += Mg[j * 32 + i] * x[j];
+  return i < nv ? s0 + s1 : T(0);
 }
 // out[t] = Jc[t] . x for the 3*ncon contact-frame Jacobian rows.  Jc is the env's global (L2) scratch,
 // read coalesced with lane = dof; xi is this lane's component of x.
@@ -182,10 +190,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   T* qvel = smem + DEX_K2_OFF_QVEL;
   T* vecA = smem + DEX_K2_OFF_VECA;
   T* vecB = smem + DEX_K2_OFF_VECB;
-  T* M = smem + DEX_K2_OFF_M;
+  T* M = st.mscr + (size_t)env * DEX_MG_ENV;  // global scratch (L2 resident), symmetric
   T* H = smem + DEX_K2_OFF_H;
   T* cinert = smem + DEX_K2_OFF_CINERT;
-  T* crb = smem + DEX_K2_OFF_CRB;
+  T* crb = cinert;  // composite inertias are accumulated in place once the RNE pass has used cinert
   T* cvel = smem + DEX_K2_OFF_CVEL;
   T* cdofdot = smem + DEX_K2_OFF_CDOFDOT;
   T* cacc = smem + DEX_K2_OFF_CACC;
@@ -248,7 +256,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     c[4] = Iw[4] - mass * off[0] * off[2];
     c[5] = Iw[5] - mass * off[1] * off[2];
     c[6] = mass * off[0]; c[7] = mass * off[1]; c[8] = mass * off[2]; c[9] = mass;
-    for (int k = 0; k < 10; ++k) { cinert[10 * b + k] = c[k]; crb[10 * b + k] = c[k]; }
+    for (int k = 0; k < 10; ++k) cinert[10 * b + k] = c[k];
     // external spatial force about the reference point: [tau + off x f ; f]
     const T* xf = m.body_xfrc + 6 * b;
     T f[3] = {dex_ldg(xf), dex_ldg(xf + 1), dex_ldg(xf + 2)}, tq[3];
@@ -256,29 +264,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     cfrc[6 * b] = -(dex_ldg(xf + 3) + tq[0]); cfrc[6 * b + 1] = -(dex_ldg(xf + 4) + tq[1]); cfrc[6 * b + 2] = -(dex_ldg(xf + 5) + tq[2]);
     cfrc[6 * b + 3] = -f[0]; cfrc[6 * b + 4] = -f[1]; cfrc[6 * b + 5] = -f[2];
   }
-  for (int t = lane; t < 32 * DEX_MSTRIDE; t += 32) M[t] = 0;
-  dex_syncwarp();
-
-  // ------------------------------------------------------------------ composite inertia (backward), M
-  for (int L = m.maxdepth; L >= 1; --L) {
-    for (int b = lane; b < nb; b += 32) {
-      if (dex_ldg(m.body_depth + b) != L) continue;
-      const int p = dex_ldg(m.body_parent + b);
-      if (p > 0) for (int k = 0; k < 10; ++k) dex_atomic_add(crb + 10 * p + k, crb[10 * b + k]);
-    }
-    dex_syncwarp();
-  }
-  if (isdof) {
-    T buf[6];
-    mul_inert_vec(buf, crb + 10 * dbody, cd);
-    for (int j = lane; j >= 0; j = dex_ldg(m.dof_parent + j)) {
-      const T* cj = cdof + 6 * j;
-      T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
-      if (j == lane) s += dex_ldg(m.dof_armature + lane);
-      M[lane * DEX_MSTRIDE + j] = s;
-      M[j * DEX_MSTRIDE + lane] = s;
-    }
-  }
+  for (int t = lane; t < DEX_MG_ENV; t += 32) M[t] = 0;
   dex_syncwarp();
 
   // ------------------------------------------------------------------ mj_comVel + mj_rne (forward), lane = body by level
@@ -341,6 +327,28 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     const T* cf = cfrc + 6 * dbody;
     bias = cd[0] * cf[0] + cd[1] * cf[1] + cd[2] * cf[2] + cd[3] * cf[3] + cd[4] * cf[4] + cd[5] * cf[5];
   }
+
+  // ------------------------------------------------------------------ composite inertia (backward), M
+  for (int L = m.maxdepth; L >= 1; --L) {
+    for (int b = lane; b < nb; b += 32) {
+      if (dex_ldg(m.body_depth + b) != L) continue;
+      const int p = dex_ldg(m.body_parent + b);
+      if (p > 0) for (int k = 0; k < 10; ++k) dex_atomic_add(crb + 10 * p + k, crb[10 * b + k]);
+    }
+    dex_syncwarp();
+  }
+  if (isdof) {
+    T buf[6];
+    mul_inert_vec(buf, crb + 10 * dbody, cd);
+    for (int j = lane; j >= 0; j = dex_ldg(m.dof_parent + j)) {
+      const T* cj = cdof + 6 * j;
+      T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+      if (j == lane) s += dex_ldg(m.dof_armature + lane);
+      M[lane * 32 + j] = s;
+      M[j * 32 + lane] = s;
+    }
+  }
+  dex_syncwarp();
 
   // ------------------------------------------------------------------ actuation (lane = actuator), passive
   vecA[lane] = 0;
@@ -494,12 +502,14 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     cdt[CD_JAR + 2] = an + mu * a2 - cdt[CD_AREF + 2];
     cdt[CD_JAR + 3] = an - mu * a2 - cdt[CD_AREF + 3];
   }
-  T grad = 0, cost = 0, oldcost = 0, gnorm_prev = 0;
+  T grad = 0, cost = 0, oldcost = 0, gnorm_prev = 0, hinv = 1, hdiag_prev = 0;
+  int asig_prev = -1;
   int iter = 0;
   const int maxiter = m.iterations;
   for (;; ++iter) {
     // ---- forces, active sets, cost (PrimalUpdateConstraint)
     T mycost = 0, fdof = 0, hdiag = 0;
+    int asig = 0;
     if (isdof) {
       mycost = T(0.5) * qacc * Ma - qacc * fs;
       if (f_loss > 0) {
@@ -519,7 +529,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       T f[4], w[4];
       for (int r = 0; r < 4; ++r) {
         const T x = cdt[CD_JAR + r];
-        if (x < 0) { f[r] = -D * x; w[r] = D; mycost += T(0.5) * D * x * x; } else { f[r] = 0; w[r] = 0; }
+        if (x < 0) { f[r] = -D * x; w[r] = D; mycost += T(0.5) * D * x * x; asig |= 1 << r; } else { f[r] = 0; w[r] = 0; }
       }
       cdt[CD_F + 0] = f[0] + f[1] + f[2] + f[3];
       cdt[CD_F + 1] = mu * (f[0] - f[1]);
@@ -554,30 +564,35 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     gnorm_prev = gnorm;
     if (iter >= maxiter) { status |= DEX_STATUS_SOLVER_MAXITER; break; }
 
-    // ---- Hessian H = M + J^T D_active J, Cholesky, search = -H^{-1} grad
-    if (isdof) {
-      for (int j = 0; j < nv; ++j) H[lane * DEX_MSTRIDE + j] = M[lane * DEX_MSTRIDE + j];
-      H[lane * DEX_MSTRIDE + lane] += hdiag;
-    }
-    for (int c = 0; c < ncon; ++c) {
-      const T* cdt = cdat + c * DEX_CDAT_STRIDE;
-      const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
-      if (w00 == 0) continue;  // no active row (warp-uniform)
-      unsigned mask = (unsigned)*(const int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK);
-      const T a0 = Jc[(3 * c) * DEX_JC_ROW + lane], a1 = Jc[(3 * c + 1) * DEX_JC_ROW + lane], a2 = Jc[(3 * c + 2) * DEX_JC_ROW + lane];
-      const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
-      const bool mine = isdof && ((mask >> lane) & 1u);
-      while (mask) {
-        const int j = dex_ffs(mask) - 1;
-        mask &= mask - 1;
-        const T b0 = dex_shfl(a0, j), b1 = dex_shfl(a1, j), b2 = dex_shfl(a2, j);
-        if (mine) H[lane * DEX_MSTRIDE + j] += t0 * b0 + t1 * b1 + t2 * b2;
+    // ---- Hessian H = M + J^T D_active J, Cholesky, search = -H^{-1} grad.  The factor is reused
+    // when the active set (hence H) is the same as in the previous iteration.
+    const unsigned sig_changed = dex_ballot(asig != asig_prev || hdiag != hdiag_prev);
+    asig_prev = asig; hdiag_prev = hdiag;
+    if (iter == 0 || sig_changed) {
+      for (int j = 0; j < nv; ++j) H[j * DEX_MSTRIDE + lane] = M[j * 32 + lane];   // H[j][lane] = M[j][lane]
+      dex_syncwarp();
+      if (isdof) H[lane * DEX_MSTRIDE + lane] += hdiag;
+      for (int c = 0; c < ncon; ++c) {
+        const T* cdt = cdat + c * DEX_CDAT_STRIDE;
+        const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
+        if (w00 == 0) continue;  // no active row (warp-uniform)
+        unsigned mask = (unsigned)*(const int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK);
+        const T a0 = Jc[(3 * c) * DEX_JC_ROW + lane], a1 = Jc[(3 * c + 1) * DEX_JC_ROW + lane], a2 = Jc[(3 * c + 2) * DEX_JC_ROW + lane];
+        const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
+        const bool mine = isdof && ((mask >> lane) & 1u);
+        while (mask) {
+          const int j = dex_ffs(mask) - 1;
+          mask &= mask - 1;
+          const T b0 = dex_shfl(a0, j), b1 = dex_shfl(a1, j), b2 = dex_shfl(a2, j);
+          if (mine) H[lane * DEX_MSTRIDE + j] += t0 * b0 + t1 * b1 + t2 * b2;
+        }
       }
+      dex_syncwarp();
+      int cfail = 0;
+      hinv = dex_chol_factor(H, nv, &cfail);
+      if (cfail) status |= DEX_STATUS_CHOL_FAIL;
     }
-    dex_syncwarp();
-    int cfail = 0;
-    const T search = dex_chol_solve(H, nv, isdof ? -grad : T(0), &cfail);
-    if (cfail) status |= DEX_STATUS_CHOL_FAIL;
+    const T search = dex_chol_apply(H, nv, hinv, isdof ? -grad : T(0));
 
     // ---- exact line search along `search` (PrimalSearch)
     vecB[lane] = isdof ? search : T(0);
@@ -642,7 +657,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   if (dbg.qacc && isdof) dbg.qacc[(size_t)env * nv + lane] = qacc;
   if (dbg.qfrc_smooth && isdof) dbg.qfrc_smooth[(size_t)env * nv + lane] = fs;
   if (dbg.qfrc_constraint && isdof) dbg.qfrc_constraint[(size_t)env * nv + lane] = qfrc_constraint;
-  if (dbg.M && isdof) for (int j = 0; j < nv; ++j) dbg.M[((size_t)env * nv + lane) * nv + j] = M[lane * DEX_MSTRIDE + j];
+  if (dbg.M && isdof) for (int j = 0; j < nv; ++j) dbg.M[((size_t)env * nv + lane) * nv + j] = M[j * 32 + lane];
   const bool bad = isdof && !(dx_abs(qacc) < T(1e10));  // mj_checkAcc (also catches NaN)
   if (dex_ballot(bad)) status |= DEX_STATUS_BADQACC;
   if (lane == 0) {
@@ -652,13 +667,17 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   if (!integrate) return;
 
   // ------------------------------------------------------------------ mj_Euler (implicit joint damping)
-  if (isdof) {
-    for (int j = 0; j < nv; ++j) H[lane * DEX_MSTRIDE + j] = M[lane * DEX_MSTRIDE + j];
-    H[lane * DEX_MSTRIDE + lane] += h * damping;
-  }
+  // only the leading m.nv_euler dofs belong to kinematic trees with joint damping; for the rest
+  // (e.g. the free object) M + hB = M is block-decoupled and the solver's qacc is already the answer
+  const int ne = m.nv_euler;
+  for (int j = 0; j < ne; ++j) H[j * DEX_MSTRIDE + lane] = M[j * 32 + lane];
+  dex_syncwarp();
+  if (lane < ne) H[lane * DEX_MSTRIDE + lane] += h * damping;
   dex_syncwarp();
   int efail = 0;
-  const T qacc_e = dex_chol_solve(H, nv, isdof ? (fs + qfrc_constraint) : T(0), &efail);
+  const T einv = dex_chol_factor(H, ne, &efail);
+  T qacc_e = dex_chol_apply(H, ne, einv, lane < ne ? (fs + qfrc_constraint) : T(0));
+  if (lane >= ne) qacc_e = qacc;
   const T qv_new = qv + h * qacc_e;
   dex_syncwarp();
   qvel[lane] = qv_new;

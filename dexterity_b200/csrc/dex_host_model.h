@@ -19,7 +19,7 @@
 
 struct HostModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
-  int nconmax, iterations, mpr_iterations;
+  int nconmax, iterations, mpr_iterations, nv_euler;
   double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
@@ -103,6 +103,12 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
   if (M.ntree > 5) return "more than 5 kinematic trees";
   M.dof_tree.assign(nv, 0);
   for (int i = 0; i < nv; ++i) M.dof_tree[i] = M.body_tree[M.dof_body[i]];
+  {  // dofs of trees that carry joint damping must be a prefix for the reduced implicit-Euler solve
+    std::vector<int> tree_damped(M.ntree, 0);
+    for (int i = 0; i < nv; ++i) if (M.dof_damping[i] > 0) tree_damped[M.dof_tree[i]] = 1;
+    M.nv_euler = 0;
+    for (int i = 0; i < nv; ++i) if (tree_damped[M.dof_tree[i]]) M.nv_euler = i + 1;
+  }
   M.body_dofmask.assign(nb, 0);
   for (int b = 1; b < nb; ++b) {
     unsigned mask = (unsigned)M.body_dofmask[M.body_parent[b]];

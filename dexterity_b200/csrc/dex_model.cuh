@@ -52,7 +52,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
 template <typename T>
 struct DevModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
-  int nconmax, iterations, mpr_iterations;
+  int nconmax, iterations, mpr_iterations, nv_euler;
   T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia;
 #define DEX_X_I(name) const int* name;
 #define DEX_X_R(name) const T* name;
@@ -80,6 +80,7 @@ struct BatchState {
   int* niter;                     // [nenv] solver iterations of the last mj_step
   const unsigned char* skip;      // optional [nenv]: 1 = leave this env untouched (it was just reset)
   T* jc;                          // [nenv][3*DEX_MAXCON][32] contact-frame Jacobian scratch (L2 resident)
+  T* mscr;                        // [nenv][32][32] mass-matrix scratch (L2 resident)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -126,7 +126,8 @@ enum DexTaskFieldId {
   DEX_FIELD_EPISODE_STATS = 24,/* f64  [8]           sum return, sum length, episodes, successes, falls, timeouts, physics errors */
   DEX_FIELD_RESET_MASK = 25,   /* u8   [nenv]        optional: envs to reset on the next dex_env_step           */
   DEX_FIELD_SKIP = 26,         /* u8   [nenv]        scratch: envs reset during the current call                */
-  DEX_FIELD_JC = 27            /* real [nenv][3*DEX_MAXCON][32] scratch: contact-frame Jacobians (stays in L2)       */
+  DEX_FIELD_JC = 27,           /* real [nenv][3*DEX_MAXCON][32] scratch: contact-frame Jacobians (stays in L2)       */
+  DEX_FIELD_MSCR = 28          /* real [nenv][32][32] scratch: dense mass matrix (stays in L2)                        */
 };
 
 /* Installs the task description (copied).  Replaces the task constructors

@@ -102,7 +102,7 @@ struct EmuModelT {
   void init(const HostModel& h) {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
-    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations;
+    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia;
 #define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
@@ -155,16 +155,16 @@ int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
 int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, void* qvel, int qvel_stride, void* ctrl,
                   int ctrl_stride, void* warm, int warm_stride, void* time, unsigned* status, void* contact, int* ncon,
                   int* niter, int nsub, int integrate, int do_collide, int do_dynamics, void* dbg_M, void* dbg_fs,
-                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, void* jc, int nthreads) {
+                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, void* jc, void* mscr, int nthreads) {
   EmuModel* m = (EmuModel*)mp;
   if (dtype == 0) {
     BatchState<float> st = {nenv, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
-                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc};
+                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc, (float*)mscr};
     DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
     emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   } else {
     BatchState<double> st = {nenv, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
-                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc};
+                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc, (double*)mscr};
     DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
     emu_run<double>(m->d.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   }
@@ -182,7 +182,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
                         (T*)f[DEX_FIELD_CTRL], (int)stride[DEX_FIELD_CTRL], (T*)f[DEX_FIELD_QACC_WARMSTART],
                         (int)stride[DEX_FIELD_QACC_WARMSTART], (T*)f[DEX_FIELD_TIME], (unsigned*)f[DEX_FIELD_STATUS],
                         (T*)f[DEX_FIELD_CONTACT], (int*)f[DEX_FIELD_NCON], (int*)f[DEX_FIELD_NITER],
-                        (const unsigned char*)f[DEX_FIELD_SKIP], (T*)f[DEX_FIELD_JC]};
+                        (const unsigned char*)f[DEX_FIELD_SKIP], (T*)f[DEX_FIELD_JC], (T*)f[DEX_FIELD_MSCR]};
     TaskState<T> ts = {(const T*)f[DEX_FIELD_ACTION], (int)stride[DEX_FIELD_ACTION], (T*)f[DEX_FIELD_OBS], (T*)f[DEX_FIELD_REWARD],
                        (T*)f[DEX_FIELD_DISCOUNT], (T*)f[DEX_FIELD_GOAL], (int*)f[DEX_FIELD_TASK_I], (T*)f[DEX_FIELD_TASK_F],
                        (unsigned*)f[DEX_FIELD_RNG], (unsigned char*)f[DEX_FIELD_SKIP], (const unsigned char*)f[DEX_FIELD_RESET_MASK],
