@@ -32,7 +32,7 @@ template <typename T> struct Xf { T R[9]; T t[3]; };  // pose of frame B express
 // constant-bank model so that the non-inlined callees never take the model's address.
 template <typename T>
 struct GeomRef {
-  const T* vert;   // body-frame hull vertices (mesh)
+  const T* vert;   // body-frame hull vertices (mesh), 4 reals per vertex (x, y, z, pad), 16-byte aligned
   int n;           // vertex count
   int type;        // DEX_GEOM_*
   const T* mat;    // geom rotation in the body frame (box)
@@ -42,7 +42,7 @@ struct GeomRef {
 template <typename T>
 DEX_DEV GeomRef<T> dex_geom_ref(const DevModel<T>& m, int g, int type) {
   GeomRef<T> r;
-  r.vert = m.vert + 3 * dex_ldg(m.geom_vertadr + g);
+  r.vert = m.vert + 4 * dex_ldg(m.geom_vertadr + g);
   r.n = dex_ldg(m.geom_vertnum + g);
   r.type = type;
   r.mat = m.geom_mat + 9 * g;
@@ -61,11 +61,13 @@ DEX_DEV_NOINLINE V3<T> dex_support_local(const T* vert, int n, int gtype, const 
     T best = -Real<T>::big();
     int bi = 0x7fffffff;
     for (int i = dex_lane(); i < n; i += 32) {
-      const T t = dex_ldg(vert + 3 * i) * lx + dex_ldg(vert + 3 * i + 1) * ly + dex_ldg(vert + 3 * i + 2) * lz;
+      T vx, vy, vz;
+      dex_ldg_xyz(vert + 4 * i, vx, vy, vz);
+      const T t = vx * lx + vy * ly + vz * lz;
       if (t > best) { best = t; bi = i; }
     }
     dex_warp_argmax(best, bi);
-    out.x = dex_ldg(vert + 3 * bi); out.y = dex_ldg(vert + 3 * bi + 1); out.z = dex_ldg(vert + 3 * bi + 2);
+    dex_ldg_xyz(vert + 4 * bi, out.x, out.y, out.z);
   } else {  // box
     T G[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
     for (int i = 0; i < 9; ++i) G[i] = dex_ldg(mat + i);

@@ -166,9 +166,10 @@ DEX_DEV T dex_matvec(const T* Mg, const T* x, int nv) {
 template <typename T>
 DEX_DEV void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
   const int lane = dex_lane();
-  for (int t = 0; t < nrows; ++t) {
-    const T s = dex_warp_sum(Jc[t * DEX_JC_ROW + lane] * xi);
-    if (lane == 0) out[t] = s;
+  for (int t = 0; t < nrows; t += 3) {   // one contact (3 frame rows) per round, reductions interleaved
+    T s0 = Jc[t * DEX_JC_ROW + lane] * xi, s1 = Jc[(t + 1) * DEX_JC_ROW + lane] * xi, s2 = Jc[(t + 2) * DEX_JC_ROW + lane] * xi;
+    dex_warp_sum3(s0, s1, s2);
+    if (lane == 0) { out[t] = s0; out[t + 1] = s1; out[t + 2] = s2; }
   }
   dex_syncwarp();
 }

@@ -184,10 +184,11 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       int t = M.geom_type[g];
       if (t != DEX_GEOM_PLANE && t != DEX_GEOM_BOX && t != DEX_GEOM_MESH) return "unsupported geom type (plane/box/mesh only)";
       if (t == DEX_GEOM_MESH) {
-        M.geom_vertadr[g] = (int)(M.vert.size() / 3);
+        M.geom_vertadr[g] = (int)(M.vert.size() / 4);
         for (int i = 0; i < vn[g]; ++i) {
           const double* p = &v[3 * (va[g] + i)];
           for (int k = 0; k < 3; ++k) M.vert.push_back(M.geom_pos[3 * g + k] + G[3 * k] * p[0] + G[3 * k + 1] * p[1] + G[3 * k + 2] * p[2]);
+          M.vert.push_back(0.0);
         }
       }
     }
@@ -197,7 +198,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
       auto grow = [&](const double* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } };
       if (M.geom_type[g] == DEX_GEOM_MESH) {
-        for (int i = 0; i < vn[g]; ++i) grow(&M.vert[3 * (M.geom_vertadr[g] + i)]);
+        for (int i = 0; i < vn[g]; ++i) grow(&M.vert[4 * (M.geom_vertadr[g] + i)]);
       } else if (M.geom_type[g] == DEX_GEOM_BOX) {
         const double* G = &M.geom_mat[9 * g];
         for (int c = 0; c < 8; ++c) {
@@ -215,7 +216,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       for (int k = 0; k < 3; ++k) { pk[k] = M.geom_pos[3 * g + k]; pk[4 + k] = M.geom_aabb[6 * g + k]; pk[7 + k] = M.geom_aabb[6 * g + 3 + k]; }
       pk[3] = M.geom_rbound[g];
     }
-    if (M.vert.empty()) M.vert.assign(3, 0.0);
+    if (M.vert.empty()) M.vert.assign(4, 0.0);
   }
   // ---- body bounding spheres (body frame); radius < 0 marks a body that owns a plane
   M.body_bsphere.assign(4 * nb, 0);

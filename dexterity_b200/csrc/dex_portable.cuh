@@ -59,6 +59,20 @@ inline int dex_ffs(unsigned x) { return __builtin_ffs((int)x); }
 #error "dex_portable.cuh: compile with nvcc (product) or -DDEX_WARP_EMU (tests/emu only)"
 #endif
 
+// 16-byte-aligned (x, y, z, pad) vertex load through the read-only path: one LDG.128 in FP32
+#if defined(__CUDACC__)
+DEX_DEV void dex_ldg_xyz(const float* p, float& x, float& y, float& z) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  x = v.x; y = v.y; z = v.z;
+}
+DEX_DEV void dex_ldg_xyz(const double* p, double& x, double& y, double& z) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  x = a.x; y = a.y; z = __ldg(p + 2);
+}
+#else
+template <typename T> inline void dex_ldg_xyz(const T* p, T& x, T& y, T& z) { x = p[0]; y = p[1]; z = p[2]; }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // warp reductions (all 32 lanes must call)
 // ---------------------------------------------------------------------------------------
@@ -84,6 +98,26 @@ template <typename T> DEX_DEV void dex_warp_argmax(T& v, int& idx) {
     T ov = dex_shfl_xor(v, m);
     int oi = dex_shfl_xor(idx, m);
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+#if defined(__CUDACC__)
+// FP32 specialisation: two REDUX instructions on an order-preserving integer key instead of ten
+// dependent shuffles (the argmax latency dominated the MPR support function in the r01b profile).
+template <> DEX_DEV void dex_warp_argmax<float>(float& v, int& idx) {
+  const unsigned u = __float_as_uint(v);
+  const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  const unsigned mx = __reduce_max_sync(DEX_FULL, key);
+  idx = __reduce_min_sync(DEX_FULL, key == mx ? idx : 0x7fffffff);
+  const unsigned r = (mx & 0x80000000u) ? (mx & 0x7fffffffu) : ~mx;
+  v = __uint_as_float(r);
+}
+#endif
+// three independent warp sums with interleaved shuffles (hides the shuffle latency)
+template <typename T> DEX_DEV void dex_warp_sum3(T& a, T& b, T& c) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const T oa = dex_shfl_xor(a, m), ob = dex_shfl_xor(b, m), oc = dex_shfl_xor(c, m);
+    a += oa; b += ob; c += oc;
   }
 }
 
