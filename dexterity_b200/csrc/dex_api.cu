@@ -12,6 +12,7 @@
 #include "dex_collide.cuh"
 #include "dex_dynamics.cuh"
 #include "dex_host_model.h"
+#include "dex_ik.cuh"
 #include "dex_task.cuh"
 
 namespace {
@@ -64,6 +65,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_task_post(DevModel<T> m
   if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K3_SMEM_T;
   dex_task_post_env<T>(m, st, ts, p, env, smem);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_ik(DevModel<T> m, DexIkParams p, const T* targets, int n, T* qout,
+                                                             int qstride, unsigned char* ok, int* attempts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (idx >= n) return;
+  T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K6_SMEM_T;
+  dex_ik_env<T>(m, p, targets, qout, qstride, ok, attempts, idx, smem);
 }
 
 template <typename T>
@@ -341,6 +353,33 @@ int dex_task_configure(DexBatch* b, const DexTaskParams* p) {
   b->task_set = true;
   return DEX_OK;
 }
+int dex_ik_solve(DexModel* model, int dtype, const void* targets, int n, const DexIkParams* p, void* qout,
+                 int64_t row_stride, unsigned char* ok, int* attempts, void* stream) {
+  if (!model || !targets || !p || !qout || !ok || n < 1) return fail(DEX_E_ARG, "bad argument");
+  const HostModel& h = model->host;
+  if (p->nsite < 1 || p->nsite > DEX_IK_MAXSITE) return fail(DEX_E_ARG, "nsite must be in 1..5");
+  for (int s = 0; s < p->nsite; ++s) if (p->site_id[s] < 0 || p->site_id[s] >= h.nsite) return fail(DEX_E_ARG, "bad site id");
+  if (h.nq != h.nv || h.njnt != h.nv) return fail(DEX_E_MODEL, "IK model must consist of hinge joints only");
+  for (int j = 0; j < h.njnt; ++j)
+    if (h.jnt_type[j] != DEX_JNT_HINGE || h.jnt_dofadr[j] != j || !h.jnt_limited[j]) return fail(DEX_E_MODEL, "IK model must consist of limited hinge joints");
+  DEX_CUDA(cudaSetDevice(model->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (dtype == DEX_F32) {
+    if (!model->has_f32) { int rc = model->f32.upload(h); if (rc) return rc; model->has_f32 = true; }
+    const size_t smem = (size_t)kWarpsPerBlock * DEX_K6_SMEM_T * sizeof(float);
+    DEX_CUDA(cudaFuncSetAttribute(k_ik<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ik<float><<<grid, kWarpsPerBlock * 32, smem, st>>>(model->f32.dev, *p, (const float*)targets, n, (float*)qout, (int)row_stride, ok, attempts);
+  } else if (dtype == DEX_F64) {
+    if (!model->has_f64) { int rc = model->f64.upload(h); if (rc) return rc; model->has_f64 = true; }
+    const size_t smem = (size_t)kWarpsPerBlock * DEX_K6_SMEM_T * sizeof(double);
+    DEX_CUDA(cudaFuncSetAttribute(k_ik<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ik<double><<<grid, kWarpsPerBlock * 32, smem, st>>>(model->f64.dev, *p, (const double*)targets, n, (double*)qout, (int)row_stride, ok, attempts);
+  } else return fail(DEX_E_ARG, "bad dtype");
+  DEX_CUDA(cudaGetLastError());
+  return DEX_OK;
+}
+
 int dex_set_profiling(DexBatch* b, int on) {
   if (!b) return fail(DEX_E_ARG, "null batch");
   b->profiling = on != 0;

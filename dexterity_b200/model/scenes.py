@@ -110,7 +110,9 @@ def shadow_hand_only() -> compile_lib.CompiledModel:
     for tip in SHADOW_FINGERTIPS:
         hand.find_body(tip).sites.append(
             mjcf.Site(name=tip + "_site", pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0])))
-    # the IK physics is the un-attached model: bodies live directly in the world
+    # the IK physics is the un-attached model: bodies live directly in the world (names keep the
+    # hand prefix so that site / joint lookups are uniform across scenes)
+    mjcf._prefix_model(hand, "shadow_hand_e/")
     scene.model.world.children = hand.world.children
     scene.model.meshes = hand.meshes
     scene.model.tendons, scene.model.actuators = hand.tendons, hand.actuators

@@ -143,6 +143,31 @@ int dex_env_reset(DexBatch* batch, void* stream);
  * discount, termination, observations): GoalEnvironment.step (reference environment.py:25-34). */
 int dex_env_step(DexBatch* batch, int nsub, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batched inverse kinematics (reference inverse_kinematics/ik_solver.py:71-228,
+ * controllers/dls/dls.py:43-77): damped-least-squares position IK for all fingertips jointly.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct DexIkParams {
+  int nsite;                 /* number of end-effector sites (<= 5)                                  */
+  int site_id[5];            /* hand.fingertip_sites                                                 */
+  int max_steps;             /* ik_solver.py:75 (default 100)                                        */
+  int num_attempts;          /* ik_solver.py:77 (default 30)                                         */
+  int early_stop;            /* ik_solver.py:76                                                      */
+  int stop_on_first;         /* ik_solver.py:78                                                      */
+  double linear_tol;         /* ik_solver.py:74 (default 1e-3)                                       */
+  double gain;               /* _LINEAR_VELOCITY_GAIN = 0.95 (ik_solver.py:20-23)                    */
+  double regularization;     /* _REGULARIZATION_WEIGHT = 1e-5 (ik_solver.py:27)                      */
+  double progress_threshold; /* _PROGRESS_THRESHOLD = 20 (ik_solver.py:31)                           */
+  unsigned long long seed;   /* restart sampling (the reference draws from the global np.random)     */
+} DexIkParams;
+
+/* Solves `n` independent target sets.  targets_dev: real [n][nsite*3] (world frame of the IK model);
+ * qpos_out_dev: real [n][row_stride] receives the joint configuration (mid-range where no solution);
+ * ok_dev: u8 [n] (0 = IKSolver.solve would return None); attempts_dev: optional i32 [n].
+ * Replaces IKSolver.solve (ik_solver.py:71-153). */
+int dex_ik_solve(DexModel* model, int dtype, const void* targets_dev, int n, const DexIkParams* params,
+                 void* qpos_out_dev, int64_t row_stride, unsigned char* ok_dev, int* attempts_dev, void* stream);
+
 /* Per-kernel-class device timing for the benchmark's roofline block: when enabled every launch is
  * bracketed by a cudaEvent pair on the launching stream.  dex_get_kernel_times synchronises and
  * returns total milliseconds and launch counts for {pre-step, collide, dynamics, post-step}. */

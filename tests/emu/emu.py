@@ -100,3 +100,17 @@ class EmuEnv:
     def step(self, action, nsub):
         self.a["ACTION"][:, :action.shape[1]] = action
         self._call(nsub, 0, nthreads=4)
+
+
+def emu_ik(model: EmuModel, params, targets: np.ndarray, dtype=np.float64, nthreads: int = 8):
+    """Runs the k_ik kernel body in the emulator.  targets: [n, nsite*3]."""
+    n = targets.shape[0]
+    t = np.ascontiguousarray(targets, dtype=dtype)
+    qout = np.zeros((n, 32), dtype)
+    ok = np.zeros(n, np.uint8)
+    attempts = np.zeros(n, np.int32)
+    model.lib.emu_ik_solve.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    model.lib.emu_ik_solve(model.ptr, 0 if dtype == np.float32 else 1, t.ctypes.data, n, ctypes.byref(params),
+                           qout.ctypes.data, 32, ok.ctypes.data, attempts.ctypes.data, nthreads)
+    return qout, ok.astype(bool), attempts

@@ -18,6 +18,7 @@
 #include "../../dexterity_b200/csrc/dex_dynamics.cuh"
 #include "../../dexterity_b200/csrc/dex_host_model.h"
 #include "../../dexterity_b200/csrc/dex_task.cuh"
+#include "../../dexterity_b200/csrc/dex_ik.cuh"
 
 namespace dex_emu {
 struct Warp {
@@ -202,6 +203,25 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
     if (nthreads <= 1) { work(0, nenv); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t) th.emplace_back(work, nenv * t / nthreads, nenv * (t + 1) / nthreads);
+    for (auto& t : th) t.join();
+  };
+  if (dtype == 0) go(float(0), m->f.dev); else go(double(0), m->d.dev);
+  return 0;
+}
+
+int emu_ik_solve(void* mp, int dtype, const void* targets, int n, const DexIkParams* p, void* qout, int qstride,
+                 unsigned char* ok, int* attempts, int nthreads) {
+  EmuModel* m = (EmuModel*)mp;
+  auto go = [&](auto tag, const auto& dev) {
+    using T = decltype(tag);
+    auto work = [&](int lo, int hi) {
+      std::vector<T> smem(DEX_K6_SMEM_T + 64);
+      for (int i = lo; i < hi; ++i)
+        dex_emu::run_warp([&]() { dex_ik_env<T>(dev, *p, (const T*)targets, (T*)qout, qstride, ok, attempts, i, smem.data()); });
+    };
+    if (nthreads <= 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(work, n * t / nthreads, n * (t + 1) / nthreads);
     for (auto& t : th) t.join();
   };
   if (dtype == 0) go(float(0), m->f.dev); else go(double(0), m->d.dev);
