@@ -213,7 +213,7 @@ int run(DexBatch* b, const DevModel<T>& m, int nsub, bool collide, bool dynamics
 }
 
 template <typename T>
-int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaStream_t s) {
+int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaStream_t s, int phases = 7) {
   if (!b->task_set) return fail(DEX_E_ARG, "dex_task_configure has not been called");
   static const int req[] = {DEX_FIELD_OBS, DEX_FIELD_REWARD, DEX_FIELD_DISCOUNT, DEX_FIELD_GOAL, DEX_FIELD_TASK_I,
                             DEX_FIELD_TASK_F, DEX_FIELD_RNG, DEX_FIELD_ACTION, DEX_FIELD_SKIP};
@@ -240,24 +240,25 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
   }
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int block = kWarpsPerBlock * 32;
-  { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
-  if (!force_reset) {
+  if (phases & 1) { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
+  if ((phases & 2) && !force_reset) {
     for (int i = 0; i < nsub; ++i) {
       { ProfScope ps(b, 1, s); k_collide<T><<<grid, block, smem1, s>>>(m, st); b->launches++; }
       { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, block, smem2, s>>>(m, st, dbg, 1); b->launches++; }
     }
   }
-  { ProfScope ps(b, 3, s); k_task_post<T><<<grid, block, smem3, s>>>(m, st, ts, b->task); b->launches++; }
+  if (phases & 4) { ProfScope ps(b, 3, s); k_task_post<T><<<grid, block, smem3, s>>>(m, st, ts, b->task); b->launches++; }
   DEX_CUDA(cudaGetLastError());
   return DEX_OK;
 }
 
-int dispatch_env(DexBatch* b, int nsub, int force_reset, void* stream) {
+int dispatch_env(DexBatch* b, int nsub, int force_reset, void* stream, int phases = 7) {
   if (!b) return fail(DEX_E_ARG, "null batch");
   if (nsub < 1) return fail(DEX_E_ARG, "nsub must be >= 1");
+  if (phases < 1 || phases > 7) return fail(DEX_E_ARG, "phases must be a non-empty subset of PRE|PHYSICS|POST");
   cudaStream_t s = (cudaStream_t)stream;
-  if (b->dtype == DEX_F32) return run_env<float>(b, b->model->f32.dev, nsub, force_reset, s);
-  return run_env<double>(b, b->model->f64.dev, nsub, force_reset, s);
+  if (b->dtype == DEX_F32) return run_env<float>(b, b->model->f32.dev, nsub, force_reset, s, phases);
+  return run_env<double>(b, b->model->f64.dev, nsub, force_reset, s, phases);
 }
 
 int dispatch(DexBatch* b, int nsub, bool collide, bool dynamics, int integrate, void* stream) {
@@ -405,5 +406,6 @@ int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
 }
 int dex_env_reset(DexBatch* b, void* stream) { return dispatch_env(b, 1, 1, stream); }
 int dex_env_step(DexBatch* b, int nsub, void* stream) { return dispatch_env(b, nsub, 0, stream); }
+int dex_env_phase(DexBatch* b, int phases, int nsub, int force_reset, void* stream) { return dispatch_env(b, nsub, force_reset, stream, phases); }
 
 }  // extern "C"

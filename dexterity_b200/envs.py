@@ -252,6 +252,132 @@ class BatchedGoalEnvironment:
         return sharding.reduce_episode_stats(self.episode_stats)
 
 
+class ReachEnvironment(BatchedGoalEnvironment):
+    """Reach task (reference manipulation/tasks/reach.py:71-220) with the Shadow hand.
+
+    Goal sampling and the collision-free initial hand configuration need masked physics
+    sub-rollouts, so a step is split into its phases (dex_env_phase) with the host-side
+    `FingertipCartesianPosition` generator acting between them; `GoalInitializationError` is retried
+    as in reference dexterity/environment.py:14-34.
+    """
+
+    _INIT_JOINT_RANGE_FRACTION = 0.5     # reach.py:45
+
+    def __init__(self, num_envs: int, seed=None, device: int = 0, dtype: torch.dtype = torch.float32,
+                 time_limit=None, dense_reward: bool = True) -> None:
+        super().__init__("reach", num_envs, seed, device, dtype, time_limit, dense_reward=dense_reward)
+        from dexterity_b200 import goals, hands
+        self.hand = hands.DexterousHand(self.compiled)
+        self.goal_generator = goals.FingertipCartesianPosition(self.hand, self.model)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(self.seed)
+        self.goal_qpos = torch.zeros(num_envs, self.hand.num_joints, dtype=dtype, device=self.device)
+        backend.lib().dex_env_phase.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        self._site_body = torch.as_tensor(self.compiled.SITE_BODY[self.hand.fingertip_site_ids], device=self.device)
+
+    def fingertip_positions(self, physics=None) -> torch.Tensor:
+        """Fingertip site world positions [n, 15] at the physics' current qpos, from the observation
+        refresh kernel when `physics` is this env's own batch, else via a scratch forward pass."""
+        if physics is None or physics is self.physics:
+            return self._obs[:, self.obs_layout["shadow_hand_e/fingertip_positions"]]
+        return _fk_sites(self.compiled, self.hand, physics)
+
+    def _phase(self, phases: int, force_reset: int = 0) -> None:
+        backend._check(backend.lib().dex_env_phase(self.physics.ptr, phases, self.n_sub_steps, force_reset,
+                                                   backend.PhysicsBatch._stream()))
+
+    def _sample_collision_free(self, ids: torch.Tensor) -> None:
+        """DexterousHand.sample_collision_free_joint_angles (dexterous_hand.py:144-168) for envs `ids`."""
+        sc = self.goal_generator._scratch_batch(ids.numel(), self.dtype)
+        pending = torch.arange(ids.numel(), device=self.device)
+        for _ in range(200):
+            m = pending.numel()
+            if m == 0:
+                return
+            q = self.hand.sample_joint_angles(m, self._gen, self._INIT_JOINT_RANGE_FRACTION, self.device, self.dtype)
+            sc.qpos[:m] = self.physics.qpos[ids[pending]]
+            sc.qpos[:m, :self.hand.num_joints] = q
+            sc.collide()
+            ok = sc.ncon[:m] == 0
+            self.physics.qpos[ids[pending[ok]], :self.hand.num_joints] = q[ok]
+            pending = pending[~ok]
+        raise RuntimeError("could not sample a collision-free hand configuration")
+
+    def _host_hooks(self) -> None:
+        """Runs after the pre-step kernel: episode initialisation and goal changes (reach.py:149-194)."""
+        fresh = self._skip.bool()
+        changed = self._task_i[:, 4].bool()
+        ids = torch.nonzero(changed, as_tuple=False).flatten()
+        if ids.numel():
+            while True:     # GoalEnvironment retry loop (environment.py:16-23)
+                try:
+                    g, gq = self.goal_generator.next_goal(self, ids, self._gen)
+                    break
+                except Exception as e:  # noqa: BLE001
+                    from dexterity_b200 import goals
+                    if not isinstance(e, goals.GoalInitializationError):
+                        raise
+            self._goal[ids, :g.shape[1]] = g
+            self.goal_qpos[ids] = gq
+        fid = torch.nonzero(fresh, as_tuple=False).flatten()
+        if fid.numel():
+            self._sample_collision_free(fid)
+
+    def reset(self) -> TimeStep:
+        self._phase(1, force_reset=1)
+        self._host_hooks()
+        self._phase(4)
+        return self._timestep()
+
+    def step_bound(self) -> TimeStep:
+        self._phase(1)
+        self._host_hooks()
+        self._phase(2 | 4)
+        return self._timestep()
+
+
+def _fk_sites(compiled, hand, physics) -> torch.Tensor:
+    """Torch forward kinematics of the fingertip sites for a scratch batch (hinge chains only)."""
+    c = compiled
+    n = physics.num_envs
+    dev, dt = physics.device, physics.dtype
+    q = physics.qpos
+    pos = [None] * c.nbody
+    rot = [None] * c.nbody
+    eye = torch.eye(3, dtype=dt, device=dev).expand(n, 3, 3)
+    pos[0], rot[0] = torch.zeros(n, 3, dtype=dt, device=dev), eye
+    needed = set()
+    for s in hand.fingertip_site_ids:
+        b = int(c.SITE_BODY[s])
+        while b > 0:
+            needed.add(b); b = int(c.BODY_PARENT[b])
+    from dexterity_b200.model import mjcf
+    for b in range(1, c.nbody):
+        if b not in needed:
+            continue
+        p = int(c.BODY_PARENT[b])
+        R0 = torch.as_tensor(mjcf.quat_to_mat(c.BODY_QUAT[b]), dtype=dt, device=dev)
+        x = pos[p] + (rot[p] @ torch.as_tensor(c.BODY_POS[b], dtype=dt, device=dev))
+        R = rot[p] @ R0
+        for j in range(int(c.BODY_JNTADR[b]), int(c.BODY_JNTADR[b] + c.BODY_JNTNUM[b])):
+            if c.JNT_TYPE[j] != 3:
+                raise NotImplementedError
+            ax = torch.as_tensor(c.JNT_AXIS[j], dtype=dt, device=dev)
+            jp = torch.as_tensor(c.JNT_POS[j], dtype=dt, device=dev)
+            ang = q[:, int(c.JNT_QPOSADR[j])] - float(c.QPOS0[int(c.JNT_QPOSADR[j])])
+            K = torch.tensor([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]], dtype=dt, device=dev)
+            Rj = torch.eye(3, dtype=dt, device=dev) + ang.sin()[:, None, None] * K + (1 - ang.cos())[:, None, None] * (K @ K)
+            anchor = x + R @ jp
+            R = R @ Rj
+            x = anchor - R @ jp
+        pos[b], rot[b] = x, R
+    out = []
+    for s in hand.fingertip_site_ids:
+        b = int(c.SITE_BODY[s])
+        out.append(pos[b] + rot[b] @ torch.as_tensor(c.SITE_POS[s], dtype=dt, device=dev))
+    return torch.cat(out, dim=1)
+
+
 def load(domain_name: str, task_name: str = "state_dense", seed: Optional[int] = None,
          strip_singleton_obs_buffer_dim: bool = True, time_limit: Optional[float] = None,
          num_envs: int = 1, device: int = 0, dtype: torch.dtype = torch.float32) -> BatchedGoalEnvironment:
@@ -262,5 +388,6 @@ def load(domain_name: str, task_name: str = "state_dense", seed: Optional[int] =
         raise ValueError(f"Unknown domain: {domain_name}")
     if task_name not in tasks[domain_name]:
         raise ValueError(f"Unknown task: {task_name}")
-    return BatchedGoalEnvironment(domain_name, num_envs, seed, device, dtype, time_limit,
-                                  dense_reward=(task_name == "state_dense"))
+    if domain_name == "reach":
+        return ReachEnvironment(num_envs, seed, device, dtype, time_limit, dense_reward=(task_name == "state_dense"))
+    return BatchedGoalEnvironment(domain_name, num_envs, seed, device, dtype, time_limit)

@@ -69,5 +69,5 @@ class DexterousHand:
         hi = torch.as_tensor(range_fraction * self.joint_range[:, 1], dtype=dtype, device=device)
         q = lo + (hi - lo) * torch.rand(num, self.num_joints, generator=generator, device=device, dtype=dtype)
         for ids in self.coupled_joint_ids:
-            q[:, ids] = q[:, ids[-1]].unsqueeze(1)
+            q[:, ids] = q[:, ids[-1]].clone().unsqueeze(1)
         return q

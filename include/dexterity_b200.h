@@ -143,6 +143,12 @@ int dex_env_reset(DexBatch* batch, void* stream);
  * discount, termination, observations): GoalEnvironment.step (reference environment.py:25-34). */
 int dex_env_step(DexBatch* batch, int nsub, void* stream);
 
+/* The same step split into phases so that a host-side GoalGenerator can act between them (the reach
+ * task samples goals with a masked physics sub-rollout, reference goals/fingertip_position.py:61-119):
+ * phases = DEX_PHASE_PRE | DEX_PHASE_PHYSICS | DEX_PHASE_POST (any non-empty subset, run in that order). */
+enum DexPhase { DEX_PHASE_PRE = 1, DEX_PHASE_PHYSICS = 2, DEX_PHASE_POST = 4 };
+int dex_env_phase(DexBatch* batch, int phases, int nsub, int force_reset, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Batched inverse kinematics (reference inverse_kinematics/ik_solver.py:71-228,
  * controllers/dls/dls.py:43-77): damped-least-squares position IK for all fingertips jointly.

@@ -22,6 +22,9 @@ def reorient_reset(compiled, rng: np.random.RandomState) -> np.ndarray:
         q[nq - 7:nq - 4] = [rng.uniform(-0.025, 0.025), rng.uniform(-0.155, -0.105), 0.16]
         quat = rng.randn(4)
         q[nq - 4:] = quat / np.linalg.norm(quat)
+    else:
+        # reach (reference reach.py:155-158): hand joints uniform in half of their range
+        q[:24] = rng.uniform(0.5 * compiled.JNT_RANGE[:24, 0], 0.5 * compiled.JNT_RANGE[:24, 1])
     return q
 
 
@@ -82,3 +85,34 @@ def upload(batch, states: Dict[str, np.ndarray]) -> None:
     batch.qpos.copy_(t(states["qpos"])); batch.qvel.copy_(t(states["qvel"]))
     batch.ctrl.copy_(t(states["ctrl"])); batch.qacc_warmstart.copy_(t(states["warm"]))
     batch.time.zero_(); batch.status.zero_()
+
+
+def mpr_stable_mask(compiled, states: Dict[str, np.ndarray], eps: float = 1e-7, trials: int = 3, seed: int = 0) -> np.ndarray:
+    """Non-degeneracy probe.  libccd's MPR terminates on whichever portal first stops expanding, so
+    for deep or face-face penetrations its (normal, depth) depend on sign decisions that flip under
+    perturbations far below FP32 resolution — in the reference engine itself.  A state is called
+    non-degenerate when the ORACLE's own contact set and normals survive `trials` random
+    perturbations of qpos of size `eps` (FP32 rounding level).  Parity is asserted on those states;
+    the degenerate share is reported alongside."""
+    rng = np.random.RandomState(seed)
+    om = orc.OracleModel(compiled)
+    d = orc.OracleData(om)
+    n = len(states["qpos"])
+    stable = np.ones(n, bool)
+
+    def contacts(q, e):
+        d.set_state(q, states["qvel"][e], states["ctrl"][e], states["warm"][e])
+        d.forward()
+        c = d.contacts()
+        return c["geom"].copy(), (c["frame"][:, 0].copy() if len(c["dist"]) else np.zeros((0, 3)))
+
+    for e in range(n):
+        g0, n0 = contacts(states["qpos"][e], e)
+        if len(n0) == 0:
+            continue
+        for _ in range(trials):
+            g1, n1 = contacts(states["qpos"][e] + eps * rng.randn(compiled.nq), e)
+            if g0.shape != g1.shape or (g0 != g1).any() or np.abs(n0 - n1).max() > 1e-3:
+                stable[e] = False
+                break
+    return stable

@@ -80,7 +80,10 @@ def test_single_step_fp32(setup):
     eq = relerr(b.qpos.cpu().numpy().astype(np.float64), ref["qpos"])
     ev = relerr(b.qvel.cpu().numpy().astype(np.float64), ref["qvel"])
     ok = (eq <= REL_TOL_F32) & (ev <= REL_TOL_F32)
+    stable = statelib.mpr_stable_mask(compiled, states)
+    print(f"reorient FP32 parity: {ok.mean():.4f} of all states, {ok[stable].mean():.4f} of the {stable.mean():.3f} non-degenerate")
     assert (b.ncon.cpu().numpy() == ref["ncon"]).mean() >= 0.99
+    assert ok[stable].mean() >= 0.985
     assert ok.mean() >= MIN_PASS_FRACTION_F32, f"only {ok.mean():.3f} of states within 1e-4 (median {np.median(ev):.2e})"
     assert np.median(ev) <= 1e-6 and np.median(eq) <= 1e-6
 

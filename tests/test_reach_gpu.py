@@ -1,0 +1,62 @@
+"""Reach task (BASELINE.json configs[0..1], Shadow hand): single-step physics parity on 4096 envs
+and the behavioural known-answer test of reference manipulation/tasks/reach_test.py:12-35."""
+import numpy as np
+import pytest
+import torch
+
+from tests import statelib
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reach_4096_single_step_matches_oracle():
+    from dexterity_b200 import backend
+    from dexterity_b200.model import scenes
+    c = scenes.load_compiled("reach_shadow")
+    assert (c.nq, c.nv, c.nu) == (24, 24, 20)
+    n = 4096
+    states = statelib.rollout_states(c, seed=12345, nstates=n, every=3, episodes=256)
+    ref = statelib.oracle_step(c, states, nsub=1)
+    model = backend.PhysicsModel(c, 0)
+    b = backend.PhysicsBatch(model, n, torch.float32)
+    statelib.upload(b, states)
+    b.step(1)
+    torch.cuda.synchronize()
+    q = b.qpos.cpu().numpy().astype(np.float64); v = b.qvel.cpu().numpy().astype(np.float64)
+    eq = np.abs(q - ref["qpos"]).max(axis=1) / np.maximum(1, np.abs(ref["qpos"]).max(axis=1))
+    ev = np.abs(v - ref["qvel"]).max(axis=1) / np.maximum(1, np.abs(ref["qvel"]).max(axis=1))
+    same = b.ncon.cpu().numpy() == ref["ncon"]
+    # north_star: <= 1e-4 relative (FP32 vs FP64 reference) on non-degenerate states.  The reach reset
+    # distribution starts with interpenetrating finger links, where MPR is chaotic in the reference
+    # algorithm itself (statelib.mpr_stable_mask); those states are counted, not hidden.
+    ok = (eq <= 1e-4) & (ev <= 1e-4)
+    stable = statelib.mpr_stable_mask(c, states)
+    print(f"reach parity: {ok.mean():.4f} of all states, {ok[stable].mean():.4f} of the {stable.mean():.3f} non-degenerate; "
+          f"median rel err {np.median(ev):.2e}")
+    assert same.mean() >= 0.995, same.mean()
+    assert stable.mean() > 0.8
+    assert ok[stable].mean() >= 0.98, (ok[stable].mean(), np.median(ev))
+    assert ok[ref["ncon"] == 0].all(), "contact-free states must all be within tolerance"
+    assert np.median(ev) <= 1e-6
+
+
+def test_reach_behaviour_like_reference():
+    from dexterity_b200 import envs
+    env = envs.load("reach", "state_sparse", seed=12345, num_envs=64)
+    ts = env.reset()
+    torch.cuda.synchronize()
+    assert (ts.step_type == 0).all()
+    assert sum(s.shape[0] for s in env.observation_spec().values()) == 117      # SURVEY §8 reach scene
+    # goals are reachable fingertip positions: finite and near the hand
+    g = env.goal[:, :15]
+    assert torch.isfinite(g).all() and (g.reshape(-1, 5, 3).norm(dim=-1) < 0.6).all()
+    # sparse reward is -1 away from the goal after a zero action (reach_test.py:12-24)
+    ts = env.step(torch.zeros(64, 20, device=env.device))
+    assert (ts.reward[env.goal_distance.max(dim=1).values > 0.01] == -1.0).all()
+    # driving the actuators to the goal configuration reaches the targets: reward 0, successes > 0 (:26-35)
+    reached = torch.zeros(64, dtype=torch.bool, device=env.device)
+    for _ in range(150):
+        ctrl = env.hand.joint_positions_to_control(env.goal_qpos)
+        ts = env.step(ctrl)
+        reached |= (env.successes > 0) & (ts.reward == 0.0)
+    assert reached.float().mean() > 0.7, reached.float().mean()
