@@ -25,10 +25,13 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(DEX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef DEX_WARPS_PER_BLOCK
+#define DEX_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_collide(DevModel<T> m, BatchState<T> st) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_collide(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
@@ -38,7 +41,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_collide(DevModel<T> m, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
                                                                    int integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -88,7 +91,7 @@ struct DeviceArrays {
     dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep;
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
-    dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia;
+    dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name)                                                                         \
   {                                                                                           \
     void* p = nullptr;                                                                        \

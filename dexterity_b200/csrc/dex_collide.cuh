@@ -384,6 +384,11 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
         T d[3] = {c2[0] - c1[0] - xpos[3 * b1], c2[1] - c1[1] - xpos[3 * b1 + 1], c2[2] - c1[2] - xpos[3 * b1 + 2]};
         T bound = r1 + r2;
         pass = dot3(d, d) <= bound * bound;
+        if (pass) {  // tighter: the two bodies' AABBs as oriented boxes (r01d: cuts surviving body pairs 61 -> 13)
+          Xf<T> rb;
+          dex_relative(xpos, xmat, b1, b2, rb);
+          pass = dex_obb_overlap(rb, m.body_pack + DEX_GPACK * b1, m.body_pack + DEX_GPACK * b2, m.max_margin);
+        }
       }
     }
     unsigned mask = dex_ballot(pass);

@@ -127,7 +127,7 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, int n, int* fail) {
     for (int j = k4; j < k; ++j) s -= rowi[j] * rowk[j];
     T dkk = dex_shfl(s, k);
     if (!(dkk > Real<T>::minval())) { bad = true; dkk = Real<T>::minval(); }
-    const T inv = T(1) / dx_sqrt(dkk);
+    const T inv = dx_rsqrt(dkk);
     if (i == k) inv_mine = inv;
     if (i >= k && i < n) rowi[k] = s * inv;
     dex_syncwarp();
@@ -636,7 +636,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       if (ls == 0) {
         g0 = g;
         if (!(g < 0) || !(hh > 0)) break;  // not a descent direction: alpha stays 0
-      } else if (dx_abs(g) <= (sizeof(T) == 4 ? T(1e-5) : T(1e-12)) * dx_abs(g0)) break;
+      } else if (dx_abs(g) <= (sizeof(T) == 4 ? T(1e-3) : T(1e-12)) * dx_abs(g0)) break;
       if (g < 0) lo = alpha; else hi = alpha;
       T next = alpha - g / hh;
       if (hi >= 0 && (next <= lo || next >= hi)) next = T(0.5) * (lo + hi);

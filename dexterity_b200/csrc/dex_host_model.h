@@ -20,7 +20,7 @@
 struct HostModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
-  double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia;
+  double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
 #define DEX_X(t, name) DEX_X_##t(name)
@@ -237,6 +237,24 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     for (int k = 0; k < 3; ++k) M.body_bsphere[4 * b + k] = c[k];
     M.body_bsphere[4 * b + 3] = plane ? (n == 1 ? -1.0 : 1e30) : r;
   }
+  // ---- body-frame AABB over each body's collidable geoms, in the geom_pack record layout (only the
+  //      aabb slots 4..9 are used) so the same OBB separating-axis routine serves bodies and geoms
+  M.body_pack.assign(12 * nb, 0);
+  for (int b = 0; b < nb; ++b) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool any = false;
+    for (int g = 0; g < M.ngeom; ++g) if (M.geom_body[g] == b) {
+      any = true;
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = std::min(lo[k], M.geom_aabb[6 * g + k] - M.geom_aabb[6 * g + 3 + k]);
+        hi[k] = std::max(hi[k], M.geom_aabb[6 * g + k] + M.geom_aabb[6 * g + 3 + k]);
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      M.body_pack[12 * b + 4 + k] = any ? 0.5 * (lo[k] + hi[k]) : 0.0;
+      M.body_pack[12 * b + 7 + k] = any ? std::min(0.5 * (hi[k] - lo[k]), 1e30) : 0.0;
+    }
+  }
   // ---- candidate pairs grouped by body pair (blob order is already grouped; verified here)
   M.pair_geom1 = I(DEXF_PAIR_GEOM1); M.pair_geom2 = I(DEXF_PAIR_GEOM2); M.pair_condim = I(DEXF_PAIR_CONDIM);
   M.pair_friction = F(DEXF_PAIR_FRICTION); M.pair_solref = F(DEXF_PAIR_SOLREF); M.pair_solimp = F(DEXF_PAIR_SOLIMP);
@@ -259,6 +277,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       M.bp_pairnum.back()++;
     }
     M.nbodypair = (int)M.bp_body1.size();
+    M.max_margin = maxmargin;
     // fold the largest pair margin into the body spheres so the body-level cull stays conservative
     for (int b = 0; b < nb; ++b) if (M.body_bsphere[4 * b + 3] >= 0) M.body_bsphere[4 * b + 3] += 0.5 * maxmargin;
   }

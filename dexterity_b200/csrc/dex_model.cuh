@@ -30,7 +30,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(I, body_parent) X(I, body_depth) X(I, body_jntadr) X(I, body_jntnum) X(I, body_dofadr) \
   X(I, body_dofnum) X(I, body_tree) X(I, body_dofmask) X(I, body_weld)                     \
   X(R, body_pos) X(R, body_quat) X(R, body_ipos) X(R, body_mass) X(R, body_inertia6)       \
-  X(R, body_xfrc) X(R, body_invweight0) X(R, body_bsphere)                                 \
+  X(R, body_xfrc) X(R, body_invweight0) X(R, body_bsphere) X(R, body_pack)                                 \
   X(I, tree_refbody)                                                                       \
   X(I, jnt_type) X(I, jnt_body) X(I, jnt_qposadr) X(I, jnt_dofadr) X(I, jnt_limited)       \
   X(R, jnt_pos) X(R, jnt_axis) X(R, jnt_range) X(R, jnt_margin) X(R, jnt_solref)           \
@@ -53,7 +53,7 @@ template <typename T>
 struct DevModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
-  T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia;
+  T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) const int* name;
 #define DEX_X_R(name) const T* name;
 #define DEX_X(t, name) DEX_X_##t(name)
@@ -99,6 +99,13 @@ template <> struct Real<double> {
 };
 
 template <typename T> DEX_DEV T dx_sqrt(T x) { return sqrt(x); }
+// reciprocal square root: one MUFU.RSQ (+ one Newton step) in FP32 instead of IEEE sqrt + divide
+#if defined(__CUDACC__)
+DEX_DEV float dx_rsqrt(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f * x * r * r); }
+DEX_DEV double dx_rsqrt(double x) { return 1.0 / sqrt(x); }
+#else
+template <typename T> inline T dx_rsqrt(T x) { return T(1) / std::sqrt(x); }
+#endif
 template <typename T> DEX_DEV T dx_abs(T x) { return x < 0 ? -x : x; }
 template <typename T> DEX_DEV T dx_min(T a, T b) { return a < b ? a : b; }
 template <typename T> DEX_DEV T dx_max(T a, T b) { return a > b ? a : b; }
@@ -110,10 +117,11 @@ template <typename T> DEX_DEV void cross3(T* r, const T* a, const T* b) {
   r[0] = x; r[1] = y; r[2] = z;
 }
 template <typename T> DEX_DEV T normalize3(T* a) {
-  T n = dx_sqrt(dot3(a, a));
-  if (n < Real<T>::minval()) { a[0] = 1; a[1] = 0; a[2] = 0; }
-  else { T inv = T(1) / n; a[0] *= inv; a[1] *= inv; a[2] *= inv; }
-  return n;
+  const T n2 = dot3(a, a);
+  if (n2 < Real<T>::minval() * Real<T>::minval()) { a[0] = 1; a[1] = 0; a[2] = 0; return T(0); }
+  const T inv = dx_rsqrt(n2);
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
+  return n2 * inv;
 }
 template <typename T> DEX_DEV void quat_mul(T* r, const T* a, const T* b) {
   T w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -123,9 +131,9 @@ template <typename T> DEX_DEV void quat_mul(T* r, const T* a, const T* b) {
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
 template <typename T> DEX_DEV void quat_normalize(T* q) {
-  T n = dx_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  if (n < Real<T>::minval()) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
-  else { T inv = T(1) / n; q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv; }
+  const T n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 < Real<T>::minval() * Real<T>::minval()) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+  else { const T inv = dx_rsqrt(n2); q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv; }
 }
 template <typename T> DEX_DEV void quat2mat(T* m, const T* q) {
   T w = q[0], x = q[1], y = q[2], z = q[3];

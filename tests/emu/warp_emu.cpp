@@ -105,7 +105,7 @@ struct EmuModelT {
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
-    dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia;
+    dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
 #define DEX_X_R(name) v_##name.assign(h.name.begin(), h.name.end()); dev.name = v_##name.data();
 #define DEX_X(t, name) DEX_X_##t(name)
