@@ -505,6 +505,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   }
   T grad = 0, cost = 0, oldcost = 0, gnorm_prev = 0, hinv = 1, hdiag_prev = 0;
   int asig_prev = -1;
+  bool small_step = false;
   int iter = 0;
   const int maxiter = m.iterations;
   for (;; ++iter) {
@@ -555,7 +556,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     }
     grad = isdof ? (Ma - fs - jtf) : T(0);
     const T gnorm = dx_sqrt(dex_warp_sum(grad * grad));
-    if (scale * gnorm < tol) break;
+    if (scale * gnorm < tol || small_step) break;
     if (iter > 0) {
       // MuJoCo stops on improvement < tolerance; in FP32 the cost is only good to ~1e-7 relative,
       // so the improvement test is honoured only once the gradient has stopped shrinking.
@@ -644,6 +645,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       alpha = next;
     }
     if (alpha == 0) break;
+    // MuJoCo's stopping rule "improvement * scale < tolerance", with the improvement taken from the
+    // line search itself (-alpha g0 / 2 at an exact line minimum) instead of a difference of costs,
+    // which FP32 cannot resolve.  The forces/gradient are still refreshed at the final iterate.
+    small_step = scale * (T(-0.5) * alpha * g0) < m.tolerance;
     // ---- move
     if (isdof) { qacc += alpha * search; Ma += alpha * Mv; }
     if (lane < ncon) {
