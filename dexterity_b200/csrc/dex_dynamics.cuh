@@ -65,7 +65,7 @@ struct DynDebug {
 };
 
 template <typename T>
-DEX_DEV void dex_impedance(const T* solimp, T pos, T margin, T* imp) {  // getimpedance
+DEX_DEV_NOINLINE void dex_impedance(const T* solimp, T pos, T margin, T* imp) {  // getimpedance
   T dmin = dx_clamp(solimp[0], T(0.0001), T(0.9999));
   T dmax = dx_clamp(solimp[1], T(0.0001), T(0.9999));
   T width = dx_max(solimp[2], Real<T>::minval());
