@@ -31,7 +31,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_collide(DevModel<T> m, BatchState<T> st) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_collide(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;

@@ -111,7 +111,7 @@ struct MprCtx {
 };
 
 template <typename T>
-DEX_DEV_NOINLINE void dex_mink(const MprCtx<T>& c, const T* dir, SupPt<T>& p) {
+DEX_DEV void dex_mink(const MprCtx<T>& c, const T* dir, SupPt<T>& p) {
   const V3<T> a = dex_support_ref(c.A, dir[0], dir[1], dir[2]);
   T nd[3] = {-dir[0], -dir[1], -dir[2]}, lb[3];
   rotT_vec(lb, c.rel.R, nd);
@@ -177,7 +177,7 @@ template <typename T> DEX_DEV void expand_portal(SupPt<T>* s, const SupPt<T>& v4
 // state.  Returns true on intersection; depth / dir / pos as libccd (pos = midpoint of the witness
 // points on A and B).
 template <typename T>
-DEX_DEV_NOINLINE bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
+DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
   SupPt<T> s[4], v4;
   T dir[3], va[3], vb[3];
   {
