@@ -35,7 +35,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_collide(DevModel<T> 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
-  if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K1_SMEM_T;
   dex_collide_env<T>(m, st, env, smem);
 }
@@ -46,7 +45,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) k_dynamics(DevModel<T>
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
-  if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
 }

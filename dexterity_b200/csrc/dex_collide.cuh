@@ -345,7 +345,7 @@ DEX_DEV void dex_store_contact(T* dst, T dist, const T* pos, const T* normal, in
 
 template <typename T>
 DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
-  if (st.skip && st.skip[env]) return;  // warp-uniform
+  if (env >= st.nenv || (st.skip && st.skip[env])) { dex_phase_sync(); dex_phase_sync(); return; }  // warp-uniform
   const int lane = dex_lane();
   T* xpos = smem;
   T* xquat = xpos + DEX_MAXBODY * 3;
@@ -357,6 +357,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   KinBuf<T> kb = {xpos, xquat, xmat, nullptr, nullptr};
   dex_fk(m, qpos, kb);
 
+  dex_phase_sync();
   // ---- broadphase
   int ncand = 0;
   for (int bp0 = 0; bp0 < m.nbodypair; bp0 += 32) {
@@ -479,6 +480,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     ncand = nkeep;
   }
   dex_syncwarp();
+  dex_phase_sync();
 
   // ---- narrowphase
   T* cout = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;

@@ -177,7 +177,7 @@ DEX_DEV void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
 template <typename T>
 DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int env,
                               T* smem, int integrate) {
-  if (st.skip && st.skip[env]) return;  // warp-uniform
+  if (env >= st.nenv || (st.skip && st.skip[env])) { dex_phase_sync(); dex_phase_sync(); dex_phase_sync(); return; }  // warp-uniform
   const int lane = dex_lane();
   const int nv = m.nv, nb = m.nbody;
   T* xpos = smem + DEX_K2_OFF_XPOS;
@@ -222,6 +222,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   }
   dex_syncwarp();
 
+  dex_phase_sync();
   // ------------------------------------------------------------------ cdof (lane = dof), cinert (lane = body)
   T cd[6];
   dex_cdof_lane(m, lane, xpos, xmat, xanchor, xaxis, ref, cd);
@@ -388,6 +389,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   const T fs = isdof ? (-damping * qv - bias + vecA[lane]) : T(0);  // qfrc_smooth
   dex_syncwarp();  // union A is dead from here on (cinert/crb/cvel/cacc/cfrc); union B may be written
 
+  dex_phase_sync();
   // ------------------------------------------------------------------ constraint rows
   // friction loss (lane = dof)
   T f_loss = 0, f_R = 1, f_D = 0, f_aref = 0;
@@ -488,6 +490,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   }
   dex_syncwarp();
 
+  dex_phase_sync();
   // ------------------------------------------------------------------ Newton solver (mj_solNewton)
   const T scale = 1 / (m.meaninertia * (nv > 1 ? nv : 1));
   const T tol = dx_max(m.tolerance, sizeof(T) == 4 ? T(1e-6) : T(1e-12));
