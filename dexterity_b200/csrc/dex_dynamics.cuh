@@ -94,61 +94,97 @@ DEX_DEV void dex_kb(const T* solref, const T* solimp, T timestep, T* K, T* B) {
   }
 }
 
-// sum_{j<k4} a[j] b[j] for 16-byte aligned rows, k4 a multiple of 4: two 128-bit shared loads per 4 terms
 template <typename T> struct alignas(16) DexVec4 { T x, y, z, w; };
-template <typename T>
-DEX_DEV T dex_dot4(const T* a, const T* b, int k4) {
-  T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (int j = 0; j < k4; j += 4) {
-    const DexVec4<T> va = *reinterpret_cast<const DexVec4<T>*>(a + j);
-    const DexVec4<T> vb = *reinterpret_cast<const DexVec4<T>*>(b + j);
-    s0 += va.x * vb.x; s1 += va.y * vb.y; s2 += va.z * vb.z; s3 += va.w * vb.w;
-  }
-  return (s0 + s1) + (s2 + s3);
-}
-// Cholesky of the SPD n x n matrix H (smem, stride DEX_MSTRIDE, lower triangle read and overwritten
-// by L; the strictly upper part of every row is zeroed so the dot products can run over whole
-// 4-element groups; rows >= n are padded with the identity).  Left-looking, lane = row, tiny code
-// (the r01b profile showed a fully unrolled register version losing to instruction-cache misses).
+// Cholesky of an SPD matrix of order n <= 32, lane = row.  Storage contract (shared by the factor and
+// the solves): the warp's 32 x DEX_MSTRIDE tile H holds the STRICTLY LOWER triangle only; the
+// diagonal, the upper triangle and every row / column >= n are zero; lane i carries its diagonal
+// entry in the register `hd` (1 for lanes >= n).  Because the upper part is zero, every dot product
+// and every substitution step runs over whole 4-column groups without masks.
+// Left-looking over 4-column blocks: the prefix dot products of the block's 4 columns share the
+// loads of row i (5 LDS.128 per 16 FMAs), the 4 x 4 diagonal block is finished with shuffles, and
+// one STS.128 per lane writes the block back; 8 warp barriers per factorisation (r01f profile: the
+// column-at-a-time version cost 3.9 k warp instructions per call, 42 % of K2).
 // Returns 1 / L[i][i] for lane i.
 template <typename T>
-DEX_DEV_NOINLINE T dex_chol_factor(T* H, int n, int* fail) {
+DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int* fail) {
   const int i = dex_lane();
   T* rowi = H + i * DEX_MSTRIDE;
-  for (int j = i + 1; j < DEX_MSTRIDE; ++j) rowi[j] = 0;
-  if (i >= n) { for (int j = 0; j <= i; ++j) rowi[j] = (j == i) ? T(1) : T(0); }
-  dex_syncwarp();
   bool bad = false;
   T inv_mine = 1;
-  for (int k = 0; k < n; ++k) {
-    const T* rowk = H + k * DEX_MSTRIDE;
-    const int k4 = k & ~3;
-    T s = rowi[k] - dex_dot4(rowi, rowk, k4);
-    for (int j = k4; j < k; ++j) s -= rowi[j] * rowk[j];
-    T dkk = dex_shfl(s, k);
-    if (!(dkk > Real<T>::minval())) { bad = true; dkk = Real<T>::minval(); }
-    const T inv = dx_rsqrt(dkk);
-    if (i == k) inv_mine = inv;
-    if (i >= k && i < n) rowi[k] = s * inv;
+  const int nblk = (n + 3) >> 2;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = 4 * kb;
+    const DexVec4<T> a = *reinterpret_cast<const DexVec4<T>*>(rowi + k0);
+    T s0 = i == k0 ? hd : a.x, s1 = i == k0 + 1 ? hd : a.y, s2 = i == k0 + 2 ? hd : a.z, s3 = i == k0 + 3 ? hd : a.w;
+    const T* r0 = H + k0 * DEX_MSTRIDE;
+    for (int g = 0; g < k0; g += 4) {
+      const DexVec4<T> vi = *reinterpret_cast<const DexVec4<T>*>(rowi + g);
+      const DexVec4<T> v0 = *reinterpret_cast<const DexVec4<T>*>(r0 + g);
+      const DexVec4<T> v1 = *reinterpret_cast<const DexVec4<T>*>(r0 + DEX_MSTRIDE + g);
+      const DexVec4<T> v2 = *reinterpret_cast<const DexVec4<T>*>(r0 + 2 * DEX_MSTRIDE + g);
+      const DexVec4<T> v3 = *reinterpret_cast<const DexVec4<T>*>(r0 + 3 * DEX_MSTRIDE + g);
+      s0 -= vi.x * v0.x + vi.y * v0.y + vi.z * v0.z + vi.w * v0.w;
+      s1 -= vi.x * v1.x + vi.y * v1.y + vi.z * v1.z + vi.w * v1.w;
+      s2 -= vi.x * v2.x + vi.y * v2.y + vi.z * v2.z + vi.w * v2.w;
+      s3 -= vi.x * v3.x + vi.y * v3.y + vi.z * v3.z + vi.w * v3.w;
+    }
+    // 4 x 4 diagonal block: column k0 + r is final once the r earlier columns of the block are applied
+    T d = dex_shfl(s0, k0);
+    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    const T i0 = dx_rsqrt(d), l0 = s0 * i0;
+    s1 -= l0 * dex_shfl(l0, k0 + 1);
+    d = dex_shfl(s1, k0 + 1);
+    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    const T i1 = dx_rsqrt(d), l1 = s1 * i1;
+    s2 -= l0 * dex_shfl(l0, k0 + 2) + l1 * dex_shfl(l1, k0 + 2);
+    d = dex_shfl(s2, k0 + 2);
+    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    const T i2 = dx_rsqrt(d), l2 = s2 * i2;
+    s3 -= l0 * dex_shfl(l0, k0 + 3) + l1 * dex_shfl(l1, k0 + 3) + l2 * dex_shfl(l2, k0 + 3);
+    d = dex_shfl(s3, k0 + 3);
+    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    const T i3 = dx_rsqrt(d), l3 = s3 * i3;
+    DexVec4<T> o;
+    o.x = i > k0 ? l0 : T(0); o.y = i > k0 + 1 ? l1 : T(0); o.z = i > k0 + 2 ? l2 : T(0); o.w = i > k0 + 3 ? l3 : T(0);
+    *reinterpret_cast<DexVec4<T>*>(rowi + k0) = o;
+    if ((i >> 2) == kb) { const int r = i & 3; inv_mine = r == 0 ? i0 : (r == 1 ? i1 : (r == 2 ? i2 : i3)); }
     dex_syncwarp();
   }
   if (bad) *fail = 1;
   return inv_mine;
 }
 // Solves L L^T x = b with the factor left in H by dex_chol_factor; lane i holds b_i / returns x_i.
+// Both substitutions are unmasked thanks to the zero diagonal / upper triangle of the tile.
 template <typename T>
 DEX_DEV_NOINLINE T dex_chol_apply(const T* H, int n, T inv_mine, T b) {
   const int i = dex_lane();
   const T* rowi = H + i * DEX_MSTRIDE;
-  for (int k = 0; k < n; ++k) {
-    const T yk = dex_shfl(b * inv_mine, k);
-    if (i == k) b = yk; else if (i > k && i < n) b -= rowi[k] * yk;
+  const int n4 = (n + 3) & ~3;
+  for (int k = 0; k < n4; k += 4) {   // L y = b
+    const DexVec4<T> l = *reinterpret_cast<const DexVec4<T>*>(rowi + k);
+    b -= l.x * dex_shfl(b * inv_mine, k);
+    b -= l.y * dex_shfl(b * inv_mine, k + 1);
+    b -= l.z * dex_shfl(b * inv_mine, k + 2);
+    b -= l.w * dex_shfl(b * inv_mine, k + 3);
   }
-  for (int k = n - 1; k >= 0; --k) {
-    const T xk = dex_shfl(b * inv_mine, k);
-    if (i == k) b = xk; else if (i < k) b -= H[k * DEX_MSTRIDE + i] * xk;
+  b *= inv_mine;
+  const T* col = H + i;
+  for (int k = n4 - 1; k >= 0; k -= 4) {   // L^T x = y
+    const T c0 = col[k * DEX_MSTRIDE], c1 = col[(k - 1) * DEX_MSTRIDE], c2 = col[(k - 2) * DEX_MSTRIDE], c3 = col[(k - 3) * DEX_MSTRIDE];
+    b -= c0 * dex_shfl(b * inv_mine, k);
+    b -= c1 * dex_shfl(b * inv_mine, k - 1);
+    b -= c2 * dex_shfl(b * inv_mine, k - 2);
+    b -= c3 * dex_shfl(b * inv_mine, k - 3);
   }
-  return b;
+  return b * inv_mine;
+}
+// Fills the warp's Cholesky tile from a symmetric matrix stored with rows of 32 (global scratch):
+// strictly lower part of the leading n x n block, zeros elsewhere; returns this lane's diagonal entry.
+template <typename T>
+DEX_DEV T dex_chol_load(T* H, const T* Mg, int n) {
+  const int lane = dex_lane();
+  for (int j = 0; j < 32; ++j) H[j * DEX_MSTRIDE + lane] = (lane < j && j < n) ? Mg[j * 32 + lane] : T(0);
+  return lane < n ? Mg[lane * 32 + lane] : T(1);
 }
 // y_i = sum_j M[j][i] x_j (M symmetric) with M in the env's global scratch (rows of 32, read coalesced
 // with lane = column) and x in shared memory.
@@ -574,9 +610,8 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     const unsigned sig_changed = dex_ballot(asig != asig_prev || hdiag != hdiag_prev);
     asig_prev = asig; hdiag_prev = hdiag;
     if (iter == 0 || sig_changed) {
-      for (int j = 0; j < nv; ++j) H[j * DEX_MSTRIDE + lane] = M[j * 32 + lane];   // H[j][lane] = M[j][lane]
+      T hd = dex_chol_load(H, M, nv) + hdiag;
       dex_syncwarp();
-      if (isdof) H[lane * DEX_MSTRIDE + lane] += hdiag;
       for (int c = 0; c < ncon; ++c) {
         const T* cdt = cdat + c * DEX_CDAT_STRIDE;
         const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
@@ -585,16 +620,17 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
         const T a0 = Jc[(3 * c) * DEX_JC_ROW + lane], a1 = Jc[(3 * c + 1) * DEX_JC_ROW + lane], a2 = Jc[(3 * c + 2) * DEX_JC_ROW + lane];
         const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
         const bool mine = isdof && ((mask >> lane) & 1u);
+        if (mine) hd += t0 * a0 + t1 * a1 + t2 * a2;
         while (mask) {
           const int j = dex_ffs(mask) - 1;
           mask &= mask - 1;
           const T b0 = dex_shfl(a0, j), b1 = dex_shfl(a1, j), b2 = dex_shfl(a2, j);
-          if (mine) H[lane * DEX_MSTRIDE + j] += t0 * b0 + t1 * b1 + t2 * b2;
+          if (mine && j < lane) H[lane * DEX_MSTRIDE + j] += t0 * b0 + t1 * b1 + t2 * b2;
         }
       }
       dex_syncwarp();
       int cfail = 0;
-      hinv = dex_chol_factor(H, nv, &cfail);
+      hinv = dex_chol_factor(H, hd, nv, &cfail);
       if (cfail) status |= DEX_STATUS_CHOL_FAIL;
     }
     const T search = dex_chol_apply(H, nv, hinv, isdof ? -grad : T(0));
@@ -679,12 +715,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   // only the leading m.nv_euler dofs belong to kinematic trees with joint damping; for the rest
   // (e.g. the free object) M + hB = M is block-decoupled and the solver's qacc is already the answer
   const int ne = m.nv_euler;
-  for (int j = 0; j < ne; ++j) H[j * DEX_MSTRIDE + lane] = M[j * 32 + lane];
-  dex_syncwarp();
-  if (lane < ne) H[lane * DEX_MSTRIDE + lane] += h * damping;
+  const T ehd = dex_chol_load(H, M, ne) + (lane < ne ? h * damping : T(0));
   dex_syncwarp();
   int efail = 0;
-  const T einv = dex_chol_factor(H, ne, &efail);
+  const T einv = dex_chol_factor(H, ehd, ne, &efail);
   T qacc_e = dex_chol_apply(H, ne, einv, lane < ne ? (fs + qfrc_constraint) : T(0));
   if (lane >= ne) qacc_e = qacc;
   const T qv_new = qv + h * qacc_e;

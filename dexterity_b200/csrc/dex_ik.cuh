@@ -96,18 +96,21 @@ DEX_DEV void dex_ik_env(const DevModel<T>& m, const DexIkParams& p, const T* tar
       }
       dex_syncwarp();
       // ---- normal matrix row: (J^T J + lambda I)[lane][j]  (dls.py:69-74)
-      for (int j = 0; j < nv; ++j) {
+      T hd = 1;
+      for (int j = 0; j < 32; ++j) {
         T a = (j == lane) ? (T)p.regularization : T(0);
         for (int s = 0; s < p.nsite; ++s) {
           const T* x = jp + (s * 32 + lane) * 4;
           const T* y = jp + (s * 32 + j) * 4;
           a += x[0] * y[0] + x[1] * y[1] + x[2] * y[2];
         }
-        if (isdof) H[lane * DEX_MSTRIDE + j] = a;
+        const bool in = isdof && j < nv;
+        if (in && j == lane) hd = a;
+        H[lane * DEX_MSTRIDE + j] = (in && j < lane) ? a : T(0);
       }
       dex_syncwarp();
       int fail = 0;
-      const T hinv = dex_chol_factor(H, nv, &fail);
+      const T hinv = dex_chol_factor(H, hd, nv, &fail);
       const T qdot = dex_chol_apply(H, nv, hinv, isdof ? rhs : T(0));
       // ---- integrate (dt = 1), clip to the joint range (ik_solver.py:189-194, 240-246)
       q = dx_clamp(q + qdot, lo, hi);
