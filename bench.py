@@ -187,7 +187,7 @@ def run_gpu(args):
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = env.physics.launch_count - launches0
-    ms4 = (ctypes.c_double * 4)(); cnt4 = (ctypes.c_int64 * 4)()
+    ms4 = (ctypes.c_double * 8)(); cnt4 = (ctypes.c_int64 * 8)()
     backend._check(lib.dex_get_kernel_times(env.physics.ptr, ms4, cnt4, 1))
     lib.dex_set_profiling(env.physics.ptr, 0)
     clocks = sampler.stop() if rank == 0 else None
@@ -225,8 +225,8 @@ def run_gpu(args):
         value = total_envs * args.steps / (dev_ms_max * 1e-3)
         e2e_value = total_envs * args.steps / (e2e_ms_max * 1e-3)
         peak, peak_src = measured_peaks()
-        names = ["task_pre", "k_collide", "k_dynamics", "task_post"]
-        per = {names[c]: (ms4[c] / max(1, cnt4[c]), cnt4[c]) for c in range(4)}
+        names = ["task_pre", "k_collide", "k_dynamics", "task_post", "k_tree"]
+        per = {names[c]: (ms4[c] / max(1, cnt4[c]), cnt4[c]) for c in range(5)}
         dom = max(("k_collide", "k_dynamics"), key=lambda k_: per[k_][0])
         dom_ms = per[dom][0]
         achieved = n * B_MJ / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

@@ -14,6 +14,7 @@
 #include "dex_host_model.h"
 #include "dex_ik.cuh"
 #include "dex_task.cuh"
+#include "dex_tree.cuh"
 
 namespace {
 
@@ -30,11 +31,20 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #endif
 constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 
+constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps spread over all SMs
+template <typename T>
+__global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {
+  const int env = blockIdx.x * kTreeBlock + threadIdx.x;
+  if (env >= st.nenv) return;
+  dex_tree_env<T>(m, st, env);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_collide(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
+  if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K1_SMEM_T;
   dex_collide_env<T>(m, st, env, smem);
 }
@@ -45,6 +55,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) k_dynamics(DevModel<T>
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
+  if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
 }
@@ -144,9 +155,9 @@ struct DexBatch {
   bool task_set = false;
   // optional per-kernel-class timing (cudaEvent pairs recorded on the launching stream)
   bool profiling = false;
-  std::vector<cudaEvent_t> ev[4];   // class: 0 pre, 1 collide, 2 dynamics, 3 post; pairs (start, stop)
-  double ms[4] = {0, 0, 0, 0};
-  int64_t count[4] = {0, 0, 0, 0};
+  std::vector<cudaEvent_t> ev[8];   // class: 0 pre, 1 collide, 2 dynamics, 3 post, 4 tree; pairs (start, stop)
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -165,8 +176,10 @@ struct ProfScope {  // records an event pair around one launch when profiling is
 
 template <typename T>
 int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, bool use_skip = false) {
-  static const int req_col[] = {DEX_FIELD_QPOS, DEX_FIELD_STATUS, DEX_FIELD_CONTACT, DEX_FIELD_NCON};
-  static const int req_dyn[] = {DEX_FIELD_QVEL, DEX_FIELD_CTRL, DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER, DEX_FIELD_JC, DEX_FIELD_MSCR};
+  // the tree kernel (K0) always runs, so its inputs and scratch are required by every entry point
+  static const int req_col[] = {DEX_FIELD_QPOS, DEX_FIELD_STATUS, DEX_FIELD_CONTACT, DEX_FIELD_NCON, DEX_FIELD_QVEL, DEX_FIELD_CTRL,
+                                DEX_FIELD_MSCR, DEX_FIELD_XKIN, DEX_FIELD_TREE};
+  static const int req_dyn[] = {DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER, DEX_FIELD_JC};
   for (int f : req_col) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   if (need_dyn) for (int f : req_dyn) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   st.nenv = b->nenv;
@@ -182,6 +195,8 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.skip = use_skip ? (const unsigned char*)b->ptr[DEX_FIELD_SKIP] : nullptr;
   st.jc = (T*)b->ptr[DEX_FIELD_JC];
   st.mscr = (T*)b->ptr[DEX_FIELD_MSCR];
+  st.xkin = (T*)b->ptr[DEX_FIELD_XKIN];
+  st.tree = (T*)b->ptr[DEX_FIELD_TREE];
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
   dbg.qacc = (T*)b->ptr[DEX_FIELD_DBG_QACC];
@@ -205,7 +220,9 @@ int run(DexBatch* b, const DevModel<T>& m, int nsub, bool collide, bool dynamics
     b->attrs_set = true;
   }
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int tgrid = (b->nenv + kTreeBlock - 1) / kTreeBlock;
   for (int i = 0; i < nsub; ++i) {
+    { ProfScope ps(b, 4, s); k_tree<T><<<tgrid, kTreeBlock, 0, s>>>(m, st); b->launches++; }
     if (collide) { ProfScope ps(b, 1, s); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, s>>>(m, st); b->launches++; }
     if (dynamics) { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, s>>>(m, st, dbg, integrate); b->launches++; }
   }
@@ -243,7 +260,9 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
   const int block = kWarpsPerBlock * 32;
   if (phases & 1) { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
   if ((phases & 2) && !force_reset) {
+    const int tgrid = (b->nenv + kTreeBlock - 1) / kTreeBlock;
     for (int i = 0; i < nsub; ++i) {
+      { ProfScope ps(b, 4, s); k_tree<T><<<tgrid, kTreeBlock, 0, s>>>(m, st); b->launches++; }
       { ProfScope ps(b, 1, s); k_collide<T><<<grid, block, smem1, s>>>(m, st); b->launches++; }
       { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, block, smem2, s>>>(m, st, dbg, 1); b->launches++; }
     }
@@ -388,12 +407,12 @@ int dex_set_profiling(DexBatch* b, int on) {
   return DEX_OK;
 }
 // Synchronises the device, folds the recorded event pairs into per-class totals and returns
-// ms[4] (total milliseconds) and count[4] (launches) for pre / collide / dynamics / post.
+// ms[8] (total milliseconds) and count[8] (launches) for pre / collide / dynamics / post / tree / (3 reserved).
 int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
   if (!b || !ms || !count) return fail(DEX_E_ARG, "null argument");
   DEX_CUDA(cudaSetDevice(b->model->device));
   DEX_CUDA(cudaDeviceSynchronize());
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 8; ++c) {
     for (size_t i = 0; i + 1 < b->ev[c].size(); i += 2) {
       float t = 0;
       if (cudaEventElapsedTime(&t, b->ev[c][i], b->ev[c][i + 1]) == cudaSuccess) { b->ms[c] += t; b->count[c]++; }

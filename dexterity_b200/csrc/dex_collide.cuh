@@ -20,6 +20,7 @@
 #define DEX_COLLIDE_CUH_
 
 #include "dex_kin.cuh"
+#include "dex_tree.cuh"
 
 // per-warp shared-memory footprint of K1, in units of T
 #define DEX_MAXCAND1 384   // capacity of the sphere-test survivor list (pass 1)
@@ -345,19 +346,24 @@ DEX_DEV void dex_store_contact(T* dst, T dist, const T* pos, const T* normal, in
 
 template <typename T>
 DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
-  if (env >= st.nenv || (st.skip && st.skip[env])) { dex_phase_sync(); dex_phase_sync(); return; }  // warp-uniform
+  if (env >= st.nenv || (st.skip && st.skip[env])) return;  // warp-uniform
   const int lane = dex_lane();
   T* xpos = smem;
   T* xquat = xpos + DEX_MAXBODY * 3;
   T* xmat = xquat + DEX_MAXBODY * 4;
-  T* qpos = xmat + DEX_MAXBODY * 9;           // 48
-  int* cand = (int*)(qpos + 48);              // DEX_MAXCAND ints (fits: sizeof(int) <= sizeof(T))
-  for (int i = lane; i < m.nq; i += 32) qpos[i] = st.qpos[(size_t)env * st.qpos_stride + i];
+  int* cand = (int*)(xmat + DEX_MAXBODY * 9 + 48);  // DEX_MAXCAND1 ints (fits: sizeof(int) <= sizeof(T))
+  (void)xquat;
+  {  // body poses of K0 (dex_tree.cuh): records of 16 = xpos(3) xquat(4) xmat(9)
+    const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
+    for (int i = lane; i < m.nbody * DEX_XKIN_BODY; i += 32) {
+      const int b = i >> 4, e = i & 15;
+      const T v = xk[i];
+      if (e < 3) xpos[3 * b + e] = v;
+      else if (e >= 7) xmat[9 * b + e - 7] = v;
+    }
+  }
   dex_syncwarp();
-  KinBuf<T> kb = {xpos, xquat, xmat, nullptr, nullptr};
-  dex_fk(m, qpos, kb);
 
-  dex_phase_sync();
   // ---- broadphase
   int ncand = 0;
   for (int bp0 = 0; bp0 < m.nbodypair; bp0 += 32) {
@@ -480,7 +486,6 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     ncand = nkeep;
   }
   dex_syncwarp();
-  dex_phase_sync();
 
   // ---- narrowphase
   T* cout = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;

@@ -1,54 +1,34 @@
-// dex_dynamics.cuh — K2: warp-per-env smooth dynamics, constraint assembly, Newton solve and
-// semi-implicit Euler (restates SURVEY.md §8a rows 11-13 and 15-20):
-//   mj_comPos (cinert/cdof about a per-tree reference point), mj_crb (dense M in smem),
-//   mj_comVel, mj_rne (bias; constant xfrc_applied folded in as external body forces),
-//   mj_passive (joint damping), mj_fwdActuation (affine actuators over joints / fixed tendons),
-//   mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint (dof friction loss, joint
-//   limits, pyramidal contacts), mj_solNewton (exact Hessian M + J^T D J, warp Cholesky, exact
-//   line search), mj_Euler with implicit joint damping.
+// dex_dynamics.cuh — K2: warp-per-env constraint assembly, Newton solve and semi-implicit Euler
+// (restates SURVEY.md §8a rows 15 and 19-20): mj_makeConstraint + mj_makeImpedance +
+// mj_referenceConstraint (dof friction loss, joint limits, pyramidal contacts), mj_solNewton (exact
+// Hessian M + J^T D J, warp Cholesky, exact line search), mj_Euler with implicit joint damping.
+// The smooth dynamics (cdof, M, qfrc_smooth) are produced by K0 (dex_tree.cuh).
 //
-// Lane mapping: lane = dof for every per-dof vector (kept in registers), lane = body for the
-// tree passes (level by level), lane = contact for per-contact scalars.  The contact-frame
-// Jacobian Jc[c][3][nv] lives in the warp's shared-memory slice; rows of friction loss and
-// joint limits are +-unit vectors and are never materialised.
+// Lane mapping: lane = dof for every per-dof vector (kept in registers), lane = contact for
+// per-contact scalars.  The contact-frame Jacobian Jc[c][3][nv] lives in a global (L2) scratch; rows
+// of friction loss and joint limits are +-unit vectors and are never materialised.
 #ifndef DEX_DYNAMICS_CUH_
 #define DEX_DYNAMICS_CUH_
 
 #include "dex_kin.cuh"
+#include "dex_tree.cuh"
 
 #define DEX_MSTRIDE 36   // rows 16-byte aligned; LDS.128 of 8 consecutive rows is bank-conflict free
-// shared memory per warp (units of T).  The Hessian / contact scratch (union B) aliases the tree-pass
-// temporaries (union A), which are dead once qfrc_smooth is known; the contact-frame Jacobian lives
-// in an L2-resident global scratch (BatchState::jc), not in shared memory -> ~15 KB per warp (FP32).
-#define DEX_K2_OFF_XPOS 0
-#define DEX_K2_OFF_XQUAT (DEX_K2_OFF_XPOS + DEX_MAXBODY * 3)
-#define DEX_K2_OFF_XMAT (DEX_K2_OFF_XQUAT + DEX_MAXBODY * 4)
-#define DEX_K2_OFF_REF (DEX_K2_OFF_XMAT + DEX_MAXBODY * 9)
+// shared memory per warp (units of T): small per-dof vectors plus the Cholesky tile and the per-contact
+// records.  The tree quantities (cdof, qfrc_smooth, M) come from K0 (dex_tree.cuh) through global
+// scratch; the contact-frame Jacobian lives in an L2-resident global scratch (BatchState::jc).
+#define DEX_K2_OFF_REF 0
 #define DEX_K2_OFF_QPOS (DEX_K2_OFF_REF + 16)
 #define DEX_K2_OFF_QVEL (DEX_K2_OFF_QPOS + 48)
 #define DEX_K2_OFF_VECA (DEX_K2_OFF_QVEL + 32)
 #define DEX_K2_OFF_VECB (DEX_K2_OFF_VECA + 32)
-#define DEX_K2_OFF_UNION (DEX_K2_OFF_VECB + 32)
-//   union A (tree passes)
-#define DEX_K2_OFF_XANCHOR DEX_K2_OFF_UNION
-#define DEX_K2_OFF_XAXIS (DEX_K2_OFF_XANCHOR + DEX_MAXJNT * 3)
-#define DEX_K2_OFF_CDOF (DEX_K2_OFF_XAXIS + DEX_MAXJNT * 3)
-#define DEX_K2_OFF_CINERT (DEX_K2_OFF_CDOF + DEX_MAXDOF * 6)
-#define DEX_K2_OFF_CVEL (DEX_K2_OFF_CINERT + DEX_MAXBODY * 10)
-#define DEX_K2_OFF_CDOFDOT (DEX_K2_OFF_CVEL + DEX_MAXBODY * 6)
-#define DEX_K2_OFF_CACC (DEX_K2_OFF_CDOFDOT + DEX_MAXDOF * 6)
-#define DEX_K2_OFF_CFRC (DEX_K2_OFF_CACC + DEX_MAXBODY * 6)
-#define DEX_K2_UNION_A (DEX_MAXJNT * 6 + DEX_MAXDOF * 12 + DEX_MAXBODY * 28)
-//   union B (constraints + solver)
-#define DEX_K2_OFF_H DEX_K2_OFF_UNION
+#define DEX_K2_OFF_H (DEX_K2_OFF_VECB + 32)
 #define DEX_K2_OFF_CDAT (DEX_K2_OFF_H + 32 * DEX_MSTRIDE)
 #define DEX_CDAT_STRIDE 24
 #define DEX_K2_OFF_CDOT (DEX_K2_OFF_CDAT + DEX_MAXCON * DEX_CDAT_STRIDE)
-#define DEX_K2_UNION_B (32 * DEX_MSTRIDE + DEX_MAXCON * DEX_CDAT_STRIDE + 96)
-#define DEX_K2_SMEM_T (DEX_K2_OFF_UNION + (DEX_K2_UNION_A > DEX_K2_UNION_B ? DEX_K2_UNION_A : DEX_K2_UNION_B))
+#define DEX_K2_SMEM_T (DEX_K2_OFF_CDOT + 96)
 #define DEX_JC_ROW 32                         // global Jc scratch: [env][3 * DEX_MAXCON][DEX_JC_ROW]
 #define DEX_JC_ENV (3 * DEX_MAXCON * DEX_JC_ROW)
-#define DEX_MG_ENV (32 * 32)                  // global M scratch: [env][32][32] (symmetric, row j = M[j][:])
 
 // cdat layout per contact
 enum { CD_MU = 0, CD_D = 1, CD_AREF = 2 /*4*/, CD_JAR = 6 /*4*/, CD_JV = 10 /*4*/, CD_F = 14 /*3 frame-space force*/,
@@ -213,219 +193,36 @@ DEX_DEV void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
 template <typename T>
 DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int env,
                               T* smem, int integrate) {
-  if (env >= st.nenv || (st.skip && st.skip[env])) { dex_phase_sync(); dex_phase_sync(); dex_phase_sync(); return; }  // warp-uniform
+  if (env >= st.nenv || (st.skip && st.skip[env])) { return; }  // warp-uniform
   const int lane = dex_lane();
-  const int nv = m.nv, nb = m.nbody;
-  T* xpos = smem + DEX_K2_OFF_XPOS;
-  T* xquat = smem + DEX_K2_OFF_XQUAT;
-  T* xmat = smem + DEX_K2_OFF_XMAT;
-  T* xanchor = smem + DEX_K2_OFF_XANCHOR;
-  T* xaxis = smem + DEX_K2_OFF_XAXIS;
+  const int nv = m.nv;
   T* ref = smem + DEX_K2_OFF_REF;
-  T* cdof = smem + DEX_K2_OFF_CDOF;
   T* qpos = smem + DEX_K2_OFF_QPOS;
   T* qvel = smem + DEX_K2_OFF_QVEL;
   T* vecA = smem + DEX_K2_OFF_VECA;
   T* vecB = smem + DEX_K2_OFF_VECB;
-  T* M = st.mscr + (size_t)env * DEX_MG_ENV;  // global scratch (L2 resident), symmetric
+  T* M = st.mscr + (size_t)env * DEX_MG_ENV;  // global scratch (L2 resident), symmetric, written by K0
   T* H = smem + DEX_K2_OFF_H;
-  T* cinert = smem + DEX_K2_OFF_CINERT;
-  T* crb = cinert;  // composite inertias are accumulated in place once the RNE pass has used cinert
-  T* cvel = smem + DEX_K2_OFF_CVEL;
-  T* cdofdot = smem + DEX_K2_OFF_CDOFDOT;
-  T* cacc = smem + DEX_K2_OFF_CACC;
-  T* cfrc = smem + DEX_K2_OFF_CFRC;
   T* Jc = st.jc + (size_t)env * DEX_JC_ENV;  // global scratch (L2 resident)
   T* cdat = smem + DEX_K2_OFF_CDAT;
   T* cdot = smem + DEX_K2_OFF_CDOT;
   const T h = m.timestep;
   unsigned status = 0;
 
-  // ------------------------------------------------------------------ load state
+  // ------------------------------------------------------------------ load state and the tree quantities of K0
   for (int i = lane; i < m.nq; i += 32) qpos[i] = st.qpos[(size_t)env * st.qpos_stride + i];
   const bool isdof = lane < nv;
   const T qv = isdof ? st.qvel[(size_t)env * st.qvel_stride + lane] : T(0);
   T qacc = isdof ? st.warm[(size_t)env * st.warm_stride + lane] : T(0);
   qvel[lane] = qv;
-  dex_syncwarp();
-
-  // ------------------------------------------------------------------ kinematics
-  KinBuf<T> kb = {xpos, xquat, xmat, xanchor, xaxis};
-  dex_fk(m, qpos, kb);
-  if (lane < m.ntree) {
-    const int rb = dex_ldg(m.tree_refbody + lane);
-    ref[3 * lane] = xpos[3 * rb]; ref[3 * lane + 1] = xpos[3 * rb + 1]; ref[3 * lane + 2] = xpos[3 * rb + 2];
-  }
-  dex_syncwarp();
-
-  dex_phase_sync();
-  // ------------------------------------------------------------------ cdof (lane = dof), cinert (lane = body)
+  const T* tree = st.tree + (size_t)env * DEX_TREE_ENV;
   T cd[6];
-  dex_cdof_lane(m, lane, xpos, xmat, xanchor, xaxis, ref, cd);
-  const int dbody = isdof ? dex_ldg(m.dof_body + lane) : 0;
-  if (isdof) for (int k = 0; k < 6; ++k) cdof[6 * lane + k] = cd[k];
-  for (int b = lane; b < nb; b += 32) {
-    T c[10];
-    const T mass = dex_ldg(m.body_mass + b);
-    const T* R = xmat + 9 * b;
-    T ip[3] = {dex_ldg(m.body_ipos + 3 * b), dex_ldg(m.body_ipos + 3 * b + 1), dex_ldg(m.body_ipos + 3 * b + 2)}, off[3];
-    rot_vec(off, R, ip);
-    const T* rp = ref + 3 * dex_ldg(m.body_tree + b);
-    off[0] += xpos[3 * b] - rp[0]; off[1] += xpos[3 * b + 1] - rp[1]; off[2] += xpos[3 * b + 2] - rp[2];
-    // I_world = R I_body R^T, I_body = [xx yy zz xy xz yz]
-    const T* I6 = m.body_inertia6 + 6 * b;
-    T Ib[9] = {dex_ldg(I6), dex_ldg(I6 + 3), dex_ldg(I6 + 4), dex_ldg(I6 + 3), dex_ldg(I6 + 1), dex_ldg(I6 + 5),
-               dex_ldg(I6 + 4), dex_ldg(I6 + 5), dex_ldg(I6 + 2)};
-    T RI[9];
-    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc)
-      RI[3 * r + cc] = R[3 * r] * Ib[cc] + R[3 * r + 1] * Ib[3 + cc] + R[3 * r + 2] * Ib[6 + cc];
-    T Iw[6];  // xx yy zz xy xz yz
-    Iw[0] = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2];
-    Iw[1] = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5];
-    Iw[2] = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8];
-    Iw[3] = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5];
-    Iw[4] = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8];
-    Iw[5] = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8];
-    const T o2 = dot3(off, off);
-    c[0] = Iw[0] + mass * (o2 - off[0] * off[0]);
-    c[1] = Iw[1] + mass * (o2 - off[1] * off[1]);
-    c[2] = Iw[2] + mass * (o2 - off[2] * off[2]);
-    c[3] = Iw[3] - mass * off[0] * off[1];
-    c[4] = Iw[4] - mass * off[0] * off[2];
-    c[5] = Iw[5] - mass * off[1] * off[2];
-    c[6] = mass * off[0]; c[7] = mass * off[1]; c[8] = mass * off[2]; c[9] = mass;
-    for (int k = 0; k < 10; ++k) cinert[10 * b + k] = c[k];
-    // external spatial force about the reference point: [tau + off x f ; f]
-    const T* xf = m.body_xfrc + 6 * b;
-    T f[3] = {dex_ldg(xf), dex_ldg(xf + 1), dex_ldg(xf + 2)}, tq[3];
-    cross3(tq, off, f);
-    cfrc[6 * b] = -(dex_ldg(xf + 3) + tq[0]); cfrc[6 * b + 1] = -(dex_ldg(xf + 4) + tq[1]); cfrc[6 * b + 2] = -(dex_ldg(xf + 5) + tq[2]);
-    cfrc[6 * b + 3] = -f[0]; cfrc[6 * b + 4] = -f[1]; cfrc[6 * b + 5] = -f[2];
-  }
-  for (int t = lane; t < DEX_MG_ENV; t += 32) M[t] = 0;
-  dex_syncwarp();
-
-  // ------------------------------------------------------------------ mj_comVel + mj_rne (forward), lane = body by level
-  for (int L = 0; L <= m.maxdepth; ++L) {
-    for (int b = lane; b < nb; b += 32) {
-      if (dex_ldg(m.body_depth + b) != L) continue;
-      T v[6], a[6];
-      if (b == 0) {
-        for (int k = 0; k < 6; ++k) { v[k] = 0; a[k] = 0; }
-        a[3] = -m.gravity[0]; a[4] = -m.gravity[1]; a[5] = -m.gravity[2];
-      } else {
-        const int p = dex_ldg(m.body_parent + b);
-        for (int k = 0; k < 6; ++k) { v[k] = cvel[6 * p + k]; a[k] = cacc[6 * p + k]; }
-        const int ja = dex_ldg(m.body_jntadr + b), jn = dex_ldg(m.body_jntnum + b);
-        for (int j = ja; j < ja + jn; ++j) {
-          const int da = dex_ldg(m.jnt_dofadr + j);
-          if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
-            for (int i = 0; i < 3; ++i) {
-              for (int k = 0; k < 6; ++k) { cdofdot[6 * (da + i) + k] = 0; v[k] += cdof[6 * (da + i) + k] * qvel[da + i]; }
-            }
-            T cdd[3][6];
-            for (int i = 0; i < 3; ++i) cross_motion(cdd[i], v, cdof + 6 * (da + 3 + i));
-            for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) {
-              cdofdot[6 * (da + 3 + i) + k] = cdd[i][k];
-              v[k] += cdof[6 * (da + 3 + i) + k] * qvel[da + 3 + i];
-              a[k] += cdd[i][k] * qvel[da + 3 + i];
-            }
-          } else {
-            T cdd[6];
-            cross_motion(cdd, v, cdof + 6 * da);
-            for (int k = 0; k < 6; ++k) {
-              cdofdot[6 * da + k] = cdd[k];
-              v[k] += cdof[6 * da + k] * qvel[da];
-              a[k] += cdd[k] * qvel[da];
-            }
-          }
-        }
-      }
-      for (int k = 0; k < 6; ++k) { cvel[6 * b + k] = v[k]; cacc[6 * b + k] = a[k]; }
-      if (b > 0) {
-        T t1[6], t2[6], t3[6];
-        mul_inert_vec(t1, cinert + 10 * b, a);
-        mul_inert_vec(t2, cinert + 10 * b, v);
-        cross_force(t3, v, t2);
-        for (int k = 0; k < 6; ++k) cfrc[6 * b + k] += t1[k] + t3[k];
-      }
-    }
-    dex_syncwarp();
-  }
-  for (int L = m.maxdepth; L >= 1; --L) {
-    for (int b = lane; b < nb; b += 32) {
-      if (dex_ldg(m.body_depth + b) != L) continue;
-      const int p = dex_ldg(m.body_parent + b);
-      if (p > 0) for (int k = 0; k < 6; ++k) dex_atomic_add(cfrc + 6 * p + k, cfrc[6 * b + k]);
-    }
-    dex_syncwarp();
-  }
-  T bias = 0;
-  if (isdof) {
-    const T* cf = cfrc + 6 * dbody;
-    bias = cd[0] * cf[0] + cd[1] * cf[1] + cd[2] * cf[2] + cd[3] * cf[3] + cd[4] * cf[4] + cd[5] * cf[5];
-  }
-
-  // ------------------------------------------------------------------ composite inertia (backward), M
-  for (int L = m.maxdepth; L >= 1; --L) {
-    for (int b = lane; b < nb; b += 32) {
-      if (dex_ldg(m.body_depth + b) != L) continue;
-      const int p = dex_ldg(m.body_parent + b);
-      if (p > 0) for (int k = 0; k < 10; ++k) dex_atomic_add(crb + 10 * p + k, crb[10 * b + k]);
-    }
-    dex_syncwarp();
-  }
-  if (isdof) {
-    T buf[6];
-    mul_inert_vec(buf, crb + 10 * dbody, cd);
-    for (int j = lane; j >= 0; j = dex_ldg(m.dof_parent + j)) {
-      const T* cj = cdof + 6 * j;
-      T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
-      if (j == lane) s += dex_ldg(m.dof_armature + lane);
-      M[lane * 32 + j] = s;
-      M[j * 32 + lane] = s;
-    }
-  }
-  dex_syncwarp();
-
-  // ------------------------------------------------------------------ actuation (lane = actuator), passive
-  vecA[lane] = 0;
-  dex_syncwarp();
-  if (lane < m.nu) {
-    const int a = lane, tid = dex_ldg(m.act_trnid + a);
-    const T gear = dex_ldg(m.act_gear + a);
-    T length = 0, vel = 0;
-    if (dex_ldg(m.act_trntype + a) == 0) {
-      length = qpos[dex_ldg(m.jnt_qposadr + tid)];
-      vel = qvel[dex_ldg(m.jnt_dofadr + tid)];
-    } else {
-      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
-      for (int w = wa; w < wa + wn; ++w) {
-        const int j = dex_ldg(m.wrap_jnt + w);
-        const T c = dex_ldg(m.wrap_coef + w);
-        length += c * qpos[dex_ldg(m.jnt_qposadr + j)];
-        vel += c * qvel[dex_ldg(m.jnt_dofadr + j)];
-      }
-    }
-    length *= gear; vel *= gear;
-    T c = st.ctrl[(size_t)env * st.ctrl_stride + a];
-    if (dex_ldg(m.act_ctrllimited + a)) c = dx_clamp(c, dex_ldg(m.act_ctrlrange + 2 * a), dex_ldg(m.act_ctrlrange + 2 * a + 1));
-    T f = dex_ldg(m.act_gainprm + 3 * a) * c + dex_ldg(m.act_biasprm + 3 * a) + dex_ldg(m.act_biasprm + 3 * a + 1) * length +
-          dex_ldg(m.act_biasprm + 3 * a + 2) * vel;
-    if (dex_ldg(m.act_forcelimited + a)) f = dx_clamp(f, dex_ldg(m.act_forcerange + 2 * a), dex_ldg(m.act_forcerange + 2 * a + 1));
-    if (dex_ldg(m.act_trntype + a) == 0) dex_atomic_add(vecA + dex_ldg(m.jnt_dofadr + tid), gear * f);
-    else {
-      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
-      for (int w = wa; w < wa + wn; ++w)
-        dex_atomic_add(vecA + dex_ldg(m.jnt_dofadr + dex_ldg(m.wrap_jnt + w)), gear * dex_ldg(m.wrap_coef + w) * f);
-    }
-  }
-  dex_syncwarp();
+  for (int k = 0; k < 6; ++k) cd[k] = isdof ? tree[k * 32 + lane] : T(0);
+  const T fs = isdof ? tree[DEX_TREE_ROW_FS * 32 + lane] : T(0);  // qfrc_smooth
+  if (lane < 16) ref[lane] = tree[DEX_TREE_ROW_REF * 32 + lane];
   const T damping = isdof ? dex_ldg(m.dof_damping + lane) : T(0);
-  const T fs = isdof ? (-damping * qv - bias + vecA[lane]) : T(0);  // qfrc_smooth
-  dex_syncwarp();  // union A is dead from here on (cinert/crb/cvel/cacc/cfrc); union B may be written
+  dex_syncwarp();
 
-  dex_phase_sync();
   // ------------------------------------------------------------------ constraint rows
   // friction loss (lane = dof)
   T f_loss = 0, f_R = 1, f_D = 0, f_aref = 0;
@@ -526,7 +323,6 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   }
   dex_syncwarp();
 
-  dex_phase_sync();
   // ------------------------------------------------------------------ Newton solver (mj_solNewton)
   const T scale = 1 / (m.meaninertia * (nv > 1 ? nv : 1));
   const T tol = dx_max(m.tolerance, sizeof(T) == 4 ? T(1e-6) : T(1e-12));

@@ -90,7 +90,18 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
   const int nb = M.nbody, nv = M.nv;
   M.body_depth.assign(nb, 0);
   M.maxdepth = 0;
-  for (int b = 1; b < nb; ++b) { M.body_depth[b] = M.body_depth[M.body_parent[b]] + 1; M.maxdepth = std::max(M.maxdepth, M.body_depth[b]); }
+  for (int b = 1; b < nb; ++b) {
+    if (M.body_parent[b] < 0 || M.body_parent[b] >= b) return "bodies must be ordered parent before child";
+    M.body_depth[b] = M.body_depth[M.body_parent[b]] + 1; M.maxdepth = std::max(M.maxdepth, M.body_depth[b]);
+  }
+  if (M.maxdepth >= 16) return "kinematic tree deeper than DEX_MAXDEPTH (16)";
+  {  // the tree kernel walks the bodies with a depth-indexed stack: requires DFS pre-order (MuJoCo's body order)
+    std::vector<int> open(M.maxdepth + 1, 0);
+    for (int b = 1; b < nb; ++b) {
+      if (open[M.body_depth[b] - 1] != M.body_parent[b]) return "bodies are not in depth-first pre-order";
+      open[M.body_depth[b]] = b;
+    }
+  }
   std::vector<int> broot = I(DEXF_BODY_ROOT);
   std::map<int, int> tree_of_root;
   M.body_tree.assign(nb, 0);

@@ -80,7 +80,9 @@ struct BatchState {
   int* niter;                     // [nenv] solver iterations of the last mj_step
   const unsigned char* skip;      // optional [nenv]: 1 = leave this env untouched (it was just reset)
   T* jc;                          // [nenv][3*DEX_MAXCON][32] contact-frame Jacobian scratch (L2 resident)
-  T* mscr;                        // [nenv][32][32] mass-matrix scratch (L2 resident)
+  T* mscr;                        // [nenv][32][32] dense mass matrix (zero-initialised once; K0 writes the non-zeros)
+  T* xkin;                        // [nenv][DEX_MAXBODY][16] body poses of K0: xpos(3) xquat(4) xmat(9)
+  T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
 };
 
 // ---------------------------------------------------------------------------------------

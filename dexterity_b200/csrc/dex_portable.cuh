@@ -23,12 +23,6 @@ template <typename T> DEX_DEV T dex_shfl(T v, int src) { return __shfl_sync(DEX_
 template <typename T> DEX_DEV T dex_shfl_xor(T v, int m) { return __shfl_xor_sync(DEX_FULL, v, m); }
 DEX_DEV unsigned dex_ballot(bool p) { return __ballot_sync(DEX_FULL, p); }
 DEX_DEV void dex_syncwarp() { __syncwarp(); }
-// CTA-wide phase alignment (keeps the CTA's warps in the same code region -> instruction-cache locality)
-#ifdef DEX_PHASE_BARRIERS
-DEX_DEV void dex_phase_sync() { __syncthreads(); }
-#else
-DEX_DEV void dex_phase_sync() {}
-#endif
 template <typename T> DEX_DEV void dex_atomic_add(T* p, T v) { atomicAdd(p, v); }
 template <typename T> DEX_DEV T dex_ldg(const T* p) { return __ldg(p); }
 DEX_DEV int dex_popc(unsigned x) { return __popc(x); }
@@ -57,7 +51,6 @@ template <typename T> inline T dex_shfl(T v, int src) {
 template <typename T> inline T dex_shfl_xor(T v, int m) { return dex_shfl(v, dex_emu::lane() ^ m); }
 inline unsigned dex_ballot(bool p) { return dex_emu::ballot(p); }
 inline void dex_syncwarp() { dex_emu::barrier(); }
-inline void dex_phase_sync() {}
 template <typename T> inline void dex_atomic_add(T* p, T v) { *p += v; }  // fibers are serialised
 template <typename T> inline T dex_ldg(const T* p) { return *p; }
 inline int dex_popc(unsigned x) { return __builtin_popcount(x); }

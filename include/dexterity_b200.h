@@ -127,7 +127,10 @@ enum DexTaskFieldId {
   DEX_FIELD_RESET_MASK = 25,   /* u8   [nenv]        optional: envs to reset on the next dex_env_step           */
   DEX_FIELD_SKIP = 26,         /* u8   [nenv]        scratch: envs reset during the current call                */
   DEX_FIELD_JC = 27,           /* real [nenv][3*DEX_MAXCON][32] scratch: contact-frame Jacobians (stays in L2)       */
-  DEX_FIELD_MSCR = 28          /* real [nenv][32][32] scratch: dense mass matrix (stays in L2)                        */
+  DEX_FIELD_MSCR = 28,         /* real [nenv][32][32] scratch: dense mass matrix; MUST be zero-initialised by the caller (only
+                                  the structural non-zeros are rewritten each step)                                    */
+  DEX_FIELD_XKIN = 29,         /* real [nenv][DEX_MAXBODY][16] scratch: body poses xpos(3) xquat(4) xmat(9) (data.xpos/xquat/xmat) */
+  DEX_FIELD_TREE = 30          /* real [nenv][8][32] scratch: cdof (rows 0-5), qfrc_smooth (row 6), tree reference points (row 7) */
 };
 
 /* Installs the task description (copied).  Replaces the task constructors
@@ -176,9 +179,10 @@ int dex_ik_solve(DexModel* model, int dtype, const void* targets_dev, int n, con
 
 /* Per-kernel-class device timing for the benchmark's roofline block: when enabled every launch is
  * bracketed by a cudaEvent pair on the launching stream.  dex_get_kernel_times synchronises and
- * returns total milliseconds and launch counts for {pre-step, collide, dynamics, post-step}. */
+ * returns total milliseconds and launch counts in arrays of 8: {pre-step, collide, solve, post-step, tree,
+ * 3 reserved}. */
 int dex_set_profiling(DexBatch* batch, int on);
-int dex_get_kernel_times(DexBatch* batch, double* ms4, int64_t* count4, int reset);
+int dex_get_kernel_times(DexBatch* batch, double* ms8, int64_t* count8, int reset);
 
 const char* dex_last_error(void);
 

@@ -19,6 +19,7 @@
 #include "../../dexterity_b200/csrc/dex_host_model.h"
 #include "../../dexterity_b200/csrc/dex_task.cuh"
 #include "../../dexterity_b200/csrc/dex_ik.cuh"
+#include "../../dexterity_b200/csrc/dex_tree.cuh"
 
 namespace dex_emu {
 struct Warp {
@@ -128,6 +129,7 @@ static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int
     std::vector<T> smem(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T) + 64);
     for (int env = lo; env < hi; ++env) {
       for (int s = 0; s < nsub; ++s) {
+        dex_tree_env<T>(m, st, env);   // K0 is thread-per-env: a plain call
         if (do_collide) dex_emu::run_warp([&]() { dex_collide_env<T>(m, st, env, smem.data()); });
         if (do_dynamics) dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem.data(), integrate); });
       }
@@ -156,16 +158,18 @@ int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
 int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, void* qvel, int qvel_stride, void* ctrl,
                   int ctrl_stride, void* warm, int warm_stride, void* time, unsigned* status, void* contact, int* ncon,
                   int* niter, int nsub, int integrate, int do_collide, int do_dynamics, void* dbg_M, void* dbg_fs,
-                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, void* jc, void* mscr, int nthreads) {
+                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, void* jc, void* mscr, void* xkin, void* tree, int nthreads) {
   EmuModel* m = (EmuModel*)mp;
   if (dtype == 0) {
     BatchState<float> st = {nenv, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
-                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc, (float*)mscr};
+                            (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc, (float*)mscr,
+                            (float*)xkin, (float*)tree};
     DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
     emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   } else {
     BatchState<double> st = {nenv, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
-                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc, (double*)mscr};
+                             (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc, (double*)mscr,
+                             (double*)xkin, (double*)tree};
     DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
     emu_run<double>(m->d.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   }
@@ -183,7 +187,8 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
                         (T*)f[DEX_FIELD_CTRL], (int)stride[DEX_FIELD_CTRL], (T*)f[DEX_FIELD_QACC_WARMSTART],
                         (int)stride[DEX_FIELD_QACC_WARMSTART], (T*)f[DEX_FIELD_TIME], (unsigned*)f[DEX_FIELD_STATUS],
                         (T*)f[DEX_FIELD_CONTACT], (int*)f[DEX_FIELD_NCON], (int*)f[DEX_FIELD_NITER],
-                        (const unsigned char*)f[DEX_FIELD_SKIP], (T*)f[DEX_FIELD_JC], (T*)f[DEX_FIELD_MSCR]};
+                        (const unsigned char*)f[DEX_FIELD_SKIP], (T*)f[DEX_FIELD_JC], (T*)f[DEX_FIELD_MSCR],
+                        (T*)f[DEX_FIELD_XKIN], (T*)f[DEX_FIELD_TREE]};
     TaskState<T> ts = {(const T*)f[DEX_FIELD_ACTION], (int)stride[DEX_FIELD_ACTION], (T*)f[DEX_FIELD_OBS], (T*)f[DEX_FIELD_REWARD],
                        (T*)f[DEX_FIELD_DISCOUNT], (T*)f[DEX_FIELD_GOAL], (int*)f[DEX_FIELD_TASK_I], (T*)f[DEX_FIELD_TASK_F],
                        (unsigned*)f[DEX_FIELD_RNG], (unsigned char*)f[DEX_FIELD_SKIP], (const unsigned char*)f[DEX_FIELD_RESET_MASK],
@@ -194,6 +199,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
       for (int env = lo; env < hi; ++env) {
         dex_emu::run_warp([&]() { dex_task_pre_env<T>(dev, st, ts, *p, env, force_reset); });
         if (!force_reset) for (int s = 0; s < nsub; ++s) {
+          dex_tree_env<T>(dev, st, env);
           dex_emu::run_warp([&]() { dex_collide_env<T>(dev, st, env, smem.data()); });
           dex_emu::run_warp([&]() { dex_dynamics_env<T>(dev, st, dbg, env, smem.data(), 1); });
         }
