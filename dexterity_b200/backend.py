@@ -19,8 +19,8 @@ LIB_PATH = os.path.join(_CSRC, "libdexb200.so")
 # enum DexFieldId (include/dexterity_b200.h)
 FIELD = dict(QPOS=0, QVEL=1, CTRL=2, QACC_WARMSTART=3, TIME=4, STATUS=5, CONTACT=6, NCON=7, NITER=8,
              DBG_M=9, DBG_QFRC_SMOOTH=10, DBG_QACC=11, DBG_QFRC_CONSTRAINT=12, DBG_EFC=13,
-             OBS=14, REWARD=15, DISCOUNT=16, DONE=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22,
-             SITE_XPOS=23, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30)
+             OBS=14, REWARD=15, DISCOUNT=16, NSLOT=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22,
+             WORK=23, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31)
 STATUS_BADQACC, STATUS_CON_OVERFLOW, STATUS_CAND_OVERFLOW, STATUS_SOLVER_MAXITER, STATUS_CHOL_FAIL = 1, 2, 4, 8, 16
 
 _lib = None
@@ -113,12 +113,18 @@ class PhysicsBatch:
             QPOS=z(n, qrow), QVEL=z(n, self.ROW), CTRL=z(n, self.ROW), QACC_WARMSTART=z(n, self.ROW), TIME=z(n),
             STATUS=z(n, dt=torch.int32), CONTACT=z(n, maxcon, cstride), NCON=z(n, dt=torch.int32),
             NITER=z(n, dt=torch.int32), JC=torch.empty(n, 3 * maxcon, 32, dtype=dtype, device=dev),
-            MSCR=z(n, 32, 32), XKIN=z(n, capacity(3) * 16), TREE=z(n, 8 * 32))
+            MSCR=z(n, 32, 32), XKIN=z(n, capacity(3) * 16), TREE=z(n, 8 * 32), STAGE=z(n, 64, 8),
+            NSLOT=z(n, dt=torch.int32))
         if debug:
             self._store.update(DBG_M=z(n, c.nv * c.nv), DBG_QFRC_SMOOTH=z(n, c.nv), DBG_QACC=z(n, c.nv),
                                DBG_QFRC_CONSTRAINT=z(n, c.nv), DBG_EFC=z(n, maxcon, 8))
         for name, t in self._store.items():
             self.bind(name, t)
+        # global narrowphase work list: word 0 = item count, then (env, slot << 24 | pair) per item
+        cap = max(32 * n, 4096)
+        work = z(1 + 2 * cap, dt=torch.int32)
+        _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
+        self._store["WORK"] = work
         # public views with the model's true widths
         self.qpos = self._store["QPOS"][:, :c.nq]
         self.qvel = self._store["QVEL"][:, :c.nv]

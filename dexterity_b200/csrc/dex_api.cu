@@ -30,17 +30,45 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define DEX_WARPS_PER_BLOCK 4
 #endif
 constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
+#ifndef DEX_K1_MINB
+#define DEX_K1_MINB 4
+#endif
+#ifndef DEX_K2_MINB
+#define DEX_K2_MINB 5
+#endif
 
 constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps spread over all SMs
 template <typename T>
 __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {
   const int env = blockIdx.x * kTreeBlock + threadIdx.x;
+  if (env == 0) *st.nwork = 0;  // the narrowphase work list of this mj_step starts empty (stream-ordered)
   if (env >= st.nenv) return;
   dex_tree_env<T>(m, st, env);
 }
 
+#ifndef DEX_NARROW_G
+#define DEX_NARROW_G 32  // lanes per convex-convex candidate in K1b (r01h: 32 -> 0.43 ms, 8 -> 0.49, 4 -> 0.47 per launch)
+#endif
+constexpr int kNarrowBlock = 128;
+constexpr int kNarrowG = DEX_NARROW_G;
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_collide(DevModel<T> m, BatchState<T> st) {
+__global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevModel<T> m, BatchState<T> st) {
+  int n = *st.nwork;
+  if (n > st.work_cap) n = st.work_cap;
+  const int per = kNarrowBlock / kNarrowG;   // items per CTA and round
+  for (int i = blockIdx.x * per + threadIdx.x / kNarrowG; i < n; i += gridDim.x * per)
+    dex_narrow_item<kNarrowG, T>(m, st, st.work[2 * (size_t)i], st.work[2 * (size_t)i + 1]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_compact(DevModel<T> m, BatchState<T> st) {
+  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (env >= st.nenv) return;
+  dex_compact_env<T>(m, st, env);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, DEX_K1_MINB) k_collide(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
@@ -50,7 +78,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_collide(DevModel<T> 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, DEX_K2_MINB) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
                                                                    int integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -174,11 +202,22 @@ struct ProfScope {  // records an event pair around one launch when profiling is
   ~ProfScope() { if (b->profiling) cudaEventRecord(b->ev[cls].back(), s); }
 };
 
+// K1b runs a grid-stride loop over a device-side item count: size the grid for ~8 items per env,
+// capped at a few CTAs per SM
+inline int narrow_grid(int nenv) {
+  const int per = kNarrowBlock / kNarrowG;
+  long long want = ((long long)nenv * 8 + per - 1) / per;
+  const long long cap = 148 * 16;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
 template <typename T>
 int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, bool use_skip = false) {
   // the tree kernel (K0) always runs, so its inputs and scratch are required by every entry point
   static const int req_col[] = {DEX_FIELD_QPOS, DEX_FIELD_STATUS, DEX_FIELD_CONTACT, DEX_FIELD_NCON, DEX_FIELD_QVEL, DEX_FIELD_CTRL,
-                                DEX_FIELD_MSCR, DEX_FIELD_XKIN, DEX_FIELD_TREE};
+                                DEX_FIELD_MSCR, DEX_FIELD_XKIN, DEX_FIELD_TREE, DEX_FIELD_STAGE, DEX_FIELD_NSLOT, DEX_FIELD_WORK};
   static const int req_dyn[] = {DEX_FIELD_QACC_WARMSTART, DEX_FIELD_TIME, DEX_FIELD_NITER, DEX_FIELD_JC};
   for (int f : req_col) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   if (need_dyn) for (int f : req_dyn) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
@@ -197,6 +236,12 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.mscr = (T*)b->ptr[DEX_FIELD_MSCR];
   st.xkin = (T*)b->ptr[DEX_FIELD_XKIN];
   st.tree = (T*)b->ptr[DEX_FIELD_TREE];
+  st.stage = (T*)b->ptr[DEX_FIELD_STAGE];
+  st.nslot = (int*)b->ptr[DEX_FIELD_NSLOT];
+  st.nwork = (int*)b->ptr[DEX_FIELD_WORK];
+  st.work = st.nwork + 1;
+  st.work_cap = (int)b->stride[DEX_FIELD_WORK];
+  if (st.work_cap < 1) return fail(DEX_E_ARG, "DEX_FIELD_WORK must be bound with row_stride = capacity in items");
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
   dbg.qacc = (T*)b->ptr[DEX_FIELD_DBG_QACC];
@@ -221,9 +266,14 @@ int run(DexBatch* b, const DevModel<T>& m, int nsub, bool collide, bool dynamics
   }
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int tgrid = (b->nenv + kTreeBlock - 1) / kTreeBlock;
+  const int ngrid = narrow_grid(b->nenv);
   for (int i = 0; i < nsub; ++i) {
     { ProfScope ps(b, 4, s); k_tree<T><<<tgrid, kTreeBlock, 0, s>>>(m, st); b->launches++; }
-    if (collide) { ProfScope ps(b, 1, s); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, s>>>(m, st); b->launches++; }
+    if (collide) {
+      { ProfScope ps(b, 1, s); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, s>>>(m, st); b->launches++; }
+      { ProfScope ps(b, 5, s); k_narrow<T><<<ngrid, kNarrowBlock, 0, s>>>(m, st); b->launches++; }
+      { ProfScope ps(b, 6, s); k_compact<T><<<grid, kWarpsPerBlock * 32, 0, s>>>(m, st); b->launches++; }
+    }
     if (dynamics) { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, s>>>(m, st, dbg, integrate); b->launches++; }
   }
   DEX_CUDA(cudaGetLastError());
@@ -261,9 +311,12 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
   if (phases & 1) { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
   if ((phases & 2) && !force_reset) {
     const int tgrid = (b->nenv + kTreeBlock - 1) / kTreeBlock;
+    const int ngrid = narrow_grid(b->nenv);
     for (int i = 0; i < nsub; ++i) {
       { ProfScope ps(b, 4, s); k_tree<T><<<tgrid, kTreeBlock, 0, s>>>(m, st); b->launches++; }
       { ProfScope ps(b, 1, s); k_collide<T><<<grid, block, smem1, s>>>(m, st); b->launches++; }
+      { ProfScope ps(b, 5, s); k_narrow<T><<<ngrid, kNarrowBlock, 0, s>>>(m, st); b->launches++; }
+      { ProfScope ps(b, 6, s); k_compact<T><<<grid, block, 0, s>>>(m, st); b->launches++; }
       { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, block, smem2, s>>>(m, st, dbg, 1); b->launches++; }
     }
   }
@@ -407,7 +460,7 @@ int dex_set_profiling(DexBatch* b, int on) {
   return DEX_OK;
 }
 // Synchronises the device, folds the recorded event pairs into per-class totals and returns
-// ms[8] (total milliseconds) and count[8] (launches) for pre / collide / dynamics / post / tree / (3 reserved).
+// ms[8] (total milliseconds) and count[8] (launches) for pre / broadphase / solve / post / tree / narrowphase / compaction / (reserved).
 int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
   if (!b || !ms || !count) return fail(DEX_E_ARG, "null argument");
   DEX_CUDA(cudaSetDevice(b->model->device));

@@ -1,21 +1,21 @@
-// dex_collide.cuh — K1: warp-per-env collision detection (restates mj_collision for the
-// suite's geom pairs).
+// dex_collide.cuh — collision detection (restates mj_collision for the suite's geom pairs,
+// SURVEY.md §8a row 14) as three kernels:
 //
-//   broadphase  : static candidate pairs grouped by body pair (compile-time filters already
-//                 applied: same weld, parent-child, <exclude>, contype/conaffinity).  Run-time
-//                 culls are conservative and therefore do not change the contact set:
-//                 body bounding spheres (plane: half-space test), then per geom pair, in the
-//                 frame of body A so that no per-geom world transform is needed: bounding
-//                 spheres, then each sphere against the other geom's body-frame AABB.  32 tests
-//                 per warp instruction; survivors are compacted with ballots.
-//   narrowphase : plane-box (mjc_PlaneBox), plane-mesh (mjc_PlaneConvex) and convex-convex
-//                 through libccd's MPR (ccdMPRPenetration) with mpr_tolerance/mpr_iterations,
-//                 carried out in the frame of body A.  The portal state is warp-uniform; the mesh
-//                 support function is the parallel part (lanes scan hull vertices, warp argmax
-//                 with lowest-index tie-break).  The support function is a real (non-inlined)
-//                 call: the r01a profile showed 54 % of K1's stall samples were instruction-cache
-//                 misses with everything inlined (111 KB of SASS).
-// Contacts are written compactly to global memory [env][DEX_MAXCON][8] for K2.
+//   K1a broadphase, WARP per env: static candidate pairs grouped by body pair (compile-time filters
+//       already applied: same weld, parent-child, <exclude>, contype/conaffinity).  Run-time culls are
+//       conservative and therefore do not change the contact set: body bounding spheres (plane:
+//       half-space test) and body OBBs, then per geom pair, in the frame of body A so that no per-geom
+//       world transform is needed: bounding spheres, sphere vs body-frame AABB, AABB vs AABB as
+//       oriented boxes.  32 tests per warp instruction; survivors are compacted with ballots.  Plane
+//       pairs (mjc_PlaneBox, mjc_PlaneConvex) are finished here; every convex-convex survivor gets a
+//       slot in the env's staging list and one entry in a GLOBAL work list.
+//   K1b narrowphase, THREAD per work item: libccd's MPR (ccdMPRPenetration) with
+//       mpr_tolerance / mpr_iterations in the frame of body A.  The portal logic is scalar per pair, so
+//       a warp that runs ONE pair keeps 1 lane's worth of work on 32 lanes (r01f profile: 12 k warp
+//       instructions per env, half of the old fused kernel); here 32 pairs share a warp and the hull
+//       scans run serially per thread (first strict maximum = lowest index, as the warp argmax had).
+//   K1c compaction, WARP per env: valid staging slots -> contact list [env][DEX_MAXCON][8] + ncon, in
+//       slot (= pair) order, which is MuJoCo's contact order.
 #ifndef DEX_COLLIDE_CUH_
 #define DEX_COLLIDE_CUH_
 
@@ -25,6 +25,8 @@
 // per-warp shared-memory footprint of K1, in units of T
 #define DEX_MAXCAND1 384   // capacity of the sphere-test survivor list (pass 1)
 #define DEX_K1_SMEM_T (DEX_MAXBODY * 16 + 48 + DEX_MAXCAND1 + 8 * 4)
+#define DEX_MAXSLOT 64     // staging slots per env (one per convex-convex candidate, four per plane-box pair)
+#define DEX_STAGE_ENV (DEX_MAXSLOT * DEX_CON_STRIDE)
 #define DEX_GPACK 12  // geom_pack: centre(3) rbound | aabb centre(3) aabb half.x | aabb half.y half.z pad pad
 
 template <typename T> struct V3 { T x, y, z; };
@@ -82,9 +84,47 @@ DEX_DEV_NOINLINE V3<T> dex_support_local(const T* vert, int n, int gtype, const 
   }
   return out;
 }
-template <typename T>
+// The same support point computed by a group of G consecutive lanes (K1b; G = 1: one thread).  Every
+// lane of the group calls with identical arguments and gets the result; the group's lanes stride over
+// the hull and the partial maxima are merged with group-masked shuffles (lowest index wins ties, as in
+// a serial "first strict maximum" scan).
+template <int G, typename T>
+DEX_DEV V3<T> dex_support_group(const T* vert, int n, int gtype, const T* mat, const T* size, const T* pack,
+                                T lx, T ly, T lz) {
+  V3<T> out;
+  if (gtype == DEX_GEOM_MESH) {
+    T best = -Real<T>::big();
+    int bi = 0x7fffffff;
+    for (int i = dex_lane() & (G - 1); i < n; i += G) {
+      T vx, vy, vz;
+      dex_ldg_xyz(vert + 4 * i, vx, vy, vz);
+      const T t = vx * lx + vy * ly + vz * lz;
+      if (t > best) { best = t; bi = i; }
+    }
+#pragma unroll
+    for (int mm = G >> 1; mm > 0; mm >>= 1) {
+      const T ov = dex_gshfl_xor<G>(best, mm);
+      const int oi = dex_gshfl_xor<G>(bi, mm);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    dex_ldg_xyz(vert + 4 * bi, out.x, out.y, out.z);
+  } else {  // box
+    T Gm[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
+    for (int i = 0; i < 9; ++i) Gm[i] = dex_ldg(mat + i);
+    rotT_vec(l2, Gm, ld);
+    cn[0] = l2[0] > 0 ? dex_ldg(size) : -dex_ldg(size);
+    cn[1] = l2[1] > 0 ? dex_ldg(size + 1) : -dex_ldg(size + 1);
+    cn[2] = l2[2] > 0 ? dex_ldg(size + 2) : -dex_ldg(size + 2);
+    rot_vec(loc, Gm, cn);
+    out.x = loc[0] + dex_ldg(pack); out.y = loc[1] + dex_ldg(pack + 1); out.z = loc[2] + dex_ldg(pack + 2);
+  }
+  return out;
+}
+// G = 32: the whole warp works on one pair (non-inlined REDUX version above); G < 32: a group of G lanes.
+template <int G, typename T>
 DEX_DEV V3<T> dex_support_ref(const GeomRef<T>& g, T lx, T ly, T lz) {
-  return dex_support_local(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
+  if (G == 32) return dex_support_local(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
+  return dex_support_group<G>(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
 }
 
 // ---- libccd helpers ---------------------------------------------------------------------
@@ -111,12 +151,12 @@ struct MprCtx {
   int iterations; // opt.mpr_iterations
 };
 
-template <typename T>
+template <int G, typename T>
 DEX_DEV void dex_mink(const MprCtx<T>& c, const T* dir, SupPt<T>& p) {
-  const V3<T> a = dex_support_ref(c.A, dir[0], dir[1], dir[2]);
+  const V3<T> a = dex_support_ref<G>(c.A, dir[0], dir[1], dir[2]);
   T nd[3] = {-dir[0], -dir[1], -dir[2]}, lb[3];
   rotT_vec(lb, c.rel.R, nd);
-  const V3<T> b = dex_support_ref(c.B, lb[0], lb[1], lb[2]);
+  const V3<T> b = dex_support_ref<G>(c.B, lb[0], lb[1], lb[2]);
   T bl[3] = {b.x, b.y, b.z}, bw[3];
   rot_vec(bw, c.rel.R, bl);
   p.v1[0] = a.x + dir[0] * c.half_margin; p.v1[1] = a.y + dir[1] * c.half_margin; p.v1[2] = a.z + dir[2] * c.half_margin;
@@ -174,10 +214,9 @@ template <typename T> DEX_DEV void expand_portal(SupPt<T>* s, const SupPt<T>& v4
   }
 }
 
-// ccdMPRPenetration in the frame of body A.  All lanes run this with identical (warp-uniform)
-// state.  Returns true on intersection; depth / dir / pos as libccd (pos = midpoint of the witness
+// ccdMPRPenetration in the frame of body A, run by a group of G lanes with identical (group-uniform) state.  Returns true on intersection; depth / dir / pos as libccd (pos = midpoint of the witness
 // points on A and B).
-template <typename T>
+template <int G, typename T>
 DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
   SupPt<T> s[4], v4;
   T dir[3], va[3], vb[3];
@@ -191,7 +230,7 @@ DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
   if (ccd_zero(s[0].v[0]) && ccd_zero(s[0].v[1]) && ccd_zero(s[0].v[2])) s[0].v[0] += T(2.220446049250313e-15);
   dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
   normalize3(dir);
-  dex_mink(c, dir, s[1]);
+  dex_mink<G>(c, dir, s[1]);
   T dt = dot3(s[1].v, dir);
   if (ccd_zero(dt) || dt < 0) return false;
   cross3(dir, s[0].v, s[1].v);
@@ -207,7 +246,7 @@ DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
     return true;
   }
   normalize3(dir);
-  dex_mink(c, dir, s[2]);
+  dex_mink<G>(c, dir, s[2]);
   dt = dot3(s[2].v, dir);
   if (ccd_zero(dt) || dt < 0) return false;
   for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
@@ -219,7 +258,7 @@ DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
   }
   for (int guard = 0;; ++guard) {  // discoverPortal: find v3
     if (guard > 100) return false;
-    dex_mink(c, dir, s[3]);
+    dex_mink<G>(c, dir, s[3]);
     dt = dot3(s[3].v, dir);
     if (ccd_zero(dt) || dt < 0) return false;
     bool cont = false;
@@ -241,14 +280,14 @@ DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
     portal_dir(s, dir);
     dt = dot3(dir, s[1].v);
     if (ccd_zero(dt) || dt > 0) break;
-    dex_mink(c, dir, v4);
+    dex_mink<G>(c, dir, v4);
     dt = dot3(v4.v, dir);
     if (!(ccd_zero(dt) || dt > 0) || portal_reach_tol(s, v4, dir, c.tolerance)) return false;
     expand_portal(s, v4);
   }
   for (int it = 0;; ++it) {  // findPenetr
     portal_dir(s, dir);
-    dex_mink(c, dir, v4);
+    dex_mink<G>(c, dir, v4);
     if (portal_reach_tol(s, v4, dir, c.tolerance) || it > c.iterations) {
       T d2 = point_tri_dist2(s[1].v, s[2].v, s[3].v, pdir);
       *depth = dx_sqrt(d2);
@@ -487,95 +526,162 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   }
   dex_syncwarp();
 
-  // ---- narrowphase
-  T* cout = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
-  int ncon = 0;
+  // ---- plane pairs are finished here; convex-convex survivors become work items for K1b
+  T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
+  int nslot = 0;   // staging slots handed out so far (warp-uniform)
+  int nwork = 0;   // convex-convex work items (warp-uniform)
+  int* work = cand;  // reuse: work[i] = slot << 24 | pair is written behind the read cursor (i <= ci)
   for (int ci = 0; ci < ncand; ++ci) {
     const int p = cand[ci];
     const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
     const int t1 = dex_ldg(m.geom_type + g1), t2 = dex_ldg(m.geom_type + g2);
+    if (t1 != DEX_GEOM_PLANE) {
+      if (nslot < DEX_MAXSLOT) {
+        dex_syncwarp();
+        if (lane == 0) work[nwork] = (nslot << 24) | p;
+        nwork++; nslot++;
+      } else status |= DEX_STATUS_CAND_OVERFLOW;
+      continue;
+    }
     const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
     const T margin = dex_ldg(m.pair_margin + p);
-    if (t1 == DEX_GEOM_PLANE) {
-      const T* G1 = m.geom_mat + 9 * g1;
-      T nl[3] = {dex_ldg(G1 + 2), dex_ldg(G1 + 5), dex_ldg(G1 + 8)}, n[3], p1[3];
-      rot_vec(n, xmat + 9 * b1, nl);
-      T pl[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 2)};
-      rot_vec(p1, xmat + 9 * b1, pl);
-      p1[0] += xpos[3 * b1]; p1[1] += xpos[3 * b1 + 1]; p1[2] += xpos[3 * b1 + 2];
-      if (t2 == DEX_GEOM_BOX) {  // mjc_PlaneBox: lanes 0..7 test the corners, first 4 hits kept
-        T cl[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g2), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 2)}, c2[3];
-        rot_vec(c2, xmat + 9 * b2, cl);
-        c2[0] += xpos[3 * b2]; c2[1] += xpos[3 * b2 + 1]; c2[2] += xpos[3 * b2 + 2];
-        T dif[3] = {c2[0] - p1[0], c2[1] - p1[1], c2[2] - p1[2]};
-        const T dist = dot3(dif, n);
-        T corner[3] = {0, 0, 0};
-        T ldist = 0;
-        bool hit = false;
-        if (lane < 8) {
-          T sz[3] = {dex_ldg(m.geom_size + 3 * g2), dex_ldg(m.geom_size + 3 * g2 + 1), dex_ldg(m.geom_size + 3 * g2 + 2)};
-          T vec[3] = {(lane & 1) ? sz[0] : -sz[0], (lane & 2) ? sz[1] : -sz[1], (lane & 4) ? sz[2] : -sz[2]};
-          T G[9], tmp[3];
-          for (int i = 0; i < 9; ++i) G[i] = dex_ldg(m.geom_mat + 9 * g2 + i);
-          rot_vec(tmp, G, vec);
-          rot_vec(corner, xmat + 9 * b2, tmp);
-          ldist = dot3(n, corner);
-          hit = !(dist + ldist > margin || ldist > 0);
-        }
-        const unsigned hm = dex_ballot(hit);
-        const int rank = dex_popc(hm & ((1u << lane) - 1u));
-        if (hit && rank < 4) {
-          if (ncon + rank < DEX_MAXCON) {
-            T cd = dist + ldist;
-            T cp[3] = {corner[0] + c2[0] - n[0] * cd * T(0.5), corner[1] + c2[1] - n[1] * cd * T(0.5),
-                       corner[2] + c2[2] - n[2] * cd * T(0.5)};
-            dex_store_contact(cout + (ncon + rank) * DEX_CON_STRIDE, cd, cp, n, p);
-          }
-        }
-        int add = dex_popc(hm); if (add > 4) add = 4;
-        if (ncon + add > DEX_MAXCON) { status |= DEX_STATUS_CON_OVERFLOW; add = DEX_MAXCON - ncon; }
-        ncon += add;
-      } else if (t2 == DEX_GEOM_MESH) {  // mjc_PlaneConvex: deepest vertex (hull-neighbour extras: next round)
-        T nn[3] = {-n[0], -n[1], -n[2]}, ld[3], w[3];
-        rotT_vec(ld, xmat + 9 * b2, nn);
-        const V3<T> sp = dex_support_ref(dex_geom_ref(m, g2, t2), ld[0], ld[1], ld[2]);
-        T sl[3] = {sp.x, sp.y, sp.z};
-        rot_vec(w, xmat + 9 * b2, sl);
-        w[0] += xpos[3 * b2]; w[1] += xpos[3 * b2 + 1]; w[2] += xpos[3 * b2 + 2];
-        T dif[3] = {w[0] - p1[0], w[1] - p1[1], w[2] - p1[2]};
-        const T dist = dot3(dif, n);
+    const T* G1 = m.geom_mat + 9 * g1;
+    T nl[3] = {dex_ldg(G1 + 2), dex_ldg(G1 + 5), dex_ldg(G1 + 8)}, n[3], p1[3];
+    rot_vec(n, xmat + 9 * b1, nl);
+    T pl[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 2)};
+    rot_vec(p1, xmat + 9 * b1, pl);
+    p1[0] += xpos[3 * b1]; p1[1] += xpos[3 * b1 + 1]; p1[2] += xpos[3 * b1 + 2];
+    if (t2 == DEX_GEOM_BOX) {  // mjc_PlaneBox: lanes 0..7 test the corners, first 4 hits kept (4 slots)
+      if (nslot + 4 > DEX_MAXSLOT) { status |= DEX_STATUS_CAND_OVERFLOW; continue; }
+      T cl[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g2), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 2)}, c2[3];
+      rot_vec(c2, xmat + 9 * b2, cl);
+      c2[0] += xpos[3 * b2]; c2[1] += xpos[3 * b2 + 1]; c2[2] += xpos[3 * b2 + 2];
+      T dif[3] = {c2[0] - p1[0], c2[1] - p1[1], c2[2] - p1[2]};
+      const T dist = dot3(dif, n);
+      T corner[3] = {0, 0, 0};
+      T ldist = 0;
+      bool hit = false;
+      if (lane < 8) {
+        T sz[3] = {dex_ldg(m.geom_size + 3 * g2), dex_ldg(m.geom_size + 3 * g2 + 1), dex_ldg(m.geom_size + 3 * g2 + 2)};
+        T vec[3] = {(lane & 1) ? sz[0] : -sz[0], (lane & 2) ? sz[1] : -sz[1], (lane & 4) ? sz[2] : -sz[2]};
+        T G[9], tmp[3];
+        for (int i = 0; i < 9; ++i) G[i] = dex_ldg(m.geom_mat + 9 * g2 + i);
+        rot_vec(tmp, G, vec);
+        rot_vec(corner, xmat + 9 * b2, tmp);
+        ldist = dot3(n, corner);
+        hit = !(dist + ldist > margin || ldist > 0);
+      }
+      const unsigned hm = dex_ballot(hit);
+      const int rank = dex_popc(hm & ((1u << lane) - 1u));
+      if (hit && rank < 4) {
+        T cd = dist + ldist;
+        T cp[3] = {corner[0] + c2[0] - n[0] * cd * T(0.5), corner[1] + c2[1] - n[1] * cd * T(0.5),
+                   corner[2] + c2[2] - n[2] * cd * T(0.5)};
+        dex_store_contact(stage + (nslot + rank) * DEX_CON_STRIDE, cd, cp, n, p);
+      }
+      int add = dex_popc(hm); if (add > 4) add = 4;
+      if (lane >= add && lane < 4) stage[(nslot + lane) * DEX_CON_STRIDE + 7] = T(-1);  // unused slots of the four
+      nslot += 4;
+    } else if (t2 == DEX_GEOM_MESH) {  // mjc_PlaneConvex: deepest vertex (hull-neighbour extras: next round)
+      if (nslot >= DEX_MAXSLOT) { status |= DEX_STATUS_CAND_OVERFLOW; continue; }
+      T nn[3] = {-n[0], -n[1], -n[2]}, ld[3], w[3];
+      rotT_vec(ld, xmat + 9 * b2, nn);
+      const V3<T> sp = dex_support_ref<32>(dex_geom_ref(m, g2, t2), ld[0], ld[1], ld[2]);
+      T sl[3] = {sp.x, sp.y, sp.z};
+      rot_vec(w, xmat + 9 * b2, sl);
+      w[0] += xpos[3 * b2]; w[1] += xpos[3 * b2 + 1]; w[2] += xpos[3 * b2 + 2];
+      T dif[3] = {w[0] - p1[0], w[1] - p1[1], w[2] - p1[2]};
+      const T dist = dot3(dif, n);
+      if (lane == 0) {
         if (dist <= margin) {
-          if (ncon < DEX_MAXCON) {
-            T cp[3] = {w[0] - T(0.5) * dist * n[0], w[1] - T(0.5) * dist * n[1], w[2] - T(0.5) * dist * n[2]};
-            if (lane == 0) dex_store_contact(cout + ncon * DEX_CON_STRIDE, dist, cp, n, p);
-            ncon++;
-          } else status |= DEX_STATUS_CON_OVERFLOW;
-        }
+          T cp[3] = {w[0] - T(0.5) * dist * n[0], w[1] - T(0.5) * dist * n[1], w[2] - T(0.5) * dist * n[2]};
+          dex_store_contact(stage + nslot * DEX_CON_STRIDE, dist, cp, n, p);
+        } else stage[nslot * DEX_CON_STRIDE + 7] = T(-1);
       }
-    } else {
-      MprCtx<T> mc;
-      mc.A = dex_geom_ref(m, g1, t1); mc.B = dex_geom_ref(m, g2, t2); mc.half_margin = T(0.5) * margin;
-      mc.tolerance = m.mpr_tolerance; mc.iterations = m.mpr_iterations;
-      dex_relative(xpos, xmat, b1, b2, mc.rel);
-      T depth, dir[3], pos[3];
-      if (dex_mpr(mc, &depth, dir, pos) && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0)) {
-        if (ncon < DEX_MAXCON) {
-          if (lane == 0) {
-            T pw[3], nw[3];
-            rot_vec(pw, xmat + 9 * b1, pos);
-            rot_vec(nw, xmat + 9 * b1, dir);
-            pw[0] += xpos[3 * b1]; pw[1] += xpos[3 * b1 + 1]; pw[2] += xpos[3 * b1 + 2];
-            dex_store_contact(cout + ncon * DEX_CON_STRIDE, margin - depth, pw, nw, p);
-          }
-          ncon++;
-        } else status |= DEX_STATUS_CON_OVERFLOW;
-      }
+      nslot++;
     }
   }
-  if (lane == 0) {
-    st.ncon[env] = ncon;
-    if (status) st.status[env] |= status;
+  dex_syncwarp();
+  // ---- append the env's work items to the global list (one atomic per env)
+  int base = 0;
+  if (lane == 0 && nwork > 0) base = dex_atomic_add_ret(st.nwork, nwork);
+  base = dex_shfl(base, 0);
+  bool ovf = false;
+  for (int i = lane; i < nwork; i += 32) {
+    const int wv = work[i];
+    if (base + i < st.work_cap) { st.work[2 * (size_t)(base + i)] = env; st.work[2 * (size_t)(base + i) + 1] = wv; }
+    else { ovf = true; stage[(wv >> 24) * DEX_CON_STRIDE + 7] = T(-1); }
   }
+  if (dex_ballot(ovf)) status |= DEX_STATUS_CAND_OVERFLOW;
+  if (lane == 0 && status) st.status[env] |= status;
+  if (lane == 0) st.nslot[env] = nslot;
+}
+
+// K1b: one convex-convex candidate per group of G lanes (all of them call this with the same item).
+// item = (env, slot << 24 | pair).
+template <int G, typename T>
+DEX_DEV void dex_narrow_item(const DevModel<T>& m, const BatchState<T>& st, int env, int wv) {
+  const int p = wv & 0xffffff, slot = wv >> 24;
+  const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
+  const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
+  const T margin = dex_ldg(m.pair_margin + p);
+  const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
+  T x1[3], R1[9], x2[3], R2[9];
+  for (int k = 0; k < 3; ++k) { x1[k] = xk[b1 * DEX_XKIN_BODY + k]; x2[k] = xk[b2 * DEX_XKIN_BODY + k]; }
+  for (int k = 0; k < 9; ++k) { R1[k] = xk[b1 * DEX_XKIN_BODY + 7 + k]; R2[k] = xk[b2 * DEX_XKIN_BODY + 7 + k]; }
+  MprCtx<T> mc;
+  mc.A = dex_geom_ref(m, g1, dex_ldg(m.geom_type + g1)); mc.B = dex_geom_ref(m, g2, dex_ldg(m.geom_type + g2));
+  mc.half_margin = T(0.5) * margin;
+  mc.tolerance = m.mpr_tolerance; mc.iterations = m.mpr_iterations;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+    mc.rel.R[3 * r + c] = R1[r] * R2[c] + R1[3 + r] * R2[3 + c] + R1[6 + r] * R2[6 + c];
+  {
+    const T d[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
+    rotT_vec(mc.rel.t, R1, d);
+  }
+  T* out = st.stage + (size_t)env * DEX_STAGE_ENV + slot * DEX_CON_STRIDE;
+  T depth, dir[3], pos[3];
+  const bool hit = dex_mpr<G>(mc, &depth, dir, pos) && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0);
+  if ((dex_lane() & (G - 1)) != 0) return;
+  if (hit) {
+    T pw[3], nw[3];
+    rot_vec(pw, R1, pos);
+    rot_vec(nw, R1, dir);
+    pw[0] += x1[0]; pw[1] += x1[1]; pw[2] += x1[2];
+    dex_store_contact(out, margin - depth, pw, nw, p);
+  } else out[7] = T(-1);
+}
+
+// K1c: staging slots -> contact list in slot order (warp per env).
+template <typename T>
+DEX_DEV void dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
+  if (st.skip && st.skip[env]) return;  // warp-uniform
+  const int lane = dex_lane();
+  const int nslot = st.nslot[env];
+  const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
+  T* cout = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
+  int ncon = 0;
+  bool overflow = false;
+  for (int s0 = 0; s0 < nslot; s0 += 32) {
+    const int sl = s0 + lane;
+    T rec[DEX_CON_STRIDE];
+    bool valid = false;
+    if (sl < nslot) {
+      for (int k = 0; k < DEX_CON_STRIDE; ++k) rec[k] = stage[sl * DEX_CON_STRIDE + k];
+      valid = rec[7] >= 0;
+    }
+    const unsigned vm = dex_ballot(valid);
+    const int idx = ncon + dex_popc(vm & ((1u << lane) - 1u));
+    if (valid) {
+      if (idx < DEX_MAXCON) { for (int k = 0; k < DEX_CON_STRIDE; ++k) cout[idx * DEX_CON_STRIDE + k] = rec[k]; }
+      else overflow = true;
+    }
+    ncon += dex_popc(vm);
+  }
+  if (dex_ballot(overflow)) { if (lane == 0) st.status[env] |= DEX_STATUS_CON_OVERFLOW; }
+  if (ncon > DEX_MAXCON) ncon = DEX_MAXCON;
+  if (lane == 0) st.ncon[env] = ncon;
+  (void)m;
 }
 
 #endif  // DEX_COLLIDE_CUH_

@@ -94,7 +94,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     if (M.body_parent[b] < 0 || M.body_parent[b] >= b) return "bodies must be ordered parent before child";
     M.body_depth[b] = M.body_depth[M.body_parent[b]] + 1; M.maxdepth = std::max(M.maxdepth, M.body_depth[b]);
   }
-  if (M.maxdepth >= 16) return "kinematic tree deeper than DEX_MAXDEPTH (16)";
+  if (M.maxdepth >= 12) return "kinematic tree deeper than DEX_MAXDEPTH (12)";
   {  // the tree kernel walks the bodies with a depth-indexed stack: requires DFS pre-order (MuJoCo's body order)
     std::vector<int> open(M.maxdepth + 1, 0);
     for (int b = 1; b < nb; ++b) {

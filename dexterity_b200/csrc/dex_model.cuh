@@ -82,6 +82,11 @@ struct BatchState {
   T* jc;                          // [nenv][3*DEX_MAXCON][32] contact-frame Jacobian scratch (L2 resident)
   T* mscr;                        // [nenv][32][32] dense mass matrix (zero-initialised once; K0 writes the non-zeros)
   T* xkin;                        // [nenv][DEX_MAXBODY][16] body poses of K0: xpos(3) xquat(4) xmat(9)
+  T* stage;                       // [nenv][DEX_MAXSLOT][8] contact staging slots of K1a / K1b (pair < 0 = no contact)
+  int* nslot;                     // [nenv] staging slots in use
+  int* work;                      // [work_cap][2] global narrowphase work list: env, slot << 24 | pair
+  int* nwork;                     // [1] number of work items (zeroed by K0 every mj_step)
+  int work_cap;
   T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
 };
 

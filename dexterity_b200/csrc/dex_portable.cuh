@@ -22,8 +22,12 @@ DEX_DEV int dex_lane() { return threadIdx.x & 31; }
 template <typename T> DEX_DEV T dex_shfl(T v, int src) { return __shfl_sync(DEX_FULL, v, src); }
 template <typename T> DEX_DEV T dex_shfl_xor(T v, int m) { return __shfl_xor_sync(DEX_FULL, v, m); }
 DEX_DEV unsigned dex_ballot(bool p) { return __ballot_sync(DEX_FULL, p); }
+// shuffles inside a group of G consecutive lanes (G a power of two); groups of one warp may diverge
+template <int G> DEX_DEV unsigned dex_gmask() { return G >= 32 ? DEX_FULL : (((1u << (G & 31)) - 1u) << (threadIdx.x & 31 & ~(G - 1))); }
+template <int G, typename T> DEX_DEV T dex_gshfl_xor(T v, int m) { return __shfl_xor_sync(dex_gmask<G>(), v, m); }
 DEX_DEV void dex_syncwarp() { __syncwarp(); }
 template <typename T> DEX_DEV void dex_atomic_add(T* p, T v) { atomicAdd(p, v); }
+DEX_DEV int dex_atomic_add_ret(int* p, int v) { return atomicAdd(p, v); }
 template <typename T> DEX_DEV T dex_ldg(const T* p) { return __ldg(p); }
 DEX_DEV int dex_popc(unsigned x) { return __popc(x); }
 DEX_DEV int dex_ffs(unsigned x) { return __ffs(x); }
@@ -50,8 +54,10 @@ template <typename T> inline T dex_shfl(T v, int src) {
 }
 template <typename T> inline T dex_shfl_xor(T v, int m) { return dex_shfl(v, dex_emu::lane() ^ m); }
 inline unsigned dex_ballot(bool p) { return dex_emu::ballot(p); }
+template <int G, typename T> inline T dex_gshfl_xor(T v, int m) { return dex_shfl(v, dex_emu::lane() ^ m); }
 inline void dex_syncwarp() { dex_emu::barrier(); }
 template <typename T> inline void dex_atomic_add(T* p, T v) { *p += v; }  // fibers are serialised
+inline int dex_atomic_add_ret(int* p, int v) { int o = *p; *p += v; return o; }
 template <typename T> inline T dex_ldg(const T* p) { return *p; }
 inline int dex_popc(unsigned x) { return __builtin_popcount(x); }
 inline int dex_ffs(unsigned x) { return __builtin_ffs((int)x); }

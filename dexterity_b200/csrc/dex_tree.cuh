@@ -24,7 +24,9 @@
 
 #include "dex_model.cuh"
 
-#define DEX_MAXDEPTH 16
+#ifndef DEX_MAXDEPTH
+#define DEX_MAXDEPTH 12
+#endif
 #define DEX_XKIN_BODY 16
 #define DEX_XKIN_ENV (DEX_MAXBODY * DEX_XKIN_BODY)
 #define DEX_TREE_ENV 256
@@ -122,11 +124,43 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
     ref[3 * t] = pos[0]; ref[3 * t + 1] = pos[1]; ref[3 * t + 2] = pos[2];
   }
 
+  // ---- actuation (mj_fwdActuation) and passive damping (before the walk: qfrc_smooth is finished as each body is left)
+  T act[DEX_MAXDOF];
+  for (int i = 0; i < DEX_MAXDOF; ++i) act[i] = 0;
+  for (int a = 0; a < m.nu; ++a) {
+    const int tid = dex_ldg(m.act_trnid + a);
+    const T gear = dex_ldg(m.act_gear + a);
+    const bool joint = dex_ldg(m.act_trntype + a) == 0;
+    T length = 0, vel = 0;
+    if (joint) {
+      length = qpos[dex_ldg(m.jnt_qposadr + tid)];
+      vel = qvel[dex_ldg(m.jnt_dofadr + tid)];
+    } else {
+      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
+      for (int w = wa; w < wa + wn; ++w) {
+        const int j = dex_ldg(m.wrap_jnt + w);
+        const T c = dex_ldg(m.wrap_coef + w);
+        length += c * qpos[dex_ldg(m.jnt_qposadr + j)];
+        vel += c * qvel[dex_ldg(m.jnt_dofadr + j)];
+      }
+    }
+    length *= gear; vel *= gear;
+    T c = st.ctrl[(size_t)env * st.ctrl_stride + a];
+    if (dex_ldg(m.act_ctrllimited + a)) c = dx_clamp(c, dex_ldg(m.act_ctrlrange + 2 * a), dex_ldg(m.act_ctrlrange + 2 * a + 1));
+    T f = dex_ldg(m.act_gainprm + 3 * a) * c + dex_ldg(m.act_biasprm + 3 * a) + dex_ldg(m.act_biasprm + 3 * a + 1) * length +
+          dex_ldg(m.act_biasprm + 3 * a + 2) * vel;
+    if (dex_ldg(m.act_forcelimited + a)) f = dx_clamp(f, dex_ldg(m.act_forcerange + 2 * a), dex_ldg(m.act_forcerange + 2 * a + 1));
+    if (joint) act[dex_ldg(m.jnt_dofadr + tid)] += gear * f;
+    else {
+      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
+      for (int w = wa; w < wa + wn; ++w) act[dex_ldg(m.jnt_dofadr + dex_ldg(m.wrap_jnt + w))] += gear * dex_ldg(m.wrap_coef + w) * f;
+    }
+  }
   // ---- depth-first walk
   T s_pos[DEX_MAXDEPTH][3], s_quat[DEX_MAXDEPTH][4], s_mat[DEX_MAXDEPTH][9];
   T s_vel[DEX_MAXDEPTH][6], s_acc[DEX_MAXDEPTH][6], s_crb[DEX_MAXDEPTH][10], s_frc[DEX_MAXDEPTH][6];
   int s_body[DEX_MAXDEPTH];
-  T cdof[DEX_MAXDOF][6], bias[DEX_MAXDOF];
+  T cdof[DEX_MAXDOF][6];
   for (int k = 0; k < 3; ++k) s_pos[0][k] = 0;
   s_quat[0][0] = 1; s_quat[0][1] = s_quat[0][2] = s_quat[0][3] = 0;
   for (int k = 0; k < 9; ++k) s_mat[0][k] = (k % 4 == 0) ? T(1) : T(0);
@@ -148,7 +182,9 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
       for (int i = da; i < da + dn; ++i) {
         const T* ci = cdof[i];
         const T* cf = s_frc[cur];
-        bias[i] = ci[0] * cf[0] + ci[1] * cf[1] + ci[2] * cf[2] + ci[3] * cf[3] + ci[4] * cf[4] + ci[5] * cf[5];
+        const T bias = ci[0] * cf[0] + ci[1] * cf[1] + ci[2] * cf[2] + ci[3] * cf[3] + ci[4] * cf[4] + ci[5] * cf[5];
+        tree[DEX_TREE_ROW_FS * 32 + i] = -dex_ldg(m.dof_damping + i) * qvel[i] - bias + act[i];  // qfrc_smooth
+        for (int k = 0; k < 6; ++k) tree[k * 32 + i] = ci[k];
         T buf[6];
         mul_inert_vec(buf, s_crb[cur], ci);
         for (int j = i; j >= 0; j = dex_ldg(m.dof_parent + j)) {
@@ -241,42 +277,6 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
     }
   }
 
-  // ---- actuation (mj_fwdActuation) and passive damping -> qfrc_smooth
-  T act[DEX_MAXDOF];
-  for (int i = 0; i < DEX_MAXDOF; ++i) act[i] = 0;
-  for (int a = 0; a < m.nu; ++a) {
-    const int tid = dex_ldg(m.act_trnid + a);
-    const T gear = dex_ldg(m.act_gear + a);
-    const bool joint = dex_ldg(m.act_trntype + a) == 0;
-    T length = 0, vel = 0;
-    if (joint) {
-      length = qpos[dex_ldg(m.jnt_qposadr + tid)];
-      vel = qvel[dex_ldg(m.jnt_dofadr + tid)];
-    } else {
-      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
-      for (int w = wa; w < wa + wn; ++w) {
-        const int j = dex_ldg(m.wrap_jnt + w);
-        const T c = dex_ldg(m.wrap_coef + w);
-        length += c * qpos[dex_ldg(m.jnt_qposadr + j)];
-        vel += c * qvel[dex_ldg(m.jnt_dofadr + j)];
-      }
-    }
-    length *= gear; vel *= gear;
-    T c = st.ctrl[(size_t)env * st.ctrl_stride + a];
-    if (dex_ldg(m.act_ctrllimited + a)) c = dx_clamp(c, dex_ldg(m.act_ctrlrange + 2 * a), dex_ldg(m.act_ctrlrange + 2 * a + 1));
-    T f = dex_ldg(m.act_gainprm + 3 * a) * c + dex_ldg(m.act_biasprm + 3 * a) + dex_ldg(m.act_biasprm + 3 * a + 1) * length +
-          dex_ldg(m.act_biasprm + 3 * a + 2) * vel;
-    if (dex_ldg(m.act_forcelimited + a)) f = dx_clamp(f, dex_ldg(m.act_forcerange + 2 * a), dex_ldg(m.act_forcerange + 2 * a + 1));
-    if (joint) act[dex_ldg(m.jnt_dofadr + tid)] += gear * f;
-    else {
-      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
-      for (int w = wa; w < wa + wn; ++w) act[dex_ldg(m.jnt_dofadr + dex_ldg(m.wrap_jnt + w))] += gear * dex_ldg(m.wrap_coef + w) * f;
-    }
-  }
-  for (int i = 0; i < nv; ++i) {
-    for (int k = 0; k < 6; ++k) tree[k * 32 + i] = cdof[i][k];
-    tree[DEX_TREE_ROW_FS * 32 + i] = -dex_ldg(m.dof_damping + i) * qvel[i] - bias[i] + act[i];
-  }
   for (int k = 0; k < 16; ++k) tree[DEX_TREE_ROW_REF * 32 + k] = ref[k];
 }
 

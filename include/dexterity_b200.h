@@ -130,7 +130,11 @@ enum DexTaskFieldId {
   DEX_FIELD_MSCR = 28,         /* real [nenv][32][32] scratch: dense mass matrix; MUST be zero-initialised by the caller (only
                                   the structural non-zeros are rewritten each step)                                    */
   DEX_FIELD_XKIN = 29,         /* real [nenv][DEX_MAXBODY][16] scratch: body poses xpos(3) xquat(4) xmat(9) (data.xpos/xquat/xmat) */
-  DEX_FIELD_TREE = 30          /* real [nenv][8][32] scratch: cdof (rows 0-5), qfrc_smooth (row 6), tree reference points (row 7) */
+  DEX_FIELD_TREE = 30,         /* real [nenv][8][32] scratch: cdof (rows 0-5), qfrc_smooth (row 6), tree reference points (row 7) */
+  DEX_FIELD_STAGE = 31,        /* real [nenv][64][8] scratch: contact staging slots of the collision kernels               */
+  DEX_FIELD_NSLOT = 17,        /* i32  [nenv]        scratch: staging slots in use                                        */
+  DEX_FIELD_WORK = 23          /* i32  [1 + 2*cap]   scratch: narrowphase work list: word 0 = item count, then (env, slot<<24|pair)
+                                  pairs; bind with row_stride = cap (the capacity in items, >= nenv * 8 recommended)     */
 };
 
 /* Installs the task description (copied).  Replaces the task constructors
@@ -179,8 +183,8 @@ int dex_ik_solve(DexModel* model, int dtype, const void* targets_dev, int n, con
 
 /* Per-kernel-class device timing for the benchmark's roofline block: when enabled every launch is
  * bracketed by a cudaEvent pair on the launching stream.  dex_get_kernel_times synchronises and
- * returns total milliseconds and launch counts in arrays of 8: {pre-step, collide, solve, post-step, tree,
- * 3 reserved}. */
+ * returns total milliseconds and launch counts in arrays of 8: {pre-step, broadphase, solve, post-step, tree,
+ * narrowphase, contact compaction, reserved}. */
 int dex_set_profiling(DexBatch* batch, int on);
 int dex_get_kernel_times(DexBatch* batch, double* ms8, int64_t* count8, int reset);
 

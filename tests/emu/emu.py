@@ -54,16 +54,18 @@ class EmuModel:
         mscr = np.zeros((nenv, 32, 32), dtype)
         xkin = np.zeros((nenv, 40 * 16), dtype)
         tree = np.zeros((nenv, 8 * 32), dtype)
+        stage = np.zeros((nenv, 64, 8), dtype)
+        nslot = np.zeros(nenv, np.int32)
         nv = c.nv
         dbg = dict(M=np.zeros((nenv, nv, nv), dtype), fs=np.zeros((nenv, nv), dtype), qacc=np.zeros((nenv, nv), dtype),
                    fc=np.zeros((nenv, nv), dtype), efc=np.zeros((nenv, MAXCON, 8), dtype)) if debug else {}
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
         self.lib.emu_run_steps.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
-            [ctypes.c_void_p, ctypes.c_int] * 4 + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 9 + [ctypes.c_int]
+            [ctypes.c_void_p, ctypes.c_int] * 4 + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 11 + [ctypes.c_int]
         self.lib.emu_run_steps(self.ptr, 0 if dtype == np.float32 else 1, nenv, p(Q), 32, p(V), 32, p(U), 32, p(Wm), 32,
                                p(time), p(status), p(contact), p(ncon), p(niter), nsub, int(integrate), int(collide),
                                int(dynamics), p(dbg.get("M")), p(dbg.get("fs")), p(dbg.get("qacc")), p(dbg.get("fc")),
-                               p(dbg.get("efc")), p(jc), p(mscr), p(xkin), p(tree), nthreads)
+                               p(dbg.get("efc")), p(jc), p(mscr), p(xkin), p(tree), p(stage), p(nslot), nthreads)
         out = dict(qpos=Q[:, :c.nq].astype(np.float64), qvel=V[:, :nv].astype(np.float64), warm=Wm[:, :nv].astype(np.float64),
                    time=time, status=status, contact=contact.astype(np.float64), ncon=ncon, niter=niter)
         out.update({k: v.astype(np.float64) for k, v in dbg.items()})
@@ -74,7 +76,7 @@ class EmuEnv:
     """Host emulation of dex_env_reset / dex_env_step (kernel bodies run by the fiber emulator)."""
 
     FIELD = dict(QPOS=0, QVEL=1, CTRL=2, QACC_WARMSTART=3, TIME=4, STATUS=5, CONTACT=6, NCON=7, NITER=8, OBS=14, REWARD=15,
-                 DISCOUNT=16, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30)
+                 DISCOUNT=16, NSLOT=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31)
 
     def __init__(self, model: EmuModel, params, nenv: int, dtype=np.float32, seed: int = 1):
         self.m, self.p, self.n, self.dtype = model, params, nenv, dtype
@@ -84,7 +86,7 @@ class EmuEnv:
                       NITER=z(nenv, dt=np.int32), OBS=z(nenv, 128), REWARD=z(nenv), DISCOUNT=z(nenv), GOAL=z(nenv, 16),
                       TASK_I=z(nenv, 8, dt=np.int32), TASK_F=z(nenv, 8), RNG=z(nenv, 4, dt=np.uint32), ACTION=z(nenv, 32),
                       EPISODE_STATS=z(8, dt=np.float64), RESET_MASK=z(nenv, dt=np.uint8), SKIP=z(nenv, dt=np.uint8), JC=z(nenv, 3 * MAXCON, 32), MSCR=z(nenv, 32, 32),
-                      XKIN=z(nenv, 40 * 16), TREE=z(nenv, 8 * 32))
+                      XKIN=z(nenv, 40 * 16), TREE=z(nenv, 8 * 32), STAGE=z(nenv, 64, 8), NSLOT=z(nenv, dt=np.int32))
         self.a["RNG"][:, 0] = seed
         self.ptrs = (ctypes.c_void_p * 32)()
         self.strides = (ctypes.c_int64 * 32)()

@@ -122,6 +122,23 @@ struct EmuModel {
   EmuModelT<double> d;
 };
 
+// collision stage of one env: broadphase (warp), narrowphase (one plain call per work item),
+// compaction (warp).  The work list is private to the calling worker thread.
+template <typename T>
+static void emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
+  std::vector<int> work(1 + 2 * DEX_MAXSLOT, 0);
+  BatchState<T> sl = st;
+  sl.nwork = work.data(); sl.work = work.data() + 1; sl.work_cap = DEX_MAXSLOT;
+  dex_emu::run_warp([&]() { dex_collide_env<T>(m, sl, env, smem); });
+  // groups of 8 fibers per item, 4 items per emulated warp (idle groups return at once)
+  for (int i0 = 0; i0 < work[0]; i0 += 4)
+    dex_emu::run_warp([&]() {
+      const int i = i0 + dex_emu::lane() / 8;
+      if (i < work[0]) dex_narrow_item<8, T>(m, sl, work[1 + 2 * i], work[2 + 2 * i]);
+    });
+  dex_emu::run_warp([&]() { dex_compact_env<T>(m, sl, env); });
+}
+
 template <typename T>
 static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int nsub, int integrate, int do_collide,
                     int do_dynamics, int nthreads) {
@@ -130,7 +147,7 @@ static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int
     for (int env = lo; env < hi; ++env) {
       for (int s = 0; s < nsub; ++s) {
         dex_tree_env<T>(m, st, env);   // K0 is thread-per-env: a plain call
-        if (do_collide) dex_emu::run_warp([&]() { dex_collide_env<T>(m, st, env, smem.data()); });
+        if (do_collide) emu_collide<T>(m, st, env, smem.data());
         if (do_dynamics) dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem.data(), integrate); });
       }
     }
@@ -158,18 +175,19 @@ int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
 int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, void* qvel, int qvel_stride, void* ctrl,
                   int ctrl_stride, void* warm, int warm_stride, void* time, unsigned* status, void* contact, int* ncon,
                   int* niter, int nsub, int integrate, int do_collide, int do_dynamics, void* dbg_M, void* dbg_fs,
-                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, void* jc, void* mscr, void* xkin, void* tree, int nthreads) {
+                  void* dbg_qacc, void* dbg_fc, void* dbg_efc, void* jc, void* mscr, void* xkin, void* tree, void* stage, int* nslot,
+                  int nthreads) {
   EmuModel* m = (EmuModel*)mp;
   if (dtype == 0) {
     BatchState<float> st = {nenv, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
                             (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc, (float*)mscr,
-                            (float*)xkin, (float*)tree};
+                            (float*)xkin, (float*)stage, nslot, nullptr, nullptr, 0, (float*)tree};
     DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
     emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   } else {
     BatchState<double> st = {nenv, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
                              (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc, (double*)mscr,
-                             (double*)xkin, (double*)tree};
+                             (double*)xkin, (double*)stage, nslot, nullptr, nullptr, 0, (double*)tree};
     DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
     emu_run<double>(m->d.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   }
@@ -188,7 +206,8 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
                         (int)stride[DEX_FIELD_QACC_WARMSTART], (T*)f[DEX_FIELD_TIME], (unsigned*)f[DEX_FIELD_STATUS],
                         (T*)f[DEX_FIELD_CONTACT], (int*)f[DEX_FIELD_NCON], (int*)f[DEX_FIELD_NITER],
                         (const unsigned char*)f[DEX_FIELD_SKIP], (T*)f[DEX_FIELD_JC], (T*)f[DEX_FIELD_MSCR],
-                        (T*)f[DEX_FIELD_XKIN], (T*)f[DEX_FIELD_TREE]};
+                        (T*)f[DEX_FIELD_XKIN], (T*)f[DEX_FIELD_STAGE], (int*)f[DEX_FIELD_NSLOT], nullptr, nullptr, 0,
+                        (T*)f[DEX_FIELD_TREE]};
     TaskState<T> ts = {(const T*)f[DEX_FIELD_ACTION], (int)stride[DEX_FIELD_ACTION], (T*)f[DEX_FIELD_OBS], (T*)f[DEX_FIELD_REWARD],
                        (T*)f[DEX_FIELD_DISCOUNT], (T*)f[DEX_FIELD_GOAL], (int*)f[DEX_FIELD_TASK_I], (T*)f[DEX_FIELD_TASK_F],
                        (unsigned*)f[DEX_FIELD_RNG], (unsigned char*)f[DEX_FIELD_SKIP], (const unsigned char*)f[DEX_FIELD_RESET_MASK],
@@ -200,7 +219,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
         dex_emu::run_warp([&]() { dex_task_pre_env<T>(dev, st, ts, *p, env, force_reset); });
         if (!force_reset) for (int s = 0; s < nsub; ++s) {
           dex_tree_env<T>(dev, st, env);
-          dex_emu::run_warp([&]() { dex_collide_env<T>(dev, st, env, smem.data()); });
+          emu_collide<T>(dev, st, env, smem.data());
           dex_emu::run_warp([&]() { dex_dynamics_env<T>(dev, st, dbg, env, smem.data(), 1); });
         }
         dex_emu::run_warp([&]() { dex_task_post_env<T>(dev, st, ts, *p, env, smem.data()); });
