@@ -46,18 +46,13 @@ __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T
   dex_tree_env<T>(m, st, env);
 }
 
-#ifndef DEX_NARROW_G
-#define DEX_NARROW_G 32  // lanes per convex-convex candidate in K1b (r01h: 32 -> 0.43 ms, 8 -> 0.49, 4 -> 0.47 per launch)
-#endif
-constexpr int kNarrowBlock = 128;
-constexpr int kNarrowG = DEX_NARROW_G;
+constexpr int kNarrowBlock = 64;
 template <typename T>
 __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevModel<T> m, BatchState<T> st) {
   int n = *st.nwork;
   if (n > st.work_cap) n = st.work_cap;
-  const int per = kNarrowBlock / kNarrowG;   // items per CTA and round
-  for (int i = blockIdx.x * per + threadIdx.x / kNarrowG; i < n; i += gridDim.x * per)
-    dex_narrow_item<kNarrowG, T>(m, st, st.work[2 * (size_t)i], st.work[2 * (size_t)i + 1]);
+  for (int i = blockIdx.x * kNarrowBlock + threadIdx.x; i < n; i += gridDim.x * kNarrowBlock)
+    dex_narrow_lane<T>(m, st, st.work[2 * (size_t)i], st.work[2 * (size_t)i + 1]);
 }
 
 template <typename T>
@@ -205,9 +200,8 @@ struct ProfScope {  // records an event pair around one launch when profiling is
 // K1b runs a grid-stride loop over a device-side item count: size the grid for ~8 items per env,
 // capped at a few CTAs per SM
 inline int narrow_grid(int nenv) {
-  const int per = kNarrowBlock / kNarrowG;
-  long long want = ((long long)nenv * 8 + per - 1) / per;
-  const long long cap = 148 * 16;
+  long long want = ((long long)nenv * 8 + kNarrowBlock - 1) / kNarrowBlock;
+  const long long cap = 148 * 32;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;

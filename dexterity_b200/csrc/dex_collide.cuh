@@ -10,10 +10,9 @@
 //       pairs (mjc_PlaneBox, mjc_PlaneConvex) are finished here; every convex-convex survivor gets a
 //       slot in the env's staging list and one entry in a GLOBAL work list.
 //   K1b narrowphase, THREAD per work item: libccd's MPR (ccdMPRPenetration) with
-//       mpr_tolerance / mpr_iterations in the frame of body A.  The portal logic is scalar per pair, so
-//       a warp that runs ONE pair keeps 1 lane's worth of work on 32 lanes (r01f profile: 12 k warp
-//       instructions per env, half of the old fused kernel); here 32 pairs share a warp and the hull
-//       scans run serially per thread (first strict maximum = lowest index, as the warp argmax had).
+//       mpr_tolerance / mpr_iterations in the frame of body A, as a phase state machine (one support
+//       evaluation per loop trip) so that the 32 pairs of a warp stay converged; mesh supports climb
+//       the hull graph from the previous support vertex.
 //   K1c compaction, WARP per env: valid staging slots -> contact list [env][DEX_MAXCON][8] + ncon, in
 //       slot (= pair) order, which is MuJoCo's contact order.
 #ifndef DEX_COLLIDE_CUH_
@@ -84,47 +83,17 @@ DEX_DEV_NOINLINE V3<T> dex_support_local(const T* vert, int n, int gtype, const 
   }
   return out;
 }
-// The same support point computed by a group of G consecutive lanes (K1b; G = 1: one thread).  Every
-// lane of the group calls with identical arguments and gets the result; the group's lanes stride over
-// the hull and the partial maxima are merged with group-masked shuffles (lowest index wins ties, as in
-// a serial "first strict maximum" scan).
-template <int G, typename T>
-DEX_DEV V3<T> dex_support_group(const T* vert, int n, int gtype, const T* mat, const T* size, const T* pack,
-                                T lx, T ly, T lz) {
-  V3<T> out;
-  if (gtype == DEX_GEOM_MESH) {
-    T best = -Real<T>::big();
-    int bi = 0x7fffffff;
-    for (int i = dex_lane() & (G - 1); i < n; i += G) {
-      T vx, vy, vz;
-      dex_ldg_xyz(vert + 4 * i, vx, vy, vz);
-      const T t = vx * lx + vy * ly + vz * lz;
-      if (t > best) { best = t; bi = i; }
-    }
-#pragma unroll
-    for (int mm = G >> 1; mm > 0; mm >>= 1) {
-      const T ov = dex_gshfl_xor<G>(best, mm);
-      const int oi = dex_gshfl_xor<G>(bi, mm);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    dex_ldg_xyz(vert + 4 * bi, out.x, out.y, out.z);
-  } else {  // box
-    T Gm[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
-    for (int i = 0; i < 9; ++i) Gm[i] = dex_ldg(mat + i);
-    rotT_vec(l2, Gm, ld);
-    cn[0] = l2[0] > 0 ? dex_ldg(size) : -dex_ldg(size);
-    cn[1] = l2[1] > 0 ? dex_ldg(size + 1) : -dex_ldg(size + 1);
-    cn[2] = l2[2] > 0 ? dex_ldg(size + 2) : -dex_ldg(size + 2);
-    rot_vec(loc, Gm, cn);
-    out.x = loc[0] + dex_ldg(pack); out.y = loc[1] + dex_ldg(pack + 1); out.z = loc[2] + dex_ldg(pack + 2);
-  }
-  return out;
-}
-// G = 32: the whole warp works on one pair (non-inlined REDUX version above); G < 32: a group of G lanes.
-template <int G, typename T>
+template <typename T>
 DEX_DEV V3<T> dex_support_ref(const GeomRef<T>& g, T lx, T ly, T lz) {
-  if (G == 32) return dex_support_local(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
-  return dex_support_group<G>(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
+  return dex_support_local(g.vert, g.n, g.type, g.mat, g.size, g.pack, lx, ly, lz);
+}
+
+// one stored contact: dist, pos(3), normal(3), pair id
+template <typename T>
+DEX_DEV void dex_store_contact(T* dst, T dist, const T* pos, const T* normal, int pair) {
+  dst[0] = dist; dst[1] = pos[0]; dst[2] = pos[1]; dst[3] = pos[2];
+  dst[4] = normal[0]; dst[5] = normal[1]; dst[6] = normal[2];
+  dst[7] = (T)pair;  // exact for pair ids < 2^24
 }
 
 // ---- libccd helpers ---------------------------------------------------------------------
@@ -142,28 +111,6 @@ template <typename T> DEX_DEV bool ccd_eq(T a, T b) {
 // Minkowski-difference support point: v = v1 - v2, v1 on geom A, v2 on geom B (both in frame A)
 template <typename T> struct SupPt { T v[3], v1[3]; };
 
-template <typename T>
-struct MprCtx {
-  GeomRef<T> A, B;
-  Xf<T> rel;
-  T half_margin;  // mjc_Convex inflates both shapes by margin/2 along the query direction
-  T tolerance;    // opt.mpr_tolerance
-  int iterations; // opt.mpr_iterations
-};
-
-template <int G, typename T>
-DEX_DEV void dex_mink(const MprCtx<T>& c, const T* dir, SupPt<T>& p) {
-  const V3<T> a = dex_support_ref<G>(c.A, dir[0], dir[1], dir[2]);
-  T nd[3] = {-dir[0], -dir[1], -dir[2]}, lb[3];
-  rotT_vec(lb, c.rel.R, nd);
-  const V3<T> b = dex_support_ref<G>(c.B, lb[0], lb[1], lb[2]);
-  T bl[3] = {b.x, b.y, b.z}, bw[3];
-  rot_vec(bw, c.rel.R, bl);
-  p.v1[0] = a.x + dir[0] * c.half_margin; p.v1[1] = a.y + dir[1] * c.half_margin; p.v1[2] = a.z + dir[2] * c.half_margin;
-  p.v[0] = p.v1[0] - (bw[0] + c.rel.t[0] - dir[0] * c.half_margin);
-  p.v[1] = p.v1[1] - (bw[1] + c.rel.t[1] - dir[1] * c.half_margin);
-  p.v[2] = p.v1[2] - (bw[2] + c.rel.t[2] - dir[2] * c.half_margin);
-}
 template <typename T> DEX_DEV T point_seg_dist2(const T* x0, const T* b, T* wit) {  // P = origin
   T dd[3] = {b[0] - x0[0], b[1] - x0[1], b[2] - x0[2]};
   T t = -dot3(x0, dd) / dot3(dd, dd);
@@ -214,110 +161,243 @@ template <typename T> DEX_DEV void expand_portal(SupPt<T>* s, const SupPt<T>& v4
   }
 }
 
-// ccdMPRPenetration in the frame of body A, run by a group of G lanes with identical (group-uniform) state.  Returns true on intersection; depth / dir / pos as libccd (pos = midpoint of the witness
-// points on A and B).
-template <int G, typename T>
-DEX_DEV bool dex_mpr(const MprCtx<T>& c, T* depth, T* pdir, T* pos) {
+// ------------------------------------------------------------------------------------------
+// K1b: ccdMPRPenetration with ONE THREAD per candidate pair, written as a state machine so that the 32
+// pairs of a warp stay converged: every trip of the loop evaluates one Minkowski support point (the
+// common, expensive part) and then advances the pair's phase (portal construction, refinement,
+// penetration search) -- libccd's discoverPortal / refinePortal / findPenetr unrolled into phases with
+// identical arithmetic and identical exits.  The r01h profile showed why: with a group of lanes per
+// pair the scalar portal logic is replicated G times and pairs of one warp diverge at once (12 of 32
+// lanes active, 2 k warp instructions per pair).
+// The mesh support function climbs the hull graph (as MuJoCo's mesh support does) from the previous
+// support vertex of the same geom; hulls of up to DEX_SCAN_MAX vertices are scanned exhaustively.
+// On a convex hull every local maximum is global, so both give the first-maximum vertex except on
+// exact ties (a face perpendicular to the direction), the degenerate states DESIGN.md describes.
+// ------------------------------------------------------------------------------------------
+#define DEX_SCAN_MAX 24
+template <typename T>
+struct LaneGeom {
+  const T* vert;   // body-frame hull vertices of the geom instance (4 reals per vertex)
+  int n, type, g;
+  int adjbase;     // mesh-vertex base into DevModel::vadj
+  int last;        // previous support vertex (warm start), -1 = none
+};
+template <typename T>
+DEX_DEV void dex_support_lane(const DevModel<T>& m, LaneGeom<T>& G, T lx, T ly, T lz, T* out) {
+  if (G.type == DEX_GEOM_MESH) {
+    int bi = 0;
+    if (G.n <= DEX_SCAN_MAX) {
+      T best = -Real<T>::big();
+      for (int i = 0; i < G.n; ++i) {
+        T vx, vy, vz;
+        dex_ldg_xyz(G.vert + 4 * i, vx, vy, vz);
+        const T t = vx * lx + vy * ly + vz * lz;
+        if (t > best) { best = t; bi = i; }
+      }
+    } else {
+      if (G.last >= 0) bi = G.last;
+      else {  // start at the hull vertex that is extreme along the dominant axis of the direction
+        const T ax = dx_abs(lx), ay = dx_abs(ly), az = dx_abs(lz);
+        const int k = ax >= ay ? (ax >= az ? (lx < 0 ? 1 : 0) : (lz < 0 ? 5 : 4)) : (ay >= az ? (ly < 0 ? 3 : 2) : (lz < 0 ? 5 : 4));
+        bi = dex_ldg(m.geom_start6 + 6 * G.g + k);
+      }
+      T vx, vy, vz;
+      dex_ldg_xyz(G.vert + 4 * bi, vx, vy, vz);
+      T best = vx * lx + vy * ly + vz * lz;
+      for (int guard = 0; guard < G.n; ++guard) {
+        const int info = dex_ldg(m.vadj + G.adjbase + bi);
+        const int* nb = m.adj + (info >> 8);
+        const int num = info & 255;
+        int nxt = bi;
+        T nv = best;
+        for (int k = 0; k < num; ++k) {
+          const int j = dex_ldg(nb + k);
+          dex_ldg_xyz(G.vert + 4 * j, vx, vy, vz);
+          const T t = vx * lx + vy * ly + vz * lz;
+          if (t > nv || (t == nv && j < nxt)) { nv = t; nxt = j; }   // ties move towards the lowest index
+        }
+        if (nxt == bi) break;
+        bi = nxt; best = nv;
+      }
+      G.last = bi;
+    }
+    dex_ldg_xyz(G.vert + 4 * bi, out[0], out[1], out[2]);
+  } else {  // box
+    const T* mat = m.geom_mat + 9 * G.g;
+    const T* size = m.geom_size + 3 * G.g;
+    const T* pack = m.geom_pack + DEX_GPACK * G.g;
+    T Gm[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
+    for (int i = 0; i < 9; ++i) Gm[i] = dex_ldg(mat + i);
+    rotT_vec(l2, Gm, ld);
+    cn[0] = l2[0] > 0 ? dex_ldg(size) : -dex_ldg(size);
+    cn[1] = l2[1] > 0 ? dex_ldg(size + 1) : -dex_ldg(size + 1);
+    cn[2] = l2[2] > 0 ? dex_ldg(size + 2) : -dex_ldg(size + 2);
+    rot_vec(loc, Gm, cn);
+    out[0] = loc[0] + dex_ldg(pack); out[1] = loc[1] + dex_ldg(pack + 1); out[2] = loc[2] + dex_ldg(pack + 2);
+  }
+}
+
+enum { MPR_P1 = 1, MPR_P2 = 2, MPR_DISCOVER = 3, MPR_REFINE = 4, MPR_PENETR = 5, MPR_DONE = 0 };
+
+// item = (env, slot << 24 | pair): runs MPR for the pair and writes the env's staging slot.
+template <typename T>
+DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int env, int wv) {
+  const int p = wv & 0xffffff, slot = wv >> 24;
+  const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
+  const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
+  const T margin = dex_ldg(m.pair_margin + p);
+  const T half_margin = T(0.5) * margin;
+  const T tolerance = m.mpr_tolerance;
+  const int iterations = m.mpr_iterations;
+  const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
+  T x1[3], R1[9];
+  Xf<T> rel;
+  {
+    T x2[3], R2[9];
+    for (int k = 0; k < 3; ++k) { x1[k] = xk[b1 * DEX_XKIN_BODY + k]; x2[k] = xk[b2 * DEX_XKIN_BODY + k]; }
+    for (int k = 0; k < 9; ++k) { R1[k] = xk[b1 * DEX_XKIN_BODY + 7 + k]; R2[k] = xk[b2 * DEX_XKIN_BODY + 7 + k]; }
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+      rel.R[3 * r + c] = R1[r] * R2[c] + R1[3 + r] * R2[3 + c] + R1[6 + r] * R2[6 + c];
+    const T d[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
+    rotT_vec(rel.t, R1, d);
+  }
+  LaneGeom<T> A = {m.vert + 4 * dex_ldg(m.geom_vertadr + g1), dex_ldg(m.geom_vertnum + g1), dex_ldg(m.geom_type + g1), g1,
+                   dex_ldg(m.geom_adjbase + g1), -1};
+  LaneGeom<T> B = {m.vert + 4 * dex_ldg(m.geom_vertadr + g2), dex_ldg(m.geom_vertnum + g2), dex_ldg(m.geom_type + g2), g2,
+                   dex_ldg(m.geom_adjbase + g2), -1};
+
   SupPt<T> s[4], v4;
   T dir[3], va[3], vb[3];
+  T depth = 0, pdir[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
+  bool hit = false;
   {
-    const T* pa = c.A.pack;
-    const T* pb = c.B.pack;
+    const T* pa = m.geom_pack + DEX_GPACK * g1;
+    const T* pb = m.geom_pack + DEX_GPACK * g2;
     T cb[3] = {dex_ldg(pb), dex_ldg(pb + 1), dex_ldg(pb + 2)}, cbw[3];
-    rot_vec(cbw, c.rel.R, cb);
-    for (int k = 0; k < 3; ++k) { s[0].v1[k] = dex_ldg(pa + k); s[0].v[k] = s[0].v1[k] - (cbw[k] + c.rel.t[k]); }
+    rot_vec(cbw, rel.R, cb);
+    for (int k = 0; k < 3; ++k) { s[0].v1[k] = dex_ldg(pa + k); s[0].v[k] = s[0].v1[k] - (cbw[k] + rel.t[k]); }
   }
   if (ccd_zero(s[0].v[0]) && ccd_zero(s[0].v[1]) && ccd_zero(s[0].v[2])) s[0].v[0] += T(2.220446049250313e-15);
   dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
   normalize3(dir);
-  dex_mink<G>(c, dir, s[1]);
-  T dt = dot3(s[1].v, dir);
-  if (ccd_zero(dt) || dt < 0) return false;
-  cross3(dir, s[0].v, s[1].v);
-  if (ccd_zero(dot3(dir, dir))) {
-    if (ccd_zero(s[1].v[0]) && ccd_zero(s[1].v[1]) && ccd_zero(s[1].v[2])) {  // touching: findPenetrTouch
-      *depth = 0; pdir[0] = pdir[1] = pdir[2] = 0;
-    } else {  // origin on v0-v1: findPenetrSegment
-      *depth = dx_sqrt(dot3(s[1].v, s[1].v));
-      pdir[0] = s[1].v[0]; pdir[1] = s[1].v[1]; pdir[2] = s[1].v[2];
-      normalize3(pdir);
-    }
-    for (int k = 0; k < 3; ++k) pos[k] = s[1].v1[k] - T(0.5) * s[1].v[k];  // (v1 + v2) / 2
-    return true;
-  }
-  normalize3(dir);
-  dex_mink<G>(c, dir, s[2]);
-  dt = dot3(s[2].v, dir);
-  if (ccd_zero(dt) || dt < 0) return false;
-  for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
-  cross3(dir, va, vb);
-  normalize3(dir);
-  if (dot3(dir, s[0].v) > 0) {
-    SupPt<T> tmp = s[1]; s[1] = s[2]; s[2] = tmp;
-    dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2];
-  }
-  for (int guard = 0;; ++guard) {  // discoverPortal: find v3
-    if (guard > 100) return false;
-    dex_mink<G>(c, dir, s[3]);
-    dt = dot3(s[3].v, dir);
-    if (ccd_zero(dt) || dt < 0) return false;
-    bool cont = false;
-    cross3(va, s[1].v, s[3].v);
-    dt = dot3(va, s[0].v);
-    if (dt < 0 && !ccd_zero(dt)) { s[2] = s[3]; cont = true; }
-    if (!cont) {
-      cross3(va, s[3].v, s[2].v);
-      dt = dot3(va, s[0].v);
-      if (dt < 0 && !ccd_zero(dt)) { s[1] = s[3]; cont = true; }
-    }
-    if (!cont) break;
-    for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
-    cross3(dir, va, vb);
-    normalize3(dir);
-  }
-  for (int guard = 0;; ++guard) {  // refinePortal
-    if (guard > 100) return false;
-    portal_dir(s, dir);
-    dt = dot3(dir, s[1].v);
-    if (ccd_zero(dt) || dt > 0) break;
-    dex_mink<G>(c, dir, v4);
-    dt = dot3(v4.v, dir);
-    if (!(ccd_zero(dt) || dt > 0) || portal_reach_tol(s, v4, dir, c.tolerance)) return false;
-    expand_portal(s, v4);
-  }
-  for (int it = 0;; ++it) {  // findPenetr
-    portal_dir(s, dir);
-    dex_mink<G>(c, dir, v4);
-    if (portal_reach_tol(s, v4, dir, c.tolerance) || it > c.iterations) {
-      T d2 = point_tri_dist2(s[1].v, s[2].v, s[3].v, pdir);
-      *depth = dx_sqrt(d2);
-      if (ccd_zero(pdir[0]) && ccd_zero(pdir[1]) && ccd_zero(pdir[2])) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; }
-      normalize3(pdir);
-      // findPos: barycentric coordinates of the origin in the portal tetrahedron
-      T b[4], t[3];
-      cross3(t, s[1].v, s[2].v); b[0] = dot3(t, s[3].v);
-      cross3(t, s[3].v, s[2].v); b[1] = dot3(t, s[0].v);
-      cross3(t, s[0].v, s[1].v); b[2] = dot3(t, s[3].v);
-      cross3(t, s[2].v, s[1].v); b[3] = dot3(t, s[0].v);
-      T sum = b[0] + b[1] + b[2] + b[3];
-      if (ccd_zero(sum) || sum < 0) {
-        b[0] = 0;
-        cross3(t, s[2].v, s[3].v); b[1] = dot3(t, dir);
-        cross3(t, s[3].v, s[1].v); b[2] = dot3(t, dir);
-        cross3(t, s[1].v, s[2].v); b[3] = dot3(t, dir);
-        sum = b[1] + b[2] + b[3];
-      }
-      T inv = T(1) / sum;
+  int phase = MPR_P1, guard = 0;
+  while (phase != MPR_DONE) {
+    // ---- Minkowski-difference support point along dir (v = v1 - v2, both shapes inflated by margin / 2)
+    {
+      T a[3], b[3], nd[3] = {-dir[0], -dir[1], -dir[2]}, lb[3], bw[3];
+      dex_support_lane(m, A, dir[0], dir[1], dir[2], a);
+      rotT_vec(lb, rel.R, nd);
+      dex_support_lane(m, B, lb[0], lb[1], lb[2], b);
+      rot_vec(bw, rel.R, b);
       for (int k = 0; k < 3; ++k) {
-        // p1 = sum b_i v1_i, p2 = sum b_i v2_i with v2 = v1 - v;  pos = (p1 + p2) / 2
-        T p1 = b[0] * s[0].v1[k] + b[1] * s[1].v1[k] + b[2] * s[2].v1[k] + b[3] * s[3].v1[k];
-        T pv = b[0] * s[0].v[k] + b[1] * s[1].v[k] + b[2] * s[2].v[k] + b[3] * s[3].v[k];
-        pos[k] = (p1 - T(0.5) * pv) * inv;
+        v4.v1[k] = a[k] + dir[k] * half_margin;
+        v4.v[k] = v4.v1[k] - (bw[k] + rel.t[k] - dir[k] * half_margin);
       }
-      return true;
     }
-    expand_portal(s, v4);
+    const T dv = dot3(v4.v, dir);
+    bool need_portal = false;
+    if (phase == MPR_P1) {
+      s[1] = v4;
+      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; continue; }
+      cross3(dir, s[0].v, s[1].v);
+      if (ccd_zero(dot3(dir, dir))) {
+        if (ccd_zero(s[1].v[0]) && ccd_zero(s[1].v[1]) && ccd_zero(s[1].v[2])) {  // touching: findPenetrTouch
+          depth = 0; pdir[0] = pdir[1] = pdir[2] = 0;
+        } else {  // origin on v0-v1: findPenetrSegment
+          depth = dx_sqrt(dot3(s[1].v, s[1].v));
+          pdir[0] = s[1].v[0]; pdir[1] = s[1].v[1]; pdir[2] = s[1].v[2];
+          normalize3(pdir);
+        }
+        for (int k = 0; k < 3; ++k) pos[k] = s[1].v1[k] - T(0.5) * s[1].v[k];  // (v1 + v2) / 2
+        hit = true; phase = MPR_DONE; continue;
+      }
+      normalize3(dir);
+      phase = MPR_P2;
+    } else if (phase == MPR_P2) {
+      s[2] = v4;
+      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; continue; }
+      for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
+      cross3(dir, va, vb);
+      normalize3(dir);
+      if (dot3(dir, s[0].v) > 0) {
+        SupPt<T> tmp = s[1]; s[1] = s[2]; s[2] = tmp;
+        dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2];
+      }
+      phase = MPR_DISCOVER; guard = 0;
+    } else if (phase == MPR_DISCOVER) {  // discoverPortal: find v3
+      s[3] = v4;
+      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; continue; }
+      bool cont = false;
+      cross3(va, s[1].v, s[3].v);
+      T dt = dot3(va, s[0].v);
+      if (dt < 0 && !ccd_zero(dt)) { s[2] = s[3]; cont = true; }
+      if (!cont) {
+        cross3(va, s[3].v, s[2].v);
+        dt = dot3(va, s[0].v);
+        if (dt < 0 && !ccd_zero(dt)) { s[1] = s[3]; cont = true; }
+      }
+      if (cont) {
+        if (++guard > 100) { phase = MPR_DONE; continue; }
+        for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
+        cross3(dir, va, vb);
+        normalize3(dir);
+      } else {
+        phase = MPR_REFINE; guard = 0;
+        need_portal = true;
+      }
+    } else {  // refinePortal / findPenetr: both test the new point against the portal, then expand it
+      const bool reach = portal_reach_tol(s, v4, dir, tolerance);
+      if (phase == MPR_REFINE) {
+        if (!(ccd_zero(dv) || dv > 0) || reach) { phase = MPR_DONE; continue; }
+      } else if (reach || guard > iterations) {
+        T d2 = point_tri_dist2(s[1].v, s[2].v, s[3].v, pdir);
+        depth = dx_sqrt(d2);
+        if (ccd_zero(pdir[0]) && ccd_zero(pdir[1]) && ccd_zero(pdir[2])) { pdir[0] = dir[0]; pdir[1] = dir[1]; pdir[2] = dir[2]; }
+        normalize3(pdir);
+        // findPos: barycentric coordinates of the origin in the portal tetrahedron
+        T b[4], t[3];
+        cross3(t, s[1].v, s[2].v); b[0] = dot3(t, s[3].v);
+        cross3(t, s[3].v, s[2].v); b[1] = dot3(t, s[0].v);
+        cross3(t, s[0].v, s[1].v); b[2] = dot3(t, s[3].v);
+        cross3(t, s[2].v, s[1].v); b[3] = dot3(t, s[0].v);
+        T sum = b[0] + b[1] + b[2] + b[3];
+        if (ccd_zero(sum) || sum < 0) {
+          b[0] = 0;
+          cross3(t, s[2].v, s[3].v); b[1] = dot3(t, dir);
+          cross3(t, s[3].v, s[1].v); b[2] = dot3(t, dir);
+          cross3(t, s[1].v, s[2].v); b[3] = dot3(t, dir);
+          sum = b[1] + b[2] + b[3];
+        }
+        T inv = T(1) / sum;
+        for (int k = 0; k < 3; ++k) {
+          // p1 = sum b_i v1_i, p2 = sum b_i v2_i with v2 = v1 - v;  pos = (p1 + p2) / 2
+          T p1 = b[0] * s[0].v1[k] + b[1] * s[1].v1[k] + b[2] * s[2].v1[k] + b[3] * s[3].v1[k];
+          T pv = b[0] * s[0].v[k] + b[1] * s[1].v[k] + b[2] * s[2].v[k] + b[3] * s[3].v[k];
+          pos[k] = (p1 - T(0.5) * pv) * inv;
+        }
+        hit = true; phase = MPR_DONE; continue;
+      }
+      expand_portal(s, v4);
+      ++guard;
+      if (phase == MPR_REFINE && guard > 100) { phase = MPR_DONE; continue; }
+      need_portal = true;
+    }
+    if (need_portal) {
+      portal_dir(s, dir);
+      if (phase == MPR_REFINE) {
+        const T dt = dot3(dir, s[1].v);
+        if (ccd_zero(dt) || dt > 0) { phase = MPR_PENETR; guard = 0; }
+      }
+    }
   }
+  T* out = st.stage + (size_t)env * DEX_STAGE_ENV + slot * DEX_CON_STRIDE;
+  if (hit && !(pdir[0] == 0 && pdir[1] == 0 && pdir[2] == 0)) {
+    T pw[3], nw[3];
+    rot_vec(pw, R1, pos);
+    rot_vec(nw, R1, pdir);
+    pw[0] += x1[0]; pw[1] += x1[1]; pw[2] += x1[2];
+    dex_store_contact(out, margin - depth, pw, nw, p);
+  } else out[7] = T(-1);
 }
 
 // pose of body b2 in the frame of body b1
@@ -376,12 +456,6 @@ DEX_DEV bool dex_obb_overlap(const Xf<T>& rel, const T* pk1, const T* pk2, T mar
 // ------------------------------------------------------------------------------------------
 // K1 body.  smem: [xpos | xquat | xmat | qpos | cand(int)]
 // ------------------------------------------------------------------------------------------
-template <typename T>
-DEX_DEV void dex_store_contact(T* dst, T dist, const T* pos, const T* normal, int pair) {
-  dst[0] = dist; dst[1] = pos[0]; dst[2] = pos[1]; dst[3] = pos[2];
-  dst[4] = normal[0]; dst[5] = normal[1]; dst[6] = normal[2];
-  dst[7] = (T)pair;  // exact for pair ids < 2^24
-}
 
 template <typename T>
 DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
@@ -586,7 +660,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
       if (nslot >= DEX_MAXSLOT) { status |= DEX_STATUS_CAND_OVERFLOW; continue; }
       T nn[3] = {-n[0], -n[1], -n[2]}, ld[3], w[3];
       rotT_vec(ld, xmat + 9 * b2, nn);
-      const V3<T> sp = dex_support_ref<32>(dex_geom_ref(m, g2, t2), ld[0], ld[1], ld[2]);
+      const V3<T> sp = dex_support_ref(dex_geom_ref(m, g2, t2), ld[0], ld[1], ld[2]);
       T sl[3] = {sp.x, sp.y, sp.z};
       rot_vec(w, xmat + 9 * b2, sl);
       w[0] += xpos[3 * b2]; w[1] += xpos[3 * b2 + 1]; w[2] += xpos[3 * b2 + 2];
@@ -615,41 +689,6 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   if (dex_ballot(ovf)) status |= DEX_STATUS_CAND_OVERFLOW;
   if (lane == 0 && status) st.status[env] |= status;
   if (lane == 0) st.nslot[env] = nslot;
-}
-
-// K1b: one convex-convex candidate per group of G lanes (all of them call this with the same item).
-// item = (env, slot << 24 | pair).
-template <int G, typename T>
-DEX_DEV void dex_narrow_item(const DevModel<T>& m, const BatchState<T>& st, int env, int wv) {
-  const int p = wv & 0xffffff, slot = wv >> 24;
-  const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
-  const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
-  const T margin = dex_ldg(m.pair_margin + p);
-  const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
-  T x1[3], R1[9], x2[3], R2[9];
-  for (int k = 0; k < 3; ++k) { x1[k] = xk[b1 * DEX_XKIN_BODY + k]; x2[k] = xk[b2 * DEX_XKIN_BODY + k]; }
-  for (int k = 0; k < 9; ++k) { R1[k] = xk[b1 * DEX_XKIN_BODY + 7 + k]; R2[k] = xk[b2 * DEX_XKIN_BODY + 7 + k]; }
-  MprCtx<T> mc;
-  mc.A = dex_geom_ref(m, g1, dex_ldg(m.geom_type + g1)); mc.B = dex_geom_ref(m, g2, dex_ldg(m.geom_type + g2));
-  mc.half_margin = T(0.5) * margin;
-  mc.tolerance = m.mpr_tolerance; mc.iterations = m.mpr_iterations;
-  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
-    mc.rel.R[3 * r + c] = R1[r] * R2[c] + R1[3 + r] * R2[3 + c] + R1[6 + r] * R2[6 + c];
-  {
-    const T d[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
-    rotT_vec(mc.rel.t, R1, d);
-  }
-  T* out = st.stage + (size_t)env * DEX_STAGE_ENV + slot * DEX_CON_STRIDE;
-  T depth, dir[3], pos[3];
-  const bool hit = dex_mpr<G>(mc, &depth, dir, pos) && !(dir[0] == 0 && dir[1] == 0 && dir[2] == 0);
-  if ((dex_lane() & (G - 1)) != 0) return;
-  if (hit) {
-    T pw[3], nw[3];
-    rot_vec(pw, R1, pos);
-    rot_vec(nw, R1, dir);
-    pw[0] += x1[0]; pw[1] += x1[1]; pw[2] += x1[2];
-    dex_store_contact(out, margin - depth, pw, nw, p);
-  } else out[7] = T(-1);
 }
 
 // K1c: staging slots -> contact list in slot order (warp per env).

@@ -203,6 +203,40 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
         }
       }
     }
+    // hull graph for the hill-climbing support function of the narrowphase: per MESH vertex one packed
+    // word (first neighbour << 8 | neighbour count) into `adj` (neighbour ids local to the mesh), per geom
+    // the mesh-vertex base of its hull and six start vertices (extreme along +-x, +-y, +-z of the body frame)
+    {
+      std::vector<int> aadr = I(DEXF_VERT_ADJADR), anum = I(DEXF_VERT_ADJNUM);
+      M.adj = I(DEXF_ADJ);
+      if (M.adj.empty()) M.adj.assign(1, 0);
+      M.vadj.assign(std::max<size_t>(aadr.size(), 1), 0);
+      for (size_t i = 0; i < aadr.size(); ++i) {
+        if (anum[i] > 255 || aadr[i] >= (1 << 23)) return "hull graph exceeds the packed adjacency format";
+        M.vadj[i] = (aadr[i] << 8) | anum[i];
+      }
+      M.geom_adjbase.assign(M.ngeom, 0);
+      M.geom_start6.assign(6 * M.ngeom, 0);
+      for (int g = 0; g < M.ngeom; ++g) {
+        if (M.geom_type[g] != DEX_GEOM_MESH) continue;
+        M.geom_adjbase[g] = va[g];
+        for (int k = 0; k < 6; ++k) {
+          int best = 0; double bv = -1e300;
+          for (int i = 0; i < vn[g]; ++i) {
+            const double t = (k & 1 ? -1.0 : 1.0) * M.vert[4 * (M.geom_vertadr[g] + i) + (k >> 1)];
+            if (t > bv) { bv = t; best = i; }
+          }
+          M.geom_start6[6 * g + k] = best;
+        }
+        for (int i = 0; i < vn[g]; ++i) {
+          if (va[g] + i >= (int)aadr.size()) return "hull graph missing for a mesh geom";
+          for (int k = 0; k < anum[va[g] + i]; ++k) {
+            const int j = M.adj[aadr[va[g] + i] + k];
+            if (j < 0 || j >= vn[g]) return "hull graph neighbour out of range";
+          }
+        }
+      }
+    }
     // body-frame AABB (centre, half extents) of every geom: tightens the broadphase (conservative)
     M.geom_aabb.assign(6 * M.ngeom, 0);
     for (int g = 0; g < M.ngeom; ++g) {

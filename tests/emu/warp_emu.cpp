@@ -130,12 +130,7 @@ static void emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, 
   BatchState<T> sl = st;
   sl.nwork = work.data(); sl.work = work.data() + 1; sl.work_cap = DEX_MAXSLOT;
   dex_emu::run_warp([&]() { dex_collide_env<T>(m, sl, env, smem); });
-  // groups of 8 fibers per item, 4 items per emulated warp (idle groups return at once)
-  for (int i0 = 0; i0 < work[0]; i0 += 4)
-    dex_emu::run_warp([&]() {
-      const int i = i0 + dex_emu::lane() / 8;
-      if (i < work[0]) dex_narrow_item<8, T>(m, sl, work[1 + 2 * i], work[2 + 2 * i]);
-    });
+  for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[1 + 2 * i], work[2 + 2 * i]);  // K1b is thread-per-item
   dex_emu::run_warp([&]() { dex_compact_env<T>(m, sl, env); });
 }
 
