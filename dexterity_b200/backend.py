@@ -120,9 +120,9 @@ class PhysicsBatch:
                                DBG_QFRC_CONSTRAINT=z(n, c.nv), DBG_EFC=z(n, maxcon, 8))
         for name, t in self._store.items():
             self.bind(name, t)
-        # global narrowphase work list: word 0 = item count, then (env, slot << 24 | pair) per item
+        # global narrowphase work list: item count, fetch cursor, then (env, slot << 24 | pair) per item
         cap = max(32 * n, 4096)
-        work = z(1 + 2 * cap, dt=torch.int32)
+        work = z(2 + 2 * cap, dt=torch.int32)
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
         # public views with the model's true widths

@@ -41,18 +41,41 @@ constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps sp
 template <typename T>
 __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {
   const int env = blockIdx.x * kTreeBlock + threadIdx.x;
-  if (env == 0) *st.nwork = 0;  // the narrowphase work list of this mj_step starts empty (stream-ordered)
+  if (env == 0) { st.nwork[0] = 0; st.nwork[1] = 0; }  // this mj_step's narrowphase work list: item count, fetch cursor
   if (env >= st.nenv) return;
   dex_tree_env<T>(m, st, env);
 }
 
-constexpr int kNarrowBlock = 64;
+#ifndef DEX_NARROW_BLOCK
+#define DEX_NARROW_BLOCK 64
+#endif
+constexpr int kNarrowBlock = DEX_NARROW_BLOCK;
+// Persistent lanes: every thread runs one pair's MPR state machine and, as soon as that pair is done,
+// takes the next item off the global list (warp-aggregated atomic on the cursor), so the 32 lanes of a
+// warp stay busy although pairs need between 1 and ~50 support evaluations.
 template <typename T>
 __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevModel<T> m, BatchState<T> st) {
-  int n = *st.nwork;
+  int n = st.nwork[0];
   if (n > st.work_cap) n = st.work_cap;
-  for (int i = blockIdx.x * kNarrowBlock + threadIdx.x; i < n; i += gridDim.x * kNarrowBlock)
-    dex_narrow_lane<T>(m, st, st.work[2 * (size_t)i], st.work[2 * (size_t)i + 1]);
+  const int lane = threadIdx.x & 31;
+  MprLane<T> L;
+  L.phase = MPR_DONE;
+  bool have = false;
+  for (;;) {
+    if (L.phase == MPR_DONE) {
+      if (have) L.finish(m, st);
+      const unsigned am = __activemask();
+      const int leader = __ffs(am) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(st.nwork + 1, __popc(am));
+      base = __shfl_sync(am, base, leader);
+      const int i = base + __popc(am & ((1u << lane) - 1u));
+      if (i >= n) break;
+      L.begin(m, st, st.work[2 * (size_t)i], st.work[2 * (size_t)i + 1]);
+      have = true;
+    }
+    L.step(m);
+  }
 }
 
 template <typename T>
@@ -200,7 +223,10 @@ struct ProfScope {  // records an event pair around one launch when profiling is
 // K1b runs a grid-stride loop over a device-side item count: size the grid for ~8 items per env,
 // capped at a few CTAs per SM
 inline int narrow_grid(int nenv) {
-  long long want = ((long long)nenv * 8 + kNarrowBlock - 1) / kNarrowBlock;
+#ifndef DEX_NARROW_LANES_PER_ENV
+#define DEX_NARROW_LANES_PER_ENV 6
+#endif
+  long long want = ((long long)nenv * DEX_NARROW_LANES_PER_ENV + kNarrowBlock - 1) / kNarrowBlock;
   const long long cap = 148 * 32;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -233,7 +259,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.stage = (T*)b->ptr[DEX_FIELD_STAGE];
   st.nslot = (int*)b->ptr[DEX_FIELD_NSLOT];
   st.nwork = (int*)b->ptr[DEX_FIELD_WORK];
-  st.work = st.nwork + 1;
+  st.work = st.nwork + 2;
   st.work_cap = (int)b->stride[DEX_FIELD_WORK];
   if (st.work_cap < 1) return fail(DEX_E_ARG, "DEX_FIELD_WORK must be bound with row_stride = capacity in items");
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];

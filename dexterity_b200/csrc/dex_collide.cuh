@@ -239,20 +239,29 @@ DEX_DEV void dex_support_lane(const DevModel<T>& m, LaneGeom<T>& G, T lx, T ly, 
 
 enum { MPR_P1 = 1, MPR_P2 = 2, MPR_DISCOVER = 3, MPR_REFINE = 4, MPR_PENETR = 5, MPR_DONE = 0 };
 
-// item = (env, slot << 24 | pair): runs MPR for the pair and writes the env's staging slot.
+// One pair's MPR state.  begin() loads the item (env, slot << 24 | pair), step() evaluates one support
+// point and advances the phase, finish() writes the env's staging slot once phase == MPR_DONE.  The
+// kernel keeps one of these per thread and refills it from the global work list as soon as its pair is
+// done, so that a warp's lanes stay busy although pairs need between 1 and ~50 support evaluations.
 template <typename T>
-DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int env, int wv) {
-  const int p = wv & 0xffffff, slot = wv >> 24;
-  const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
-  const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
-  const T margin = dex_ldg(m.pair_margin + p);
-  const T half_margin = T(0.5) * margin;
-  const T tolerance = m.mpr_tolerance;
-  const int iterations = m.mpr_iterations;
-  const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
-  T x1[3], R1[9];
+struct MprLane {
+  SupPt<T> s[4];
+  T dir[3];
   Xf<T> rel;
+  LaneGeom<T> A, B;
+  T half_margin, depth, pdir[3], pos[3];
+  int env, p, slot, b1, phase, guard;
+  bool hit;
+
+  DEX_DEV void begin(const DevModel<T>& m, const BatchState<T>& st, int env_, int wv) {
+  env = env_; p = wv & 0xffffff; slot = wv >> 24;
+  const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
+  b1 = dex_ldg(m.geom_body + g1);
+  const int b2 = dex_ldg(m.geom_body + g2);
+  half_margin = T(0.5) * dex_ldg(m.pair_margin + p);
+  const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
   {
+    T x1[3], R1[9];
     T x2[3], R2[9];
     for (int k = 0; k < 3; ++k) { x1[k] = xk[b1 * DEX_XKIN_BODY + k]; x2[k] = xk[b2 * DEX_XKIN_BODY + k]; }
     for (int k = 0; k < 9; ++k) { R1[k] = xk[b1 * DEX_XKIN_BODY + 7 + k]; R2[k] = xk[b2 * DEX_XKIN_BODY + 7 + k]; }
@@ -261,15 +270,12 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
     const T d[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
     rotT_vec(rel.t, R1, d);
   }
-  LaneGeom<T> A = {m.vert + 4 * dex_ldg(m.geom_vertadr + g1), dex_ldg(m.geom_vertnum + g1), dex_ldg(m.geom_type + g1), g1,
-                   dex_ldg(m.geom_adjbase + g1), -1};
-  LaneGeom<T> B = {m.vert + 4 * dex_ldg(m.geom_vertadr + g2), dex_ldg(m.geom_vertnum + g2), dex_ldg(m.geom_type + g2), g2,
-                   dex_ldg(m.geom_adjbase + g2), -1};
-
-  SupPt<T> s[4], v4;
-  T dir[3], va[3], vb[3];
-  T depth = 0, pdir[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
-  bool hit = false;
+  A.vert = m.vert + 4 * dex_ldg(m.geom_vertadr + g1); A.n = dex_ldg(m.geom_vertnum + g1); A.type = dex_ldg(m.geom_type + g1);
+  A.g = g1; A.adjbase = dex_ldg(m.geom_adjbase + g1); A.last = -1;
+  B.vert = m.vert + 4 * dex_ldg(m.geom_vertadr + g2); B.n = dex_ldg(m.geom_vertnum + g2); B.type = dex_ldg(m.geom_type + g2);
+  B.g = g2; B.adjbase = dex_ldg(m.geom_adjbase + g2); B.last = -1;
+  depth = 0; pdir[0] = pdir[1] = pdir[2] = 0; pos[0] = pos[1] = pos[2] = 0;
+  hit = false;
   {
     const T* pa = m.geom_pack + DEX_GPACK * g1;
     const T* pb = m.geom_pack + DEX_GPACK * g2;
@@ -280,8 +286,15 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
   if (ccd_zero(s[0].v[0]) && ccd_zero(s[0].v[1]) && ccd_zero(s[0].v[2])) s[0].v[0] += T(2.220446049250313e-15);
   dir[0] = -s[0].v[0]; dir[1] = -s[0].v[1]; dir[2] = -s[0].v[2];
   normalize3(dir);
-  int phase = MPR_P1, guard = 0;
-  while (phase != MPR_DONE) {
+  phase = MPR_P1; guard = 0;
+  }
+
+  // one support evaluation + phase update; `continue` of the loop form = return
+  DEX_DEV void step(const DevModel<T>& m) {
+    const T tolerance = m.mpr_tolerance;
+    const int iterations = m.mpr_iterations;
+    SupPt<T> v4;
+    T va[3], vb[3];
     // ---- Minkowski-difference support point along dir (v = v1 - v2, both shapes inflated by margin / 2)
     {
       T a[3], b[3], nd[3] = {-dir[0], -dir[1], -dir[2]}, lb[3], bw[3];
@@ -298,7 +311,7 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
     bool need_portal = false;
     if (phase == MPR_P1) {
       s[1] = v4;
-      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; continue; }
+      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; return; }
       cross3(dir, s[0].v, s[1].v);
       if (ccd_zero(dot3(dir, dir))) {
         if (ccd_zero(s[1].v[0]) && ccd_zero(s[1].v[1]) && ccd_zero(s[1].v[2])) {  // touching: findPenetrTouch
@@ -309,13 +322,13 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
           normalize3(pdir);
         }
         for (int k = 0; k < 3; ++k) pos[k] = s[1].v1[k] - T(0.5) * s[1].v[k];  // (v1 + v2) / 2
-        hit = true; phase = MPR_DONE; continue;
+        hit = true; phase = MPR_DONE; return;
       }
       normalize3(dir);
       phase = MPR_P2;
     } else if (phase == MPR_P2) {
       s[2] = v4;
-      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; continue; }
+      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; return; }
       for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
       cross3(dir, va, vb);
       normalize3(dir);
@@ -326,7 +339,7 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
       phase = MPR_DISCOVER; guard = 0;
     } else if (phase == MPR_DISCOVER) {  // discoverPortal: find v3
       s[3] = v4;
-      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; continue; }
+      if (ccd_zero(dv) || dv < 0) { phase = MPR_DONE; return; }
       bool cont = false;
       cross3(va, s[1].v, s[3].v);
       T dt = dot3(va, s[0].v);
@@ -337,7 +350,7 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
         if (dt < 0 && !ccd_zero(dt)) { s[1] = s[3]; cont = true; }
       }
       if (cont) {
-        if (++guard > 100) { phase = MPR_DONE; continue; }
+        if (++guard > 100) { phase = MPR_DONE; return; }
         for (int k = 0; k < 3; ++k) { va[k] = s[1].v[k] - s[0].v[k]; vb[k] = s[2].v[k] - s[0].v[k]; }
         cross3(dir, va, vb);
         normalize3(dir);
@@ -348,7 +361,7 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
     } else {  // refinePortal / findPenetr: both test the new point against the portal, then expand it
       const bool reach = portal_reach_tol(s, v4, dir, tolerance);
       if (phase == MPR_REFINE) {
-        if (!(ccd_zero(dv) || dv > 0) || reach) { phase = MPR_DONE; continue; }
+        if (!(ccd_zero(dv) || dv > 0) || reach) { phase = MPR_DONE; return; }
       } else if (reach || guard > iterations) {
         T d2 = point_tri_dist2(s[1].v, s[2].v, s[3].v, pdir);
         depth = dx_sqrt(d2);
@@ -375,11 +388,11 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
           T pv = b[0] * s[0].v[k] + b[1] * s[1].v[k] + b[2] * s[2].v[k] + b[3] * s[3].v[k];
           pos[k] = (p1 - T(0.5) * pv) * inv;
         }
-        hit = true; phase = MPR_DONE; continue;
+        hit = true; phase = MPR_DONE; return;
       }
       expand_portal(s, v4);
       ++guard;
-      if (phase == MPR_REFINE && guard > 100) { phase = MPR_DONE; continue; }
+      if (phase == MPR_REFINE && guard > 100) { phase = MPR_DONE; return; }
       need_portal = true;
     }
     if (need_portal) {
@@ -390,14 +403,31 @@ DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int 
       }
     }
   }
+
+  DEX_DEV void finish(const DevModel<T>& m, const BatchState<T>& st) const {
   T* out = st.stage + (size_t)env * DEX_STAGE_ENV + slot * DEX_CON_STRIDE;
   if (hit && !(pdir[0] == 0 && pdir[1] == 0 && pdir[2] == 0)) {
+    const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV + b1 * DEX_XKIN_BODY;
+    T x1[3], R1[9];
+    for (int k = 0; k < 3; ++k) x1[k] = xk[k];
+    for (int k = 0; k < 9; ++k) R1[k] = xk[7 + k];
+    const T margin = 2 * half_margin;
     T pw[3], nw[3];
     rot_vec(pw, R1, pos);
     rot_vec(nw, R1, pdir);
     pw[0] += x1[0]; pw[1] += x1[1]; pw[2] += x1[2];
     dex_store_contact(out, margin - depth, pw, nw, p);
   } else out[7] = T(-1);
+  }
+};
+
+// plain per-item form (test emulator)
+template <typename T>
+DEX_DEV void dex_narrow_lane(const DevModel<T>& m, const BatchState<T>& st, int env, int wv) {
+  MprLane<T> L;
+  L.begin(m, st, env, wv);
+  while (L.phase != MPR_DONE) L.step(m);
+  L.finish(m, st);
 }
 
 // pose of body b2 in the frame of body b1

@@ -86,7 +86,7 @@ struct BatchState {
   T* stage;                       // [nenv][DEX_MAXSLOT][8] contact staging slots of K1a / K1b (pair < 0 = no contact)
   int* nslot;                     // [nenv] staging slots in use
   int* work;                      // [work_cap][2] global narrowphase work list: env, slot << 24 | pair
-  int* nwork;                     // [1] number of work items (zeroed by K0 every mj_step)
+  int* nwork;                     // [2] number of work items, fetch cursor of K1b (both zeroed by K0 every mj_step)
   int work_cap;
   T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
 };

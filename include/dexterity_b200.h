@@ -133,7 +133,7 @@ enum DexTaskFieldId {
   DEX_FIELD_TREE = 30,         /* real [nenv][8][32] scratch: cdof (rows 0-5), qfrc_smooth (row 6), tree reference points (row 7) */
   DEX_FIELD_STAGE = 31,        /* real [nenv][64][8] scratch: contact staging slots of the collision kernels               */
   DEX_FIELD_NSLOT = 17,        /* i32  [nenv]        scratch: staging slots in use                                        */
-  DEX_FIELD_WORK = 23          /* i32  [1 + 2*cap]   scratch: narrowphase work list: word 0 = item count, then (env, slot<<24|pair)
+  DEX_FIELD_WORK = 23          /* i32  [2 + 2*cap]   scratch: narrowphase work list: item count, fetch cursor, then (env, slot<<24|pair)
                                   pairs; bind with row_stride = cap (the capacity in items, >= nenv * 8 recommended)     */
 };
 

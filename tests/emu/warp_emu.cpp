@@ -126,11 +126,11 @@ struct EmuModel {
 // compaction (warp).  The work list is private to the calling worker thread.
 template <typename T>
 static void emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
-  std::vector<int> work(1 + 2 * DEX_MAXSLOT, 0);
+  std::vector<int> work(2 + 2 * DEX_MAXSLOT, 0);
   BatchState<T> sl = st;
-  sl.nwork = work.data(); sl.work = work.data() + 1; sl.work_cap = DEX_MAXSLOT;
+  sl.nwork = work.data(); sl.work = work.data() + 2; sl.work_cap = DEX_MAXSLOT;
   dex_emu::run_warp([&]() { dex_collide_env<T>(m, sl, env, smem); });
-  for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[1 + 2 * i], work[2 + 2 * i]);  // K1b is thread-per-item
+  for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[2 + 2 * i], work[3 + 2 * i]);  // K1b is thread-per-item
   dex_emu::run_warp([&]() { dex_compact_env<T>(m, sl, env); });
 }
 
