@@ -51,6 +51,7 @@ def lib() -> ctypes.CDLL:
         L.dex_launch_count.restype = ctypes.c_int64
         L.dex_launch_count.argtypes = [ctypes.c_void_p]
         L.dex_capacity.argtypes = [ctypes.c_int]
+        L.dex_set_chunks.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -125,6 +126,7 @@ class PhysicsBatch:
         work = z(2 + 2 * cap, dt=torch.int32)
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
+        self.set_chunks(int(os.environ.get("DEX_CHUNKS", "1")))
         # public views with the model's true widths
         self.qpos = self._store["QPOS"][:, :c.nq]
         self.qvel = self._store["QVEL"][:, :c.nv]
@@ -158,6 +160,10 @@ class PhysicsBatch:
     @staticmethod
     def _stream() -> ctypes.c_void_p:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def set_chunks(self, nchunk: int) -> None:
+        """Env chunks that run as independent kernel pipelines on library-owned streams (1..4)."""
+        _check(lib().dex_set_chunks(self._ptr, int(nchunk)))
 
     def step(self, nsub: int = 1) -> None:
         """nsub x mj_step (collision, constraint solve, Euler integration)."""

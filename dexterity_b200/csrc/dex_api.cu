@@ -40,8 +40,8 @@ constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps spread over all SMs
 template <typename T>
 __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {
-  const int env = blockIdx.x * kTreeBlock + threadIdx.x;
-  if (env == 0) { st.nwork[0] = 0; st.nwork[1] = 0; }  // this mj_step's narrowphase work list: item count, fetch cursor
+  const int env = st.env0 + blockIdx.x * kTreeBlock + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; }  // this mj_step's work list: item count, fetch cursor
   if (env >= st.nenv) return;
   dex_tree_env<T>(m, st, env);
 }
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevModel<T> m, BatchSta
 
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_compact(DevModel<T> m, BatchState<T> st) {
-  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int env = st.env0 + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (env >= st.nenv) return;
   dex_compact_env<T>(m, st, env);
 }
@@ -89,7 +89,7 @@ template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, DEX_K1_MINB) k_collide(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * kWarpsPerBlock + warp;
+  const int env = st.env0 + blockIdx.x * kWarpsPerBlock + warp;
   if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K1_SMEM_T;
   dex_collide_env<T>(m, st, env, smem);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, DEX_K2_MINB) k_dynamics(D
                                                                    int integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * kWarpsPerBlock + warp;
+  const int env = st.env0 + blockIdx.x * kWarpsPerBlock + warp;
   if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
@@ -181,6 +181,8 @@ struct DeviceArrays {
 
 }  // namespace
 
+#define DEX_MAXCHUNK 4
+
 struct DexModel {
   int device = 0;
   HostModel host;
@@ -197,6 +199,10 @@ struct DexBatch {
   int64_t stride[DEX_FIELD_COUNT];
   int64_t launches = 0;
   bool attrs_set = false;
+  // env chunks run as independent pipelines on library-owned streams (forked from / joined to the caller's)
+  int nchunk = 1;
+  cudaStream_t cs[DEX_MAXCHUNK] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[DEX_MAXCHUNK] = {nullptr, nullptr, nullptr, nullptr};
   DexTaskParams task;
   bool task_set = false;
   // optional per-kernel-class timing (cudaEvent pairs recorded on the launching stream)
@@ -242,6 +248,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   for (int f : req_col) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   if (need_dyn) for (int f : req_dyn) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required tensor not bound: field " + std::to_string(f));
   st.nenv = b->nenv;
+  st.env0 = 0;
   st.qpos = (T*)b->ptr[DEX_FIELD_QPOS]; st.qpos_stride = (int)b->stride[DEX_FIELD_QPOS];
   st.qvel = (T*)b->ptr[DEX_FIELD_QVEL]; st.qvel_stride = (int)b->stride[DEX_FIELD_QVEL];
   st.ctrl = (T*)b->ptr[DEX_FIELD_CTRL]; st.ctrl_stride = (int)b->stride[DEX_FIELD_CTRL];
@@ -271,33 +278,79 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
 }
 
 template <typename T>
+int set_attrs(DexBatch* b) {
+  if (b->attrs_set) return DEX_OK;
+  DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T))));
+  // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
+  DEX_CUDA(cudaFuncSetAttribute(k_tree<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  DEX_CUDA(cudaFuncSetAttribute(k_narrow<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  b->attrs_set = true;
+  return DEX_OK;
+}
+
+// nsub x (K0 tree, K1a broadphase, K1b narrowphase, K1c compaction, K2 solve) for every env.  With
+// nchunk > 1 the env range is cut into contiguous chunks, each an independent pipeline on its own
+// stream: the kernels are latency-bound at 20 % occupancy, so different stages of different chunks fill
+// each other's idle issue slots and kernel tails.  Every chunk owns a slice of the work list.
+template <typename T>
+int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const DynDebug<T>& dbg, int nsub, bool collide,
+                   bool dynamics, int integrate, cudaStream_t s) {
+  int rc = set_attrs<T>(b);
+  if (rc) return rc;
+  const size_t smem1 = (size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T);
+  const size_t smem2 = (size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T);
+  int nchunk = b->nchunk;
+  if (b->nenv < 1024 * nchunk) nchunk = 1;
+  if (st.work_cap / nchunk < 64) nchunk = 1;
+  if (nchunk > 1) {
+    if (!b->ev_fork) {
+      DEX_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+      for (int c = 0; c < DEX_MAXCHUNK; ++c) {
+        DEX_CUDA(cudaStreamCreateWithFlags(&b->cs[c], cudaStreamNonBlocking));
+        DEX_CUDA(cudaEventCreateWithFlags(&b->ev_join[c], cudaEventDisableTiming));
+      }
+    }
+    DEX_CUDA(cudaEventRecord(b->ev_fork, s));
+  }
+  int* const work_base = st.nwork;
+  const int cap_total = st.work_cap;
+  const int cap_c = (cap_total - 2 * (nchunk - 1)) / nchunk;  // items per chunk slice (each slice has its own 2-word header)
+  for (int c = 0; c < nchunk; ++c) {
+    cudaStream_t cs = s;
+    if (nchunk > 1) { cs = b->cs[c]; DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_fork, 0)); }
+    st.env0 = (int)((long long)b->nenv * c / nchunk);
+    st.nenv = (int)((long long)b->nenv * (c + 1) / nchunk);
+    st.nwork = work_base + (size_t)c * (2 + 2 * (size_t)cap_c);
+    st.work = st.nwork + 2;
+    st.work_cap = cap_c;
+    const int n = st.nenv - st.env0;
+    const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int tgrid = (n + kTreeBlock - 1) / kTreeBlock;
+    const int ngrid = narrow_grid(n);
+    for (int i = 0; i < nsub; ++i) {
+      { ProfScope ps(b, 4, cs); k_tree<T><<<tgrid, kTreeBlock, 0, cs>>>(m, st); b->launches++; }
+      if (collide) {
+        { ProfScope ps(b, 1, cs); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, cs>>>(m, st); b->launches++; }
+        { ProfScope ps(b, 5, cs); k_narrow<T><<<ngrid, kNarrowBlock, 0, cs>>>(m, st); b->launches++; }
+        { ProfScope ps(b, 6, cs); k_compact<T><<<grid, kWarpsPerBlock * 32, 0, cs>>>(m, st); b->launches++; }
+      }
+      if (dynamics) { ProfScope ps(b, 2, cs); k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, cs>>>(m, st, dbg, integrate); b->launches++; }
+    }
+    if (nchunk > 1) { DEX_CUDA(cudaEventRecord(b->ev_join[c], cs)); DEX_CUDA(cudaStreamWaitEvent(s, b->ev_join[c], 0)); }
+  }
+  DEX_CUDA(cudaGetLastError());
+  return DEX_OK;
+}
+
+template <typename T>
 int run(DexBatch* b, const DevModel<T>& m, int nsub, bool collide, bool dynamics, int integrate, cudaStream_t s) {
   BatchState<T> st;
   DynDebug<T> dbg;
   int rc = make_state<T>(b, st, dbg, dynamics);
   if (rc) return rc;
   DEX_CUDA(cudaSetDevice(b->model->device));
-  const size_t smem1 = (size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T);
-  const size_t smem2 = (size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T);
-  if (!b->attrs_set) {
-    DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    b->attrs_set = true;
-  }
-  const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int tgrid = (b->nenv + kTreeBlock - 1) / kTreeBlock;
-  const int ngrid = narrow_grid(b->nenv);
-  for (int i = 0; i < nsub; ++i) {
-    { ProfScope ps(b, 4, s); k_tree<T><<<tgrid, kTreeBlock, 0, s>>>(m, st); b->launches++; }
-    if (collide) {
-      { ProfScope ps(b, 1, s); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, s>>>(m, st); b->launches++; }
-      { ProfScope ps(b, 5, s); k_narrow<T><<<ngrid, kNarrowBlock, 0, s>>>(m, st); b->launches++; }
-      { ProfScope ps(b, 6, s); k_compact<T><<<grid, kWarpsPerBlock * 32, 0, s>>>(m, st); b->launches++; }
-    }
-    if (dynamics) { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, s>>>(m, st, dbg, integrate); b->launches++; }
-  }
-  DEX_CUDA(cudaGetLastError());
-  return DEX_OK;
+  return launch_physics<T>(b, m, st, dbg, nsub, collide, dynamics, integrate, s);
 }
 
 template <typename T>
@@ -318,27 +371,13 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
   ts.reset_mask = (const unsigned char*)b->ptr[DEX_FIELD_RESET_MASK];
   ts.stats = (double*)b->ptr[DEX_FIELD_EPISODE_STATS];
   DEX_CUDA(cudaSetDevice(b->model->device));
-  const size_t smem1 = (size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T);
-  const size_t smem2 = (size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T);
   const size_t smem3 = (size_t)kWarpsPerBlock * DEX_K3_SMEM_T * sizeof(T);
-  if (!b->attrs_set) {
-    DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    b->attrs_set = true;
-  }
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int block = kWarpsPerBlock * 32;
   if (phases & 1) { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
   if ((phases & 2) && !force_reset) {
-    const int tgrid = (b->nenv + kTreeBlock - 1) / kTreeBlock;
-    const int ngrid = narrow_grid(b->nenv);
-    for (int i = 0; i < nsub; ++i) {
-      { ProfScope ps(b, 4, s); k_tree<T><<<tgrid, kTreeBlock, 0, s>>>(m, st); b->launches++; }
-      { ProfScope ps(b, 1, s); k_collide<T><<<grid, block, smem1, s>>>(m, st); b->launches++; }
-      { ProfScope ps(b, 5, s); k_narrow<T><<<ngrid, kNarrowBlock, 0, s>>>(m, st); b->launches++; }
-      { ProfScope ps(b, 6, s); k_compact<T><<<grid, block, 0, s>>>(m, st); b->launches++; }
-      { ProfScope ps(b, 2, s); k_dynamics<T><<<grid, block, smem2, s>>>(m, st, dbg, 1); b->launches++; }
-    }
+    rc = launch_physics<T>(b, m, st, dbg, nsub, true, true, 1, s);
+    if (rc) return rc;
   }
   if (phases & 4) { ProfScope ps(b, 3, s); k_task_post<T><<<grid, block, smem3, s>>>(m, st, ts, b->task); b->launches++; }
   DEX_CUDA(cudaGetLastError());
@@ -418,7 +457,21 @@ int dex_batch_create(DexModel* model, int num_envs, int dtype, DexBatch** out) {
   return DEX_OK;
 }
 
-void dex_batch_destroy(DexBatch* b) { delete b; }
+void dex_batch_destroy(DexBatch* b) {
+  if (!b) return;
+  if (b->ev_fork) {
+    cudaSetDevice(b->model->device);
+    cudaEventDestroy(b->ev_fork);
+    for (int c = 0; c < DEX_MAXCHUNK; ++c) { cudaStreamDestroy(b->cs[c]); cudaEventDestroy(b->ev_join[c]); }
+  }
+  delete b;
+}
+
+int dex_set_chunks(DexBatch* b, int nchunk) {
+  if (!b || nchunk < 1 || nchunk > DEX_MAXCHUNK) return fail(DEX_E_ARG, "nchunk must be in 1..4");
+  b->nchunk = nchunk;
+  return DEX_OK;
+}
 
 int dex_bind(DexBatch* b, int field, void* dev_ptr, int64_t row_stride) {
   if (!b || field < 0 || field >= DEX_FIELD_COUNT) return fail(DEX_E_ARG, "bad field");

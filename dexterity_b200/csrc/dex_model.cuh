@@ -68,7 +68,8 @@ struct DevModel {
 // Row-major [num_envs][stride]; strides are in elements.
 template <typename T>
 struct BatchState {
-  int nenv;
+  int nenv;                       // one past the last env of this launch
+  int env0;                       // first env of this launch (env chunks run as independent pipelines)
   T* qpos; int qpos_stride;
   T* qvel; int qvel_stride;
   T* ctrl; int ctrl_stride;

@@ -84,6 +84,11 @@ int dex_mj_forward(DexBatch* batch, void* stream);
 /* Collision only (position stage): contacts + ncon. */
 int dex_mj_collide(DexBatch* batch, void* stream);
 
+/* Cuts the env range into `nchunk` (1..4) contiguous chunks that run as independent kernel pipelines on
+ * library-owned streams, forked from and joined to the caller's stream inside every call (no host
+ * synchronisation; results are identical for every nchunk).  Default 1. */
+int dex_set_chunks(DexBatch* batch, int nchunk);
+
 /* Number of this library's kernels launched since batch creation (bench `gpu_launches`). */
 int64_t dex_launch_count(const DexBatch* batch);
 

@@ -174,13 +174,13 @@ int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, vo
                   int nthreads) {
   EmuModel* m = (EmuModel*)mp;
   if (dtype == 0) {
-    BatchState<float> st = {nenv, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
+    BatchState<float> st = {nenv, 0, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
                             (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc, (float*)mscr,
                             (float*)xkin, (float*)stage, nslot, nullptr, nullptr, 0, (float*)tree};
     DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
     emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   } else {
-    BatchState<double> st = {nenv, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
+    BatchState<double> st = {nenv, 0, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
                              (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc, (double*)mscr,
                              (double*)xkin, (double*)stage, nslot, nullptr, nullptr, 0, (double*)tree};
     DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
@@ -196,7 +196,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
   EmuModel* m = (EmuModel*)mp;
   auto go = [&](auto tag, const auto& dev) {
     using T = decltype(tag);
-    BatchState<T> st = {nenv, (T*)f[DEX_FIELD_QPOS], (int)stride[DEX_FIELD_QPOS], (T*)f[DEX_FIELD_QVEL], (int)stride[DEX_FIELD_QVEL],
+    BatchState<T> st = {nenv, 0, (T*)f[DEX_FIELD_QPOS], (int)stride[DEX_FIELD_QPOS], (T*)f[DEX_FIELD_QVEL], (int)stride[DEX_FIELD_QVEL],
                         (T*)f[DEX_FIELD_CTRL], (int)stride[DEX_FIELD_CTRL], (T*)f[DEX_FIELD_QACC_WARMSTART],
                         (int)stride[DEX_FIELD_QACC_WARMSTART], (T*)f[DEX_FIELD_TIME], (unsigned*)f[DEX_FIELD_STATUS],
                         (T*)f[DEX_FIELD_CONTACT], (int*)f[DEX_FIELD_NCON], (int*)f[DEX_FIELD_NITER],
