@@ -49,6 +49,17 @@ __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T
 #ifndef DEX_NARROW_BLOCK
 #define DEX_NARROW_BLOCK 64
 #endif
+constexpr int kTreeWarps = 4;  // K0, 8-lanes-per-env form: 4 envs per warp, 16 per CTA
+template <typename T>
+__global__ void __launch_bounds__(kTreeWarps * 32) k_tree8(DevModel<T> m, BatchState<T> st) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; }
+  const int env_base = st.env0 + (blockIdx.x * kTreeWarps + warp) * DEX_K0_ENVS;
+  if (env_base >= st.nenv) return;
+  dex_tree_warp<T>(m, st, env_base, reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K0_SMEM_T);
+}
+
 constexpr int kNarrowBlock = DEX_NARROW_BLOCK;
 // Persistent lanes: every thread runs one pair's MPR state machine and, as soon as that pair is done,
 // takes the next item off the global list (warp-aggregated atomic on the cursor), so the 32 lanes of a
@@ -143,7 +154,7 @@ struct DeviceArrays {
   int upload(const HostModel& h) {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
-    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
+    dev.k0_rounds = h.k0_rounds; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep;
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
@@ -200,6 +211,7 @@ struct DexBatch {
   int64_t launches = 0;
   bool attrs_set = false;
   // env chunks run as independent pipelines on library-owned streams (forked from / joined to the caller's)
+  bool tree_scalar = false;  // force the thread-per-env tree kernel (tests / tuning)
   int nchunk = 1;
   cudaStream_t cs[DEX_MAXCHUNK] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[DEX_MAXCHUNK] = {nullptr, nullptr, nullptr, nullptr};
@@ -284,6 +296,7 @@ int set_attrs(DexBatch* b) {
   DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T))));
   // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
   DEX_CUDA(cudaFuncSetAttribute(k_tree<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  DEX_CUDA(cudaFuncSetAttribute(k_tree8<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T))));
   DEX_CUDA(cudaFuncSetAttribute(k_narrow<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   b->attrs_set = true;
   return DEX_OK;
@@ -327,9 +340,16 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
     const int n = st.nenv - st.env0;
     const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int tgrid = (n + kTreeBlock - 1) / kTreeBlock;
+    const int t8grid = (n + kTreeWarps * DEX_K0_ENVS - 1) / (kTreeWarps * DEX_K0_ENVS);
+    const size_t smem0 = (size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T);
     const int ngrid = narrow_grid(n);
     for (int i = 0; i < nsub; ++i) {
-      { ProfScope ps(b, 4, cs); k_tree<T><<<tgrid, kTreeBlock, 0, cs>>>(m, st); b->launches++; }
+      {
+        ProfScope ps(b, 4, cs);
+        if (m.k0_rounds > 0 && !b->tree_scalar) k_tree8<T><<<t8grid, kTreeWarps * 32, smem0, cs>>>(m, st);
+        else k_tree<T><<<tgrid, kTreeBlock, 0, cs>>>(m, st);
+        b->launches++;
+      }
       if (collide) {
         { ProfScope ps(b, 1, cs); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, cs>>>(m, st); b->launches++; }
         { ProfScope ps(b, 5, cs); k_narrow<T><<<ngrid, kNarrowBlock, 0, cs>>>(m, st); b->launches++; }
@@ -465,6 +485,12 @@ void dex_batch_destroy(DexBatch* b) {
     for (int c = 0; c < DEX_MAXCHUNK; ++c) { cudaStreamDestroy(b->cs[c]); cudaEventDestroy(b->ev_join[c]); }
   }
   delete b;
+}
+
+int dex_set_tree_kernel(DexBatch* b, int scalar) {
+  if (!b) return fail(DEX_E_ARG, "null batch");
+  b->tree_scalar = scalar != 0;
+  return DEX_OK;
 }
 
 int dex_set_chunks(DexBatch* b, int nchunk) {

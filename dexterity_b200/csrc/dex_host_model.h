@@ -20,6 +20,7 @@
 struct HostModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
+  int k0_rounds;
   double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
@@ -100,6 +101,27 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     for (int b = 1; b < nb; ++b) {
       if (open[M.body_depth[b] - 1] != M.body_parent[b]) return "bodies are not in depth-first pre-order";
       open[M.body_depth[b]] = b;
+    }
+  }
+  {  // schedule of the 8-lanes-per-env tree kernel: round = tree depth, a lane follows a chain of first children
+    const int G = 8;
+    M.k0_rounds = M.maxdepth;
+    M.k0_body.assign(std::max(1, M.maxdepth * G), -1);
+    M.k0_src.assign(std::max(1, M.maxdepth * G), -1);
+    std::vector<int> lane_of(nb, -1);
+    for (int d = 1; d <= M.maxdepth && M.k0_rounds; ++d) {
+      int* rb = &M.k0_body[(d - 1) * G];
+      int* rs = &M.k0_src[(d - 1) * G];
+      for (int pass = 0; pass < 2 && M.k0_rounds; ++pass)   // pass 0: first children keep the parent's lane
+        for (int b = 1; b < nb; ++b) {
+          if (M.body_depth[b] != d || lane_of[b] >= 0) continue;
+          const int p = M.body_parent[b];
+          int l = -1;
+          if (pass == 0) { if (p > 0 && rb[lane_of[p]] < 0) l = lane_of[p]; else continue; }
+          else for (int k = 0; k < G; ++k) if (rb[k] < 0) { l = k; break; }
+          if (l < 0) { M.k0_rounds = 0; break; }   // level wider than 8 bodies
+          rb[l] = b; rs[l] = p > 0 ? lane_of[p] : -1; lane_of[b] = l;
+        }
     }
   }
   std::vector<int> broot = I(DEXF_BODY_ROOT);

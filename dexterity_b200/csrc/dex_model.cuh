@@ -31,7 +31,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(I, body_dofnum) X(I, body_tree) X(I, body_dofmask) X(I, body_weld)                     \
   X(R, body_pos) X(R, body_quat) X(R, body_ipos) X(R, body_mass) X(R, body_inertia6)       \
   X(R, body_xfrc) X(R, body_invweight0) X(R, body_bsphere) X(R, body_pack)                                 \
-  X(I, tree_refbody)                                                                       \
+  X(I, tree_refbody) X(I, k0_body) X(I, k0_src)                                            \
   X(I, jnt_type) X(I, jnt_body) X(I, jnt_qposadr) X(I, jnt_dofadr) X(I, jnt_limited)       \
   X(R, jnt_pos) X(R, jnt_axis) X(R, jnt_range) X(R, jnt_margin) X(R, jnt_solref)           \
   X(R, jnt_solimp) X(R, qpos0)                                                             \
@@ -54,6 +54,7 @@ template <typename T>
 struct DevModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
+  int k0_rounds;  // rounds of the 8-lanes-per-env tree kernel schedule (0 = model does not fit: thread-per-env kernel)
   T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) const int* name;
 #define DEX_X_R(name) const T* name;

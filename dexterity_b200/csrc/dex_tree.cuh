@@ -280,4 +280,217 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
   for (int k = 0; k < 16; ++k) tree[DEX_TREE_ROW_REF * 32 + k] = ref[k];
 }
 
+// ------------------------------------------------------------------------------------------
+// K0, second form: EIGHT LANES per env (four envs per warp), one lane per kinematic chain.
+// The thread-per-env walk above is the most instruction-efficient form, but at 16 384 envs it leaves a
+// B200 with 3.5 warps per SM and 3 KB of local state per thread, i.e. bound by L2 latency (r01g profile:
+// IPC 0.25, 0.27 ms per launch).  Here the host assigns every body to a (round, lane) slot, one round per
+// tree depth; a lane keeps the pose / velocity / acceleration of its current body in registers, a child
+// fetches its parent's state with shuffles from the parent's lane, and the own inertia / force of every
+// body lives in shared memory where children add their subtree totals on the way back up.  Same
+// arithmetic as dex_tree_env, body by body.  Models whose widest tree level exceeds 8 bodies keep the
+// thread-per-env kernel (DevModel::k0_rounds == 0).
+// ------------------------------------------------------------------------------------------
+#define DEX_K0_G 8
+#define DEX_K0_ENVS 4
+#define DEX_K0_OFF_OWN 0                                   // [body][16]: crb(10) cfrc(6)
+#define DEX_K0_OFF_CDOF (DEX_K0_OFF_OWN + DEX_MAXBODY * 16)  // [dof][6]
+#define DEX_K0_OFF_ACT (DEX_K0_OFF_CDOF + DEX_MAXDOF * 6)
+#define DEX_K0_OFF_REF (DEX_K0_OFF_ACT + DEX_MAXDOF)
+#define DEX_K0_ENV_T (DEX_K0_OFF_REF + 16)
+#define DEX_K0_SMEM_T (DEX_K0_ENVS * DEX_K0_ENV_T)
+
+template <typename T>
+DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int env_base, T* smem) {
+  const int lane = dex_lane(), gl = lane & (DEX_K0_G - 1), ge = lane / DEX_K0_G;
+  const int env = env_base + ge;
+  const bool live = env < st.nenv && !(st.skip && st.skip[env]);   // dead groups compute on a valid env and write nothing
+  const int envr = env < st.nenv ? env : st.nenv - 1;
+  T* sm = smem + ge * DEX_K0_ENV_T;
+  T* own = sm + DEX_K0_OFF_OWN;
+  T* cdofs = sm + DEX_K0_OFF_CDOF;
+  T (*cdof)[6] = reinterpret_cast<T (*)[6]>(cdofs);
+  T* act = sm + DEX_K0_OFF_ACT;
+  T* ref = sm + DEX_K0_OFF_REF;
+  const T* qpos = st.qpos + (size_t)envr * st.qpos_stride;
+  const T* qvel = st.qvel + (size_t)envr * st.qvel_stride;
+  T* xkin = st.xkin + (size_t)envr * DEX_XKIN_ENV;
+  T* tree = st.tree + (size_t)envr * DEX_TREE_ENV;
+  T* M = st.mscr + (size_t)envr * DEX_MG_ENV;
+
+  for (int i = gl; i < DEX_MAXDOF; i += DEX_K0_G) act[i] = 0;
+  for (int i = gl; i < 16; i += DEX_K0_G) ref[i] = 0;
+  dex_syncwarp();
+  // ---- actuation (lane = actuator)
+  for (int a = gl; a < m.nu; a += DEX_K0_G) {
+    const int tid = dex_ldg(m.act_trnid + a);
+    const T gear = dex_ldg(m.act_gear + a);
+    const bool joint = dex_ldg(m.act_trntype + a) == 0;
+    T length = 0, vel = 0;
+    if (joint) {
+      length = qpos[dex_ldg(m.jnt_qposadr + tid)];
+      vel = qvel[dex_ldg(m.jnt_dofadr + tid)];
+    } else {
+      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
+      for (int w = wa; w < wa + wn; ++w) {
+        const int j = dex_ldg(m.wrap_jnt + w);
+        const T c = dex_ldg(m.wrap_coef + w);
+        length += c * qpos[dex_ldg(m.jnt_qposadr + j)];
+        vel += c * qvel[dex_ldg(m.jnt_dofadr + j)];
+      }
+    }
+    length *= gear; vel *= gear;
+    T c = st.ctrl[(size_t)envr * st.ctrl_stride + a];
+    if (dex_ldg(m.act_ctrllimited + a)) c = dx_clamp(c, dex_ldg(m.act_ctrlrange + 2 * a), dex_ldg(m.act_ctrlrange + 2 * a + 1));
+    T f = dex_ldg(m.act_gainprm + 3 * a) * c + dex_ldg(m.act_biasprm + 3 * a) + dex_ldg(m.act_biasprm + 3 * a + 1) * length +
+          dex_ldg(m.act_biasprm + 3 * a + 2) * vel;
+    if (dex_ldg(m.act_forcelimited + a)) f = dx_clamp(f, dex_ldg(m.act_forcerange + 2 * a), dex_ldg(m.act_forcerange + 2 * a + 1));
+    if (joint) dex_atomic_add(act + dex_ldg(m.jnt_dofadr + tid), gear * f);
+    else {
+      const int wa = dex_ldg(m.ten_adr + tid), wn = dex_ldg(m.ten_num + tid);
+      for (int w = wa; w < wa + wn; ++w)
+        dex_atomic_add(act + dex_ldg(m.jnt_dofadr + dex_ldg(m.wrap_jnt + w)), gear * dex_ldg(m.wrap_coef + w) * f);
+    }
+  }
+  // ---- per-tree reference points (lane = tree): FK along the path world -> reference body
+  for (int t = 1 + gl; t < m.ntree; t += DEX_K0_G) {
+    int path[DEX_MAXDEPTH], n = 0;
+    for (int b = dex_ldg(m.tree_refbody + t); b > 0; b = dex_ldg(m.body_parent + b)) path[n++] = b;
+    T pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = n - 1; i >= 0; --i) {
+      T npos[3], nquat[4], nmat[9];
+      dex_body_fk<T>(m, qpos, path[i], pos, quat, mat, npos, nquat, nmat, nullptr, nullptr);
+      for (int k = 0; k < 3; ++k) pos[k] = npos[k];
+      for (int k = 0; k < 4; ++k) quat[k] = nquat[k];
+      for (int k = 0; k < 9; ++k) mat[k] = nmat[k];
+    }
+    ref[3 * t] = pos[0]; ref[3 * t + 1] = pos[1]; ref[3 * t + 2] = pos[2];
+  }
+  dex_syncwarp();
+  if (live && gl == 0) {  // world body record
+    for (int k = 0; k < 16; ++k) xkin[k] = (k == 3 || k == 7 || k == 11 || k == 15) ? T(1) : T(0);
+  }
+
+  // ---- forward rounds (one per tree depth): lane state = pose / velocity / acceleration of its latest body
+  T pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  T vel[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
+  const int nround = m.k0_rounds;
+  for (int r = 0; r < nround; ++r) {
+    const int b = dex_ldg(m.k0_body + r * DEX_K0_G + gl);
+    const int src = dex_ldg(m.k0_src + r * DEX_K0_G + gl);
+    const int sl = (lane & ~(DEX_K0_G - 1)) | (src < 0 ? gl : src);
+    T ppos[3], pquat[4], pmat[9], v[6], a[6];
+    for (int k = 0; k < 3; ++k) ppos[k] = dex_shfl(pos[k], sl);
+    for (int k = 0; k < 4; ++k) pquat[k] = dex_shfl(quat[k], sl);
+    for (int k = 0; k < 9; ++k) pmat[k] = dex_shfl(mat[k], sl);
+    for (int k = 0; k < 6; ++k) { v[k] = dex_shfl(vel[k], sl); a[k] = dex_shfl(acc[k], sl); }
+    if (src < 0) {  // child of the world body
+      for (int k = 0; k < 3; ++k) ppos[k] = 0;
+      pquat[0] = 1; pquat[1] = pquat[2] = pquat[3] = 0;
+      for (int k = 0; k < 9; ++k) pmat[k] = (k % 4 == 0) ? T(1) : T(0);
+      for (int k = 0; k < 6; ++k) { v[k] = 0; a[k] = 0; }
+      a[3] = -m.gravity[0]; a[4] = -m.gravity[1]; a[5] = -m.gravity[2];
+    }
+    if (b >= 0) {
+      dex_body_fk<T>(m, qpos, b, ppos, pquat, pmat, pos, quat, mat, ref, cdof);
+      if (live) {
+        T* xo = xkin + b * DEX_XKIN_BODY;
+        for (int k = 0; k < 3; ++k) xo[k] = pos[k];
+        for (int k = 0; k < 4; ++k) xo[3 + k] = quat[k];
+        for (int k = 0; k < 9; ++k) xo[7 + k] = mat[k];
+      }
+      // cinert about the tree reference point (mj_comPos)
+      const T* rp = ref + 3 * dex_ldg(m.body_tree + b);
+      const T mass = dex_ldg(m.body_mass + b);
+      const T ip[3] = {dex_ldg(m.body_ipos + 3 * b), dex_ldg(m.body_ipos + 3 * b + 1), dex_ldg(m.body_ipos + 3 * b + 2)};
+      T off[3], c[10];
+      rot_vec(off, mat, ip);
+      off[0] += pos[0] - rp[0]; off[1] += pos[1] - rp[1]; off[2] += pos[2] - rp[2];
+      {
+        const T* I6 = m.body_inertia6 + 6 * b;
+        const T Ib[9] = {dex_ldg(I6), dex_ldg(I6 + 3), dex_ldg(I6 + 4), dex_ldg(I6 + 3), dex_ldg(I6 + 1), dex_ldg(I6 + 5),
+                         dex_ldg(I6 + 4), dex_ldg(I6 + 5), dex_ldg(I6 + 2)};
+        T RI[9];
+        for (int rr = 0; rr < 3; ++rr) for (int cc = 0; cc < 3; ++cc)
+          RI[3 * rr + cc] = mat[3 * rr] * Ib[cc] + mat[3 * rr + 1] * Ib[3 + cc] + mat[3 * rr + 2] * Ib[6 + cc];
+        const T o2 = dot3(off, off);
+        c[0] = RI[0] * mat[0] + RI[1] * mat[1] + RI[2] * mat[2] + mass * (o2 - off[0] * off[0]);
+        c[1] = RI[3] * mat[3] + RI[4] * mat[4] + RI[5] * mat[5] + mass * (o2 - off[1] * off[1]);
+        c[2] = RI[6] * mat[6] + RI[7] * mat[7] + RI[8] * mat[8] + mass * (o2 - off[2] * off[2]);
+        c[3] = RI[0] * mat[3] + RI[1] * mat[4] + RI[2] * mat[5] - mass * off[0] * off[1];
+        c[4] = RI[0] * mat[6] + RI[1] * mat[7] + RI[2] * mat[8] - mass * off[0] * off[2];
+        c[5] = RI[3] * mat[6] + RI[4] * mat[7] + RI[5] * mat[8] - mass * off[1] * off[2];
+        c[6] = mass * off[0]; c[7] = mass * off[1]; c[8] = mass * off[2]; c[9] = mass;
+      }
+      // velocity / acceleration through the body's joints (mj_comVel, mj_rne forward)
+      {
+        const int ja = dex_ldg(m.body_jntadr + b), jn = dex_ldg(m.body_jntnum + b);
+        for (int j = ja; j < ja + jn; ++j) {
+          const int da = dex_ldg(m.jnt_dofadr + j);
+          if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+            for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) v[k] += cdof[da + i][k] * qvel[da + i];
+            T cdd[3][6];
+            for (int i = 0; i < 3; ++i) cross_motion(cdd[i], v, cdof[da + 3 + i]);
+            for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) {
+              v[k] += cdof[da + 3 + i][k] * qvel[da + 3 + i];
+              a[k] += cdd[i][k] * qvel[da + 3 + i];
+            }
+          } else {
+            T cdd[6];
+            cross_motion(cdd, v, cdof[da]);
+            for (int k = 0; k < 6; ++k) { v[k] += cdof[da][k] * qvel[da]; a[k] += cdd[k] * qvel[da]; }
+          }
+        }
+      }
+      for (int k = 0; k < 6; ++k) { vel[k] = v[k]; acc[k] = a[k]; }
+      // own spatial force: I a + v x* (I v) - external force about the reference point
+      {
+        const T* xf = m.body_xfrc + 6 * b;
+        const T f[3] = {dex_ldg(xf), dex_ldg(xf + 1), dex_ldg(xf + 2)};
+        T tq[3], t1[6], t2[6], t3[6];
+        cross3(tq, off, f);
+        mul_inert_vec(t1, c, a);
+        mul_inert_vec(t2, c, v);
+        cross_force(t3, v, t2);
+        T* o = own + b * 16;
+        for (int k = 0; k < 10; ++k) o[k] = c[k];
+        o[10] = -(dex_ldg(xf + 3) + tq[0]) + t1[0] + t3[0];
+        o[11] = -(dex_ldg(xf + 4) + tq[1]) + t1[1] + t3[1];
+        o[12] = -(dex_ldg(xf + 5) + tq[2]) + t1[2] + t3[2];
+        o[13] = -f[0] + t1[3] + t3[3]; o[14] = -f[1] + t1[4] + t3[4]; o[15] = -f[2] + t1[5] + t3[5];
+      }
+    }
+    dex_syncwarp();
+  }
+  // ---- backward rounds: a body's slot holds its subtree totals once all deeper rounds are done
+  for (int r = nround - 1; r >= 0; --r) {
+    const int b = dex_ldg(m.k0_body + r * DEX_K0_G + gl);
+    if (b >= 0) {
+      T tot[16];
+      for (int k = 0; k < 16; ++k) tot[k] = own[b * 16 + k];
+      const int da = dex_ldg(m.body_dofadr + b), dn = dex_ldg(m.body_dofnum + b);
+      for (int i = da; i < da + dn; ++i) {
+        const T* ci = cdof[i];
+        const T bias = ci[0] * tot[10] + ci[1] * tot[11] + ci[2] * tot[12] + ci[3] * tot[13] + ci[4] * tot[14] + ci[5] * tot[15];
+        T buf[6];
+        mul_inert_vec(buf, tot, ci);
+        if (live) {
+          tree[DEX_TREE_ROW_FS * 32 + i] = -dex_ldg(m.dof_damping + i) * qvel[i] - bias + act[i];  // qfrc_smooth
+          for (int k = 0; k < 6; ++k) tree[k * 32 + i] = ci[k];
+        }
+        for (int j = i; j >= 0; j = dex_ldg(m.dof_parent + j)) {
+          const T* cj = cdof[j];
+          T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+          if (j == i) s += dex_ldg(m.dof_armature + i);
+          if (live) { M[i * 32 + j] = s; M[j * 32 + i] = s; }
+        }
+      }
+      const int p = dex_ldg(m.body_parent + b);
+      if (p > 0) for (int k = 0; k < 16; ++k) dex_atomic_add(own + p * 16 + k, tot[k]);
+    }
+    dex_syncwarp();
+  }
+  if (live) for (int k = gl; k < 16; k += DEX_K0_G) tree[DEX_TREE_ROW_REF * 32 + k] = ref[k];
+}
+
 #endif  // DEX_TREE_CUH_

@@ -89,6 +89,10 @@ int dex_mj_collide(DexBatch* batch, void* stream);
  * synchronisation; results are identical for every nchunk).  Default 1. */
 int dex_set_chunks(DexBatch* batch, int nchunk);
 
+/* Chooses the form of the tree kernel K0: 0 (default) = eight lanes per env when the model's tree fits
+ * its schedule, 1 = always one thread per env.  Both compute the same quantities. */
+int dex_set_tree_kernel(DexBatch* batch, int thread_per_env);
+
 /* Number of this library's kernels launched since batch creation (bench `gpu_launches`). */
 int64_t dex_launch_count(const DexBatch* batch);
 

@@ -104,7 +104,7 @@ struct EmuModelT {
   void init(const HostModel& h) {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
-    dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
+    dev.k0_rounds = h.k0_rounds; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
@@ -134,16 +134,28 @@ static void emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, 
   dex_emu::run_warp([&]() { dex_compact_env<T>(m, sl, env); });
 }
 
+// K0 for the envs e0 .. e0+3: the 8-lanes-per-env warp form when the model has a schedule, else one
+// plain call per env (thread-per-env form)
+template <typename T>
+static void emu_tree(const DevModel<T>& m, const BatchState<T>& st, int e0, T* smem) {
+  if (m.k0_rounds > 0 && !getenv("DEX_EMU_TREE_SCALAR")) dex_emu::run_warp([&]() { dex_tree_warp<T>(m, st, e0, smem); });
+  else for (int env = e0; env < std::min(st.nenv, e0 + DEX_K0_ENVS); ++env) dex_tree_env<T>(m, st, env);
+}
+
 template <typename T>
 static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int nsub, int integrate, int do_collide,
                     int do_dynamics, int nthreads) {
   auto work = [&](int lo, int hi) {
-    std::vector<T> smem(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T) + 64);
-    for (int env = lo; env < hi; ++env) {
+    std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K0_SMEM_T) + 64);
+    BatchState<T> sb = st;
+    sb.nenv = hi;   // the 4-env tree warps must not spill into another worker's range
+    for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {
       for (int s = 0; s < nsub; ++s) {
-        dex_tree_env<T>(m, st, env);   // K0 is thread-per-env: a plain call
-        if (do_collide) emu_collide<T>(m, st, env, smem.data());
-        if (do_dynamics) dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem.data(), integrate); });
+        emu_tree<T>(m, sb, e0, smem.data());
+        for (int env = e0; env < std::min(hi, e0 + DEX_K0_ENVS); ++env) {
+          if (do_collide) emu_collide<T>(m, sb, env, smem.data());
+          if (do_dynamics) dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, sb, dbg, env, smem.data(), integrate); });
+        }
       }
     }
   };
@@ -164,6 +176,7 @@ void* emu_model_create(const void* blob, uint64_t nbytes, char* err, int errlen)
 }
 void emu_model_destroy(void* m) { delete (EmuModel*)m; }
 int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
+int emu_k0_rounds(void* m) { return ((EmuModel*)m)->host.k0_rounds; }
 
 // dtype: 0 = float32, 1 = float64.  All arrays are host arrays of that dtype, row-major with the
 // given strides.  dbg_* may be null.
@@ -209,15 +222,20 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
                        (double*)f[DEX_FIELD_EPISODE_STATS]};
     DynDebug<T> dbg = {nullptr, nullptr, nullptr, nullptr, nullptr};
     auto work = [&](int lo, int hi) {
-      std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T) + 64);
-      for (int env = lo; env < hi; ++env) {
-        dex_emu::run_warp([&]() { dex_task_pre_env<T>(dev, st, ts, *p, env, force_reset); });
+      std::vector<T> smem(std::max<int>(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T), DEX_K0_SMEM_T) + 64);
+      BatchState<T> sb = st;
+      sb.nenv = hi;
+      for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {
+        const int e1 = std::min(hi, e0 + DEX_K0_ENVS);
+        for (int env = e0; env < e1; ++env) dex_emu::run_warp([&]() { dex_task_pre_env<T>(dev, sb, ts, *p, env, force_reset); });
         if (!force_reset) for (int s = 0; s < nsub; ++s) {
-          dex_tree_env<T>(dev, st, env);
-          emu_collide<T>(dev, st, env, smem.data());
-          dex_emu::run_warp([&]() { dex_dynamics_env<T>(dev, st, dbg, env, smem.data(), 1); });
+          emu_tree<T>(dev, sb, e0, smem.data());
+          for (int env = e0; env < e1; ++env) {
+            emu_collide<T>(dev, sb, env, smem.data());
+            dex_emu::run_warp([&]() { dex_dynamics_env<T>(dev, sb, dbg, env, smem.data(), 1); });
+          }
         }
-        dex_emu::run_warp([&]() { dex_task_post_env<T>(dev, st, ts, *p, env, smem.data()); });
+        for (int env = e0; env < e1; ++env) dex_emu::run_warp([&]() { dex_task_post_env<T>(dev, sb, ts, *p, env, smem.data()); });
       }
     };
     if (nthreads <= 1) { work(0, nenv); return; }

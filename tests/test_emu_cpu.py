@@ -30,6 +30,17 @@ def test_kernel_bodies_fp64_match_oracle(reorient_model, emu_model, states):
     assert np.abs(out["qpos"] - ref["qpos"]).max() < 1e-10 and np.abs(out["qvel"] - ref["qvel"]).max() < 1e-7
 
 
+def test_tree_kernel_forms_agree(reorient_model, emu_model, states, monkeypatch):
+    """K0 exists as a thread-per-env walk and as an 8-lanes-per-env schedule; both must give the same step."""
+    assert emu_model.lib.emu_k0_rounds(ctypes.c_void_p(emu_model.ptr)) > 0   # the Shadow hand fits the 8-lane schedule
+    a = emu_model.run(states["qpos"], states["qvel"], states["ctrl"], states["warm"], nsub=2, dtype=np.float64, debug=True)
+    monkeypatch.setenv("DEX_EMU_TREE_SCALAR", "1")
+    b = emu_model.run(states["qpos"], states["qvel"], states["ctrl"], states["warm"], nsub=2, dtype=np.float64, debug=True)
+    for k in ("qpos", "qvel", "M", "fs"):
+        assert np.abs(a[k] - b[k]).max() < 1e-10, k
+    assert (a["ncon"] == b["ncon"]).all()
+
+
 def test_kernel_bodies_fp32_match_oracle(reorient_model, emu_model, states):
     ref = statelib.oracle_step(reorient_model, states, nsub=1)
     out = emu_model.run(states["qpos"], states["qvel"], states["ctrl"], states["warm"], nsub=1, dtype=np.float32)
