@@ -178,6 +178,42 @@ void emu_model_destroy(void* m) { delete (EmuModel*)m; }
 int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
 int emu_k0_rounds(void* m) { return ((EmuModel*)m)->host.k0_rounds; }
 
+// Hill-climbing support function of K1b against an exhaustive scan, for every mesh geom and `ndir` random
+// directions (warm-started from the previous direction's vertex, as inside one MPR run).
+// out[0] = supports evaluated, out[1] = a different vertex was returned, out[2] = ... with a smaller support value
+// (must be 0: on a convex hull every local maximum is global), out[3] = largest shortfall of the support value.
+int emu_support_check(void* mp, int ndir, unsigned seed, double* out) {
+  EmuModel* em = (EmuModel*)mp;
+  const DevModel<double>& m = em->d.dev;
+  unsigned s = seed ? seed : 1u;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return (double)(s & 0xffffff) / 0xffffff * 2.0 - 1.0; };
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (int g = 0; g < m.ngeom; ++g) {
+    if (m.geom_type[g] != DEX_GEOM_MESH) continue;
+    LaneGeom<double> G = {m.vert + 4 * m.geom_vertadr[g], m.geom_vertnum[g], DEX_GEOM_MESH, g, m.geom_adjbase[g], -1};
+    double d[3] = {rnd(), rnd(), rnd()};
+    for (int k = 0; k < ndir; ++k) {
+      if (k % 8 == 0) { d[0] = rnd(); d[1] = rnd(); d[2] = rnd(); G.last = -1; }   // fresh direction, cold start
+      else { d[0] += 0.3 * rnd(); d[1] += 0.3 * rnd(); d[2] += 0.3 * rnd(); }    // nearby direction, warm start
+      double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      if (n < 1e-6) continue;
+      const double l[3] = {d[0] / n, d[1] / n, d[2] / n};
+      double got[3];
+      dex_support_lane<double>(m, G, l[0], l[1], l[2], got);
+      int bi = 0; double best = -1e300;
+      for (int i = 0; i < G.n; ++i) {
+        const double t = G.vert[4 * i] * l[0] + G.vert[4 * i + 1] * l[1] + G.vert[4 * i + 2] * l[2];
+        if (t > best) { best = t; bi = i; }
+      }
+      const double tg = got[0] * l[0] + got[1] * l[1] + got[2] * l[2];
+      out[0] += 1;
+      if (got[0] != G.vert[4 * bi] || got[1] != G.vert[4 * bi + 1] || got[2] != G.vert[4 * bi + 2]) out[1] += 1;
+      if (tg < best) { out[2] += 1; out[3] = std::max(out[3], best - tg); }
+    }
+  }
+  return 0;
+}
+
 // dtype: 0 = float32, 1 = float64.  All arrays are host arrays of that dtype, row-major with the
 // given strides.  dbg_* may be null.
 int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, void* qvel, int qvel_stride, void* ctrl,

@@ -41,6 +41,19 @@ def test_tree_kernel_forms_agree(reorient_model, emu_model, states, monkeypatch)
     assert (a["ncon"] == b["ncon"]).all()
 
 
+def test_hill_climbing_support_is_exact(emu_model):
+    """The narrowphase climbs the hull graph instead of scanning every vertex (as MuJoCo's mesh support does).
+    On a convex hull a local maximum is the global one: over all 204 hulls and cold / warm starts the support VALUE
+    must equal the exhaustive maximum; only the vertex may differ, and only on exact ties."""
+    out = (ctypes.c_double * 4)()
+    emu_model.lib.emu_support_check.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
+    emu_model.lib.emu_support_check(ctypes.c_void_p(emu_model.ptr), 400, 12345, out)
+    n, other_vertex, smaller, shortfall = out[0], out[1], out[2], out[3]
+    assert n > 50000
+    assert smaller == 0, f"{smaller} of {n} supports below the exhaustive maximum (largest shortfall {shortfall:.3e})"
+    assert other_vertex == 0
+
+
 def test_kernel_bodies_fp32_match_oracle(reorient_model, emu_model, states):
     ref = statelib.oracle_step(reorient_model, states, nsub=1)
     out = emu_model.run(states["qpos"], states["qvel"], states["ctrl"], states["warm"], nsub=1, dtype=np.float32)

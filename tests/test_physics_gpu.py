@@ -132,6 +132,35 @@ def test_full_size_properties(reorient_model):
     assert torch.equal(outs[0][0][:64], outs[0][0][64:128])
 
 
+def test_kernel_forms_and_env_chunks_agree(setup):
+    """K0 has two forms (eight lanes per env / one thread per env) and the env range can be cut into stream
+    chunks: every combination must give the same 5 mj_steps (bit-identical for the chunks, which only move envs
+    between launches; to rounding for the two tree forms, which order the subtree sums differently)."""
+    from dexterity_b200 import backend
+    compiled, states, ref, model = setup
+    n = 4096
+    idx = np.arange(n) % len(states["qpos"])
+    tiled = {k: v[idx] for k, v in states.items()}
+    L = backend.lib()
+    L.dex_set_tree_kernel.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int]
+    outs = {}
+    for name, scalar, chunks in (("lanes8", 0, 1), ("thread", 1, 1), ("lanes8_4chunks", 0, 4)):
+        b = backend.PhysicsBatch(model, n, torch.float32)
+        backend._check(L.dex_set_tree_kernel(b.ptr, scalar))
+        b.set_chunks(chunks)
+        statelib.upload(b, tiled)
+        b.step(5)
+        torch.cuda.synchronize()
+        assert (b.status & 1).sum().item() == 0
+        outs[name] = (b.qpos.clone(), b.qvel.clone(), b.ncon.clone())
+    assert torch.equal(outs["lanes8"][0], outs["lanes8_4chunks"][0]) and torch.equal(outs["lanes8"][1], outs["lanes8_4chunks"][1])
+    assert torch.equal(outs["lanes8"][2], outs["lanes8_4chunks"][2])
+    same_contacts = outs["lanes8"][2] == outs["thread"][2]
+    assert same_contacts.float().mean() > 0.995
+    dq = (outs["lanes8"][0] - outs["thread"][0]).abs().max(dim=1).values[same_contacts]
+    assert dq.median() < 1e-6 and (dq < 1e-4).float().mean() > 0.98
+
+
 def test_unbound_or_bad_calls_fail_loudly(reorient_model):
     from dexterity_b200 import backend
     model = backend.PhysicsModel(reorient_model, 0)
