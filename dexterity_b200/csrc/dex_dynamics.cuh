@@ -127,7 +127,10 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int* fail) {
     DexVec4<T> o;
     o.x = i > k0 ? l0 : T(0); o.y = i > k0 + 1 ? l1 : T(0); o.z = i > k0 + 2 ? l2 : T(0); o.w = i > k0 + 3 ? l3 : T(0);
     *reinterpret_cast<DexVec4<T>*>(rowi + k0) = o;
-    if ((i >> 2) == kb) { const int r = i & 3; inv_mine = r == 0 ? i0 : (r == 1 ? i1 : (r == 2 ? i2 : i3)); }
+    {  // branch-free: lane i keeps the inverse pivot of its own column
+      const int r = i - k0;
+      inv_mine = r == 0 ? i0 : (r == 1 ? i1 : (r == 2 ? i2 : (r == 3 ? i3 : inv_mine)));
+    }
     dex_syncwarp();
   }
   if (bad) *fail = 1;
@@ -161,18 +164,20 @@ DEX_DEV_NOINLINE T dex_chol_apply(const T* H, int n, T inv_mine, T b) {
 // Fills the warp's Cholesky tile from a symmetric matrix stored with rows of 32 (global scratch):
 // strictly lower part of the leading n x n block, zeros elsewhere; returns this lane's diagonal entry.
 template <typename T>
-DEX_DEV T dex_chol_load(T* H, const T* Mg, int n) {
+DEX_DEV_NOINLINE T dex_chol_load(T* H, const T* Mg, int n) {
   const int lane = dex_lane();
+#pragma unroll 8
   for (int j = 0; j < 32; ++j) H[j * DEX_MSTRIDE + lane] = (lane < j && j < n) ? Mg[j * 32 + lane] : T(0);
   return lane < n ? Mg[lane * 32 + lane] : T(1);
 }
 // y_i = sum_j M[j][i] x_j (M symmetric) with M in the env's global scratch (rows of 32, read coalesced
 // with lane = column) and x in shared memory.
 template <typename T>
-DEX_DEV T dex_matvec(const T* Mg, const T* x, int nv) {
+DEX_DEV_NOINLINE T dex_matvec(const T* Mg, const T* x, int nv) {
   const int i = dex_lane();
   T s0 = 0, s1 = 0;
   int j = 0;
+#pragma unroll 4
   for (; j + 1 < nv; j += 2) { s0 += Mg[j * 32 + i] * x[j]; s1 += Mg[(j + 1) * 32 + i] * x[j + 1]; }
   if (j < nv) s0 += Mg[j * 32 + i] * x[j];
   return i < nv ? s0 + s1 : T(0);
@@ -180,8 +185,9 @@ DEX_DEV T dex_matvec(const T* Mg, const T* x, int nv) {
 // out[t] = Jc[t] . x for the 3*ncon contact-frame Jacobian rows.  Jc is the env's global (L2) scratch,
 // read coalesced with lane = dof; xi is this lane's component of x.
 template <typename T>
-DEX_DEV void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
+DEX_DEV_NOINLINE void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
   const int lane = dex_lane();
+#pragma unroll 1
   for (int t = 0; t < nrows; t += 3) {   // one contact (3 frame rows) per round, reductions interleaved
     T s0 = Jc[t * DEX_JC_ROW + lane] * xi, s1 = Jc[(t + 1) * DEX_JC_ROW + lane] * xi, s2 = Jc[(t + 2) * DEX_JC_ROW + lane] * xi;
     dex_warp_sum3(s0, s1, s2);
