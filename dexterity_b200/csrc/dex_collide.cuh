@@ -195,29 +195,43 @@ DEX_DEV void dex_support_lane(const DevModel<T>& m, LaneGeom<T>& G, T lx, T ly, 
         if (t > best) { best = t; bi = i; }
       }
     } else {
-      if (G.last >= 0) bi = G.last;
-      else {  // start at the hull vertex that is extreme along the dominant axis of the direction
-        const T ax = dx_abs(lx), ay = dx_abs(ly), az = dx_abs(lz);
-        const int k = ax >= ay ? (ax >= az ? (lx < 0 ? 1 : 0) : (lz < 0 ? 5 : 4)) : (ay >= az ? (ly < 0 ? 3 : 2) : (lz < 0 ? 5 : 4));
-        bi = dex_ldg(m.geom_start6 + 6 * G.g + k);
-      }
+      // start: the best of 14 landmark vertices (same work in every lane) and the previous support vertex
       T vx, vy, vz;
-      dex_ldg_xyz(G.vert + 4 * bi, vx, vy, vz);
-      T best = vx * lx + vy * ly + vz * lz;
-      for (int guard = 0; guard < G.n; ++guard) {
-        const int info = dex_ldg(m.vadj + G.adjbase + bi);
-        const int* nb = m.adj + (info >> 8);
-        const int num = info & 255;
-        int nxt = bi;
-        T nv = best;
-        for (int k = 0; k < num; ++k) {
-          const int j = dex_ldg(nb + k);
-          dex_ldg_xyz(G.vert + 4 * j, vx, vy, vz);
-          const T t = vx * lx + vy * ly + vz * lz;
-          if (t > nv || (t == nv && j < nxt)) { nv = t; nxt = j; }   // ties move towards the lowest index
+      T best = -Real<T>::big();
+      const int* lm = m.geom_start16 + 16 * G.g;
+#pragma unroll 7
+      for (int k = 0; k < 14; ++k) {
+        const int j = dex_ldg(lm + k);
+        dex_ldg_xyz(G.vert + 4 * j, vx, vy, vz);
+        const T t = vx * lx + vy * ly + vz * lz;
+        const bool bt = t > best;
+        best = bt ? t : best; bi = bt ? j : bi;
+      }
+      if (G.last >= 0) {
+        dex_ldg_xyz(G.vert + 4 * G.last, vx, vy, vz);
+        const T t = vx * lx + vy * ly + vz * lz;
+        const bool bt = t > best;
+        best = bt ? t : best; bi = bt ? G.last : bi;
+      }
+      // climb: one neighbour per trip (a single flat loop keeps the lanes of a warp together); a move happens
+      // when all neighbours of the current vertex are seen; ties move towards the lowest index
+      int info = dex_ldg(m.vadj + G.adjbase + bi);
+      const int* nb = m.adj + (info >> 8);
+      int num = info & 255, k = 0, nxt = bi;
+      T nv = best;
+      for (int guard = 0; guard < 64 * G.n; ++guard) {
+        if (k == num) {
+          if (nxt == bi) break;
+          bi = nxt; best = nv;
+          info = dex_ldg(m.vadj + G.adjbase + bi);
+          nb = m.adj + (info >> 8); num = info & 255; k = 0;
         }
-        if (nxt == bi) break;
-        bi = nxt; best = nv;
+        const int j = dex_ldg(nb + k);
+        dex_ldg_xyz(G.vert + 4 * j, vx, vy, vz);
+        const T t = vx * lx + vy * ly + vz * lz;
+        const bool bt = (t > nv) | ((t == nv) & (j < nxt));
+        nv = bt ? t : nv; nxt = bt ? j : nxt;
+        ++k;
       }
       G.last = bi;
     }

@@ -227,7 +227,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     }
     // hull graph for the hill-climbing support function of the narrowphase: per MESH vertex one packed
     // word (first neighbour << 8 | neighbour count) into `adj` (neighbour ids local to the mesh), per geom
-    // the mesh-vertex base of its hull and six start vertices (extreme along +-x, +-y, +-z of the body frame)
+    // the mesh-vertex base of its hull and 14 landmark vertices (extreme along the axes and the cube diagonals of the body frame)
     {
       std::vector<int> aadr = I(DEXF_VERT_ADJADR), anum = I(DEXF_VERT_ADJNUM);
       M.adj = I(DEXF_ADJ);
@@ -238,17 +238,21 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
         M.vadj[i] = (aadr[i] << 8) | anum[i];
       }
       M.geom_adjbase.assign(M.ngeom, 0);
-      M.geom_start6.assign(6 * M.ngeom, 0);
+      M.geom_start16.assign(16 * M.ngeom, 0);
+      // 14 landmark directions (6 axes, 8 cube diagonals; the last two slots repeat +x / -x)
+      static const double LD[16][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {1, 1, 1}, {1, 1, -1},
+                                       {1, -1, 1}, {1, -1, -1}, {-1, 1, 1}, {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}, {1, 0, 0}, {-1, 0, 0}};
       for (int g = 0; g < M.ngeom; ++g) {
         if (M.geom_type[g] != DEX_GEOM_MESH) continue;
         M.geom_adjbase[g] = va[g];
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 16; ++k) {
           int best = 0; double bv = -1e300;
           for (int i = 0; i < vn[g]; ++i) {
-            const double t = (k & 1 ? -1.0 : 1.0) * M.vert[4 * (M.geom_vertadr[g] + i) + (k >> 1)];
+            const double* v = &M.vert[4 * (M.geom_vertadr[g] + i)];
+            const double t = LD[k][0] * v[0] + LD[k][1] * v[1] + LD[k][2] * v[2];
             if (t > bv) { bv = t; best = i; }
           }
-          M.geom_start6[6 * g + k] = best;
+          M.geom_start16[16 * g + k] = best;
         }
         for (int i = 0; i < vn[g]; ++i) {
           if (va[g] + i >= (int)aadr.size()) return "hull graph missing for a mesh geom";
