@@ -195,18 +195,22 @@ DEX_DEV void dex_support_lane(const DevModel<T>& m, LaneGeom<T>& G, T lx, T ly, 
         if (t > best) { best = t; bi = i; }
       }
     } else {
-      // start: the best of 14 landmark vertices (same work in every lane) and the previous support vertex
+      // start: the table vertex of the direction's cube-map cell, or the previous support vertex if that is better
       T vx, vy, vz;
-      T best = -Real<T>::big();
-      const int* lm = m.geom_start16 + 16 * G.g;
-#pragma unroll 7
-      for (int k = 0; k < 14; ++k) {
-        const int j = dex_ldg(lm + k);
-        dex_ldg_xyz(G.vert + 4 * j, vx, vy, vz);
-        const T t = vx * lx + vy * ly + vz * lz;
-        const bool bt = t > best;
-        best = bt ? t : best; bi = bt ? j : bi;
+      {
+        const T ax = dx_abs(lx), ay = dx_abs(ly), az = dx_abs(lz);
+        int axis; T dm, du, dv;
+        if (ax >= ay && ax >= az) { axis = 0; dm = lx; du = ly; dv = lz; }
+        else if (ay >= az) { axis = 1; dm = ly; du = lz; dv = lx; }
+        else { axis = 2; dm = lz; du = lx; dv = ly; }
+        const T inv = T(4) / dx_max(dx_abs(dm), Real<T>::minval());
+        int iu = (int)(du * inv + T(4)), iv = (int)(dv * inv + T(4));
+        iu = iu < 0 ? 0 : (iu > 7 ? 7 : iu); iv = iv < 0 ? 0 : (iv > 7 ? 7 : iv);
+        const int c = ((2 * axis + (dm < 0 ? 1 : 0)) << 6) | (iu << 3) | iv;
+        bi = (dex_ldg(m.geom_cubemap + DEX_CUBEMAP_WORDS * G.g + (c >> 1)) >> (16 * (c & 1))) & 0xffff;
       }
+      dex_ldg_xyz(G.vert + 4 * bi, vx, vy, vz);
+      T best = vx * lx + vy * ly + vz * lz;
       if (G.last >= 0) {
         dex_ldg_xyz(G.vert + 4 * G.last, vx, vy, vz);
         const T t = vx * lx + vy * ly + vz * lz;

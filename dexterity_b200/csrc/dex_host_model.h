@@ -227,7 +227,7 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     }
     // hull graph for the hill-climbing support function of the narrowphase: per MESH vertex one packed
     // word (first neighbour << 8 | neighbour count) into `adj` (neighbour ids local to the mesh), per geom
-    // the mesh-vertex base of its hull and 14 landmark vertices (extreme along the axes and the cube diagonals of the body frame)
+    // the mesh-vertex base of its hull and a cube-map table of start vertices
     {
       std::vector<int> aadr = I(DEXF_VERT_ADJADR), anum = I(DEXF_VERT_ADJNUM);
       M.adj = I(DEXF_ADJ);
@@ -238,21 +238,26 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
         M.vadj[i] = (aadr[i] << 8) | anum[i];
       }
       M.geom_adjbase.assign(M.ngeom, 0);
-      M.geom_start16.assign(16 * M.ngeom, 0);
-      // 14 landmark directions (6 axes, 8 cube diagonals; the last two slots repeat +x / -x)
-      static const double LD[16][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {1, 1, 1}, {1, 1, -1},
-                                       {1, -1, 1}, {1, -1, -1}, {-1, 1, 1}, {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}, {1, 0, 0}, {-1, 0, 0}};
+      // start-vertex cube map: 6 faces x 8 x 8 cells, the exhaustive support vertex of each cell-centre direction,
+      // two 16-bit vertex ids per word
+      M.geom_cubemap.assign(DEX_CUBEMAP_WORDS * M.ngeom, 0);
       for (int g = 0; g < M.ngeom; ++g) {
         if (M.geom_type[g] != DEX_GEOM_MESH) continue;
+        if (vn[g] >= 65536) return "hull too large for the 16-bit start-vertex table";
         M.geom_adjbase[g] = va[g];
-        for (int k = 0; k < 16; ++k) {
+        for (int c = 0; c < 384; ++c) {
+          const int face = c >> 6, iu = (c >> 3) & 7, iv = c & 7;
+          const double u = (iu + 0.5) / 4.0 - 1.0, v = (iv + 0.5) / 4.0 - 1.0, sgn = (face & 1) ? -1.0 : 1.0;
+          double d[3];
+          const int ax = face >> 1;
+          d[ax] = sgn; d[(ax + 1) % 3] = u; d[(ax + 2) % 3] = v;
           int best = 0; double bv = -1e300;
           for (int i = 0; i < vn[g]; ++i) {
-            const double* v = &M.vert[4 * (M.geom_vertadr[g] + i)];
-            const double t = LD[k][0] * v[0] + LD[k][1] * v[1] + LD[k][2] * v[2];
+            const double* p = &M.vert[4 * (M.geom_vertadr[g] + i)];
+            const double t = d[0] * p[0] + d[1] * p[1] + d[2] * p[2];
             if (t > bv) { bv = t; best = i; }
           }
-          M.geom_start16[16 * g + k] = best;
+          M.geom_cubemap[DEX_CUBEMAP_WORDS * g + (c >> 1)] |= best << (16 * (c & 1));
         }
         for (int i = 0; i < vn[g]; ++i) {
           if (va[g] + i >= (int)aadr.size()) return "hull graph missing for a mesh geom";

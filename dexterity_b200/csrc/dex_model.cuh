@@ -14,6 +14,7 @@
 #define DEX_MAXCON 24      // per-env contact capacity (overflow sets a status bit)
 #define DEX_MAXCAND 128    // per-env narrowphase candidate capacity
 #define DEX_CON_STRIDE 8   // words per stored contact: dist, pos(3), normal(3), pair id
+#define DEX_CUBEMAP_WORDS 192  // per mesh geom: 6 x 8 x 8 start vertices for the hill-climbing support, 2 per word
 
 // per-env status bits (SURVEY.md §5 failure detection: mirrors upstream PhysicsError handling)
 #define DEX_STATUS_BADQACC 1u
@@ -44,7 +45,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(R, act_gear) X(R, act_gainprm) X(R, act_biasprm) X(R, act_ctrlrange) X(R, act_forcerange) \
   X(I, geom_type) X(I, geom_body) X(I, geom_vertadr) X(I, geom_vertnum)                    \
   X(R, geom_pos) X(R, geom_mat) X(R, geom_size) X(R, geom_rbound) X(R, geom_aabb) X(R, geom_pack) X(R, vert)               \
-  X(I, geom_adjbase) X(I, geom_start16) X(I, vadj) X(I, adj)                                \
+  X(I, geom_adjbase) X(I, geom_cubemap) X(I, vadj) X(I, adj)                                \
   X(I, bp_body1) X(I, bp_body2) X(I, bp_pairadr) X(I, bp_pairnum)                          \
   X(I, pair_geom1) X(I, pair_geom2) X(I, pair_condim) X(R, pair_friction) X(R, pair_solref) \
   X(R, pair_solimp) X(R, pair_margin) X(R, pair_gap)                                       \
