@@ -23,7 +23,9 @@
 
 // per-warp shared-memory footprint of K1, in units of T
 #define DEX_MAXCAND1 384   // capacity of the sphere-test survivor list (pass 1)
-#define DEX_K1_SMEM_T (DEX_MAXBODY * 16 + 48 + DEX_MAXCAND1 + 8 * 4)
+#define DEX_MAXGEOM 256    // world bounding spheres of all geoms are staged in shared memory
+#define DEX_MAXBPL 128     // body pairs that survive the body-level culls
+#define DEX_K1_SMEM_T (DEX_MAXBODY * 16 + DEX_MAXGEOM * 4 + DEX_MAXCAND1 + DEX_MAXBPL + 8 * 4)
 #define DEX_MAXSLOT 64     // staging slots per env (one per convex-convex candidate, four per plane-box pair)
 #define DEX_STAGE_ENV (DEX_MAXSLOT * DEX_CON_STRIDE)
 #define DEX_GPACK 12  // geom_pack: centre(3) rbound | aabb centre(3) aabb half.x | aabb half.y half.z pad pad
@@ -502,7 +504,7 @@ DEX_DEV bool dex_obb_overlap(const Xf<T>& rel, const T* pk1, const T* pk2, T mar
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 body.  smem: [xpos | xquat | xmat | qpos | cand(int)]
+// K1a body.  smem: [xpos | xmat | geom spheres | body spheres | cand(int) | surviving body pairs(int)]
 // ------------------------------------------------------------------------------------------
 
 template <typename T>
@@ -510,10 +512,11 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   if (env >= st.nenv || (st.skip && st.skip[env])) return;  // warp-uniform
   const int lane = dex_lane();
   T* xpos = smem;
-  T* xquat = xpos + DEX_MAXBODY * 3;
-  T* xmat = xquat + DEX_MAXBODY * 4;
-  int* cand = (int*)(xmat + DEX_MAXBODY * 9 + 48);  // DEX_MAXCAND1 ints (fits: sizeof(int) <= sizeof(T))
-  (void)xquat;
+  T* xmat = xpos + DEX_MAXBODY * 3;
+  T* gsph = xmat + DEX_MAXBODY * 9;                 // [DEX_MAXGEOM][4] world bounding spheres: centre, radius
+  T* bsph = gsph + DEX_MAXGEOM * 4;                 // [DEX_MAXBODY][4] world body bounding spheres
+  int* cand = (int*)(bsph + DEX_MAXBODY * 4);       // DEX_MAXCAND1 ints (fits: sizeof(int) <= sizeof(T))
+  int* bpl = cand + DEX_MAXCAND1;                   // DEX_MAXBPL surviving body pairs
   {  // body poses of K0 (dex_tree.cuh): records of 16 = xpos(3) xquat(4) xmat(9)
     const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
     for (int i = lane; i < m.nbody * DEX_XKIN_BODY; i += 32) {
@@ -524,86 +527,112 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     }
   }
   dex_syncwarp();
+  // ---- world-frame bounding spheres of every geom and every body (one lane each)
+  for (int g = lane; g < m.ngeom; g += 32) {
+    const int b = dex_ldg(m.geom_body + g);
+    const T* pk = m.geom_pack + DEX_GPACK * g;
+    T l[3] = {dex_ldg(pk), dex_ldg(pk + 1), dex_ldg(pk + 2)}, c[3];
+    rot_vec(c, xmat + 9 * b, l);
+    gsph[4 * g] = c[0] + xpos[3 * b]; gsph[4 * g + 1] = c[1] + xpos[3 * b + 1]; gsph[4 * g + 2] = c[2] + xpos[3 * b + 2];
+    gsph[4 * g + 3] = dex_ldg(pk + 3);
+  }
+  for (int b = lane; b < m.nbody; b += 32) {
+    const T* bs = m.body_bsphere + 4 * b;
+    T l[3] = {dex_ldg(bs), dex_ldg(bs + 1), dex_ldg(bs + 2)}, c[3];
+    rot_vec(c, xmat + 9 * b, l);
+    bsph[4 * b] = c[0] + xpos[3 * b]; bsph[4 * b + 1] = c[1] + xpos[3 * b + 1]; bsph[4 * b + 2] = c[2] + xpos[3 * b + 2];
+    bsph[4 * b + 3] = dex_ldg(bs + 3);
+  }
+  dex_syncwarp();
 
-  // ---- broadphase
-  int ncand = 0;
+  // ---- broadphase, body pairs: bounding spheres (plane bodies: half-space test) for all pairs, survivors
+  //      compacted, then the bodies' AABBs as oriented boxes on dense lanes (r01d: 273 -> 61 -> 13 pairs)
+  const T slack = T(1e-6);   // world-frame centres carry FP32 rounding: keep every cull conservative
+  int nbp = 0;
   for (int bp0 = 0; bp0 < m.nbodypair; bp0 += 32) {
     const int bp = bp0 + lane;
     bool pass = false;
     if (bp < m.nbodypair) {
       const int b1 = dex_ldg(m.bp_body1 + bp), b2 = dex_ldg(m.bp_body2 + bp);
-      const T r1 = dex_ldg(m.body_bsphere + 4 * b1 + 3), r2 = dex_ldg(m.body_bsphere + 4 * b2 + 3);
-      T c2[3];
-      T l2[3] = {dex_ldg(m.body_bsphere + 4 * b2), dex_ldg(m.body_bsphere + 4 * b2 + 1), dex_ldg(m.body_bsphere + 4 * b2 + 2)};
-      rot_vec(c2, xmat + 9 * b2, l2);
-      c2[0] += xpos[3 * b2]; c2[1] += xpos[3 * b2 + 1]; c2[2] += xpos[3 * b2 + 2];
+      const T r1 = bsph[4 * b1 + 3], r2 = bsph[4 * b2 + 3];
       if (r1 < 0) {  // body 1 owns a plane (planes sort first in a pair): half-space test of body 2's sphere
         const int gp = dex_ldg(m.pair_geom1 + dex_ldg(m.bp_pairadr + bp));
         const T* G = m.geom_mat + 9 * gp;
-        T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3], pl[3], pw[3];
+        T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
         rot_vec(n, xmat + 9 * b1, nl);
-        pl[0] = dex_ldg(m.geom_pack + DEX_GPACK * gp); pl[1] = dex_ldg(m.geom_pack + DEX_GPACK * gp + 1); pl[2] = dex_ldg(m.geom_pack + DEX_GPACK * gp + 2);
-        rot_vec(pw, xmat + 9 * b1, pl);
-        T d[3] = {c2[0] - pw[0] - xpos[3 * b1], c2[1] - pw[1] - xpos[3 * b1 + 1], c2[2] - pw[2] - xpos[3 * b1 + 2]};
-        pass = dot3(d, n) <= r2;
+        T d[3] = {bsph[4 * b2] - gsph[4 * gp], bsph[4 * b2 + 1] - gsph[4 * gp + 1], bsph[4 * b2 + 2] - gsph[4 * gp + 2]};
+        pass = dot3(d, n) <= r2 + slack;
       } else {
-        T c1[3];
-        T l1[3] = {dex_ldg(m.body_bsphere + 4 * b1), dex_ldg(m.body_bsphere + 4 * b1 + 1), dex_ldg(m.body_bsphere + 4 * b1 + 2)};
-        rot_vec(c1, xmat + 9 * b1, l1);
-        T d[3] = {c2[0] - c1[0] - xpos[3 * b1], c2[1] - c1[1] - xpos[3 * b1 + 1], c2[2] - c1[2] - xpos[3 * b1 + 2]};
-        T bound = r1 + r2;
+        T d[3] = {bsph[4 * b2] - bsph[4 * b1], bsph[4 * b2 + 1] - bsph[4 * b1 + 1], bsph[4 * b2 + 2] - bsph[4 * b1 + 2]};
+        const T bound = r1 + r2 + slack;
         pass = dot3(d, d) <= bound * bound;
-        if (pass) {  // tighter: the two bodies' AABBs as oriented boxes (r01d: cuts surviving body pairs 61 -> 13)
-          Xf<T> rb;
-          dex_relative(xpos, xmat, b1, b2, rb);
-          pass = dex_obb_overlap(rb, m.body_pack + DEX_GPACK * b1, m.body_pack + DEX_GPACK * b2, m.max_margin);
-        }
       }
     }
-    unsigned mask = dex_ballot(pass);
-    while (mask) {
-      const int kk = dex_ffs(mask) - 1;
-      mask &= mask - 1;
-      const int bpk = bp0 + kk;
-      const int adr = dex_ldg(m.bp_pairadr + bpk), num = dex_ldg(m.bp_pairnum + bpk);
-      const int b1 = dex_ldg(m.bp_body1 + bpk), b2 = dex_ldg(m.bp_body2 + bpk);
-      Xf<T> rel;
-      dex_relative(xpos, xmat, b1, b2, rel);
-      // pass 1: bounding spheres only (cheap, mostly rejects); survivors are compacted so that the
-      // costlier AABB / OBB tests of pass 2 run on dense lanes (r01d: 900 pairs visited per env, 86
-      // survive the spheres, 7 survive everything)
-      for (int p0 = 0; p0 < num; p0 += 32) {
-        const int p = adr + p0 + lane;
-        bool ok = false;
-        if (p0 + lane < num) {
-          const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
-          const T margin = dex_ldg(m.pair_margin + p);
-          const T* pk1 = m.geom_pack + DEX_GPACK * g1;
-          const T* pk2 = m.geom_pack + DEX_GPACK * g2;
-          T c2l[3] = {dex_ldg(pk2), dex_ldg(pk2 + 1), dex_ldg(pk2 + 2)}, c2[3];
-          rot_vec(c2, rel.R, c2l);
-          c2[0] += rel.t[0]; c2[1] += rel.t[1]; c2[2] += rel.t[2];            // centre of geom 2 in frame 1
-          const T r2 = dex_ldg(pk2 + 3);
-          T d[3] = {c2[0] - dex_ldg(pk1), c2[1] - dex_ldg(pk1 + 1), c2[2] - dex_ldg(pk1 + 2)};
-          if (dex_ldg(m.geom_type + g1) == DEX_GEOM_PLANE) {
-            const T* G = m.geom_mat + 9 * g1;
-            T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)};
-            ok = dot3(d, nl) <= margin + r2;
-          } else {
-            const T bound = margin + dex_ldg(pk1 + 3) + r2;
-            ok = dot3(d, d) <= bound * bound;
-          }
-        }
-        const unsigned m2 = dex_ballot(ok);
-        if (ok) {
-          const int idx = ncand + dex_popc(m2 & ((1u << lane) - 1u));
-          if (idx < DEX_MAXCAND1) cand[idx] = p;
-        }
-        ncand += dex_popc(m2);
+    const unsigned mk = dex_ballot(pass);
+    if (pass) cand[nbp + dex_popc(mk & ((1u << lane) - 1u))] = bp;   // nbodypair <= DEX_MAXCAND1 (host check)
+    nbp += dex_popc(mk);
+  }
+  dex_syncwarp();
+  int nbpl = 0;
+  unsigned status = 0;
+  for (int c0 = 0; c0 < nbp; c0 += 32) {
+    bool pass = false;
+    int bp = 0;
+    if (c0 + lane < nbp) {
+      bp = cand[c0 + lane];
+      const int b1 = dex_ldg(m.bp_body1 + bp), b2 = dex_ldg(m.bp_body2 + bp);
+      pass = true;
+      if (bsph[4 * b1 + 3] >= 0) {
+        Xf<T> rb;
+        dex_relative(xpos, xmat, b1, b2, rb);
+        pass = dex_obb_overlap(rb, m.body_pack + DEX_GPACK * b1, m.body_pack + DEX_GPACK * b2, m.max_margin + 2 * slack);
       }
+    }
+    const unsigned mk = dex_ballot(pass);
+    if (pass) {
+      const int idx = nbpl + dex_popc(mk & ((1u << lane) - 1u));
+      if (idx < DEX_MAXBPL) bpl[idx] = bp;
+    }
+    nbpl += dex_popc(mk);
+  }
+  if (nbpl > DEX_MAXBPL) { status |= DEX_STATUS_CAND_OVERFLOW; nbpl = DEX_MAXBPL; }
+  dex_syncwarp();
+
+  // ---- broadphase, geom pairs, pass 1: world-frame bounding spheres of the geoms of every surviving body pair
+  //      (cheap, mostly rejects); survivors are compacted so that the costlier AABB / OBB tests of pass 2 run on
+  //      dense lanes (r01d: 900 pairs visited per env, 86 survive the spheres, 7 survive everything)
+  int ncand = 0;
+  for (int bi = 0; bi < nbpl; ++bi) {
+    const int bpk = bpl[bi];
+    const int adr = dex_ldg(m.bp_pairadr + bpk), num = dex_ldg(m.bp_pairnum + bpk);
+    const int b1 = dex_ldg(m.bp_body1 + bpk);
+    const bool plane = bsph[4 * b1 + 3] < 0;
+    for (int p0 = 0; p0 < num; p0 += 32) {
+      const int p = adr + p0 + lane;
+      bool ok = false;
+      if (p0 + lane < num) {
+        const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
+        const T margin = dex_ldg(m.pair_margin + p);
+        T d[3] = {gsph[4 * g2] - gsph[4 * g1], gsph[4 * g2 + 1] - gsph[4 * g1 + 1], gsph[4 * g2 + 2] - gsph[4 * g1 + 2]};
+        const T r2 = gsph[4 * g2 + 3];
+        if (plane && dex_ldg(m.geom_type + g1) == DEX_GEOM_PLANE) {
+          const T* G = m.geom_mat + 9 * g1;
+          T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
+          rot_vec(n, xmat + 9 * b1, nl);
+          ok = dot3(d, n) <= margin + r2 + slack;
+        } else {
+          const T bound = margin + gsph[4 * g1 + 3] + r2 + slack;
+          ok = dot3(d, d) <= bound * bound;
+        }
+      }
+      const unsigned m2 = dex_ballot(ok);
+      if (ok) {
+        const int idx = ncand + dex_popc(m2 & ((1u << lane) - 1u));
+        if (idx < DEX_MAXCAND1) cand[idx] = p;
+      }
+      ncand += dex_popc(m2);
     }
   }
-  unsigned status = 0;
   if (ncand > DEX_MAXCAND1) { status |= DEX_STATUS_CAND_OVERFLOW; ncand = DEX_MAXCAND1; }
   dex_syncwarp();
   // pass 2: sphere-vs-AABB both ways, then AABB-vs-AABB as oriented boxes; in-place compaction

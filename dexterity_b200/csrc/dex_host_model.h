@@ -353,6 +353,8 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       M.bp_pairnum.back()++;
     }
     M.nbodypair = (int)M.bp_body1.size();
+    if (M.nbodypair > 384) return "more than 384 candidate body pairs (DEX_MAXCAND1)";
+    if (M.ngeom > 256) return "more than 256 geoms (DEX_MAXGEOM)";
     M.max_margin = maxmargin;
     // fold the largest pair margin into the body spheres so the body-level cull stays conservative
     for (int b = 0; b < nb; ++b) if (M.body_bsphere[4 * b + 3] >= 0) M.body_bsphere[4 * b + 3] += 0.5 * maxmargin;
