@@ -64,8 +64,11 @@ constexpr int kNarrowBlock = DEX_NARROW_BLOCK;
 // Persistent lanes: every thread runs one pair's MPR state machine and, as soon as that pair is done,
 // takes the next item off the global list (warp-aggregated atomic on the cursor), so the 32 lanes of a
 // warp stay busy although pairs need between 1 and ~50 support evaluations.
+#ifndef DEX_NARROW_MINB
+#define DEX_NARROW_MINB 8
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevModel<T> m, BatchState<T> st) {
+__global__ void __launch_bounds__(kNarrowBlock, DEX_NARROW_MINB) k_narrow(DevModel<T> m, BatchState<T> st) {
   int n = st.nwork[0];
   if (n > st.work_cap) n = st.work_cap;
   const int lane = threadIdx.x & 31;
@@ -96,11 +99,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_compact(DevModel<T> m, 
   dex_compact_env<T>(m, st, env);
 }
 
+// K1a: one warp (= one env) per CTA: envs differ a lot in surviving pairs, single-warp CTAs retire independently
+constexpr int kCollideWarps = 1;
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, DEX_K1_MINB) k_collide(DevModel<T> m, BatchState<T> st) {
+__global__ void __launch_bounds__(kCollideWarps * 32, DEX_K1_MINB * kWarpsPerBlock / kCollideWarps) k_collide(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  const int env = st.env0 + blockIdx.x * kWarpsPerBlock + warp;
+  const int env = st.env0 + blockIdx.x * kCollideWarps + warp;
   if (env >= st.nenv) return;
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K1_SMEM_T;
   dex_collide_env<T>(m, st, env, smem);
@@ -292,7 +297,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
 template <typename T>
 int set_attrs(DexBatch* b) {
   if (b->attrs_set) return DEX_OK;
-  DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T))));
   DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T))));
   // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
   DEX_CUDA(cudaFuncSetAttribute(k_tree<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
@@ -311,7 +316,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
                    bool dynamics, int integrate, cudaStream_t s) {
   int rc = set_attrs<T>(b);
   if (rc) return rc;
-  const size_t smem1 = (size_t)kWarpsPerBlock * DEX_K1_SMEM_T * sizeof(T);
+  const size_t smem1 = (size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T);
   const size_t smem2 = (size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T);
   int nchunk = b->nchunk;
   if (b->nenv < 1024 * nchunk) nchunk = 1;
@@ -351,7 +356,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
         b->launches++;
       }
       if (collide) {
-        { ProfScope ps(b, 1, cs); k_collide<T><<<grid, kWarpsPerBlock * 32, smem1, cs>>>(m, st); b->launches++; }
+        { ProfScope ps(b, 1, cs); k_collide<T><<<(n + kCollideWarps - 1) / kCollideWarps, kCollideWarps * 32, smem1, cs>>>(m, st); b->launches++; }
         { ProfScope ps(b, 5, cs); k_narrow<T><<<ngrid, kNarrowBlock, 0, cs>>>(m, st); b->launches++; }
         { ProfScope ps(b, 6, cs); k_compact<T><<<grid, kWarpsPerBlock * 32, 0, cs>>>(m, st); b->launches++; }
       }

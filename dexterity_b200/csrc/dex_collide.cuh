@@ -219,25 +219,33 @@ DEX_DEV void dex_support_lane(const DevModel<T>& m, LaneGeom<T>& G, T lx, T ly, 
         const bool bt = t > best;
         best = bt ? t : best; bi = bt ? G.last : bi;
       }
-      // climb: one neighbour per trip (a single flat loop keeps the lanes of a warp together); a move happens
-      // when all neighbours of the current vertex are seen; ties move towards the lowest index
-      int info = dex_ldg(m.vadj + G.adjbase + bi);
-      const int* nb = m.adj + (info >> 8);
-      int num = info & 255, k = 0, nxt = bi;
-      T nv = best;
-      for (int guard = 0; guard < 64 * G.n; ++guard) {
-        if (k == num) {
-          if (nxt == bi) break;
-          bi = nxt; best = nv;
-          info = dex_ldg(m.vadj + G.adjbase + bi);
-          nb = m.adj + (info >> 8); num = info & 255; k = 0;
+      // climb: all neighbours of the current vertex per trip, eight at a time with the loads of a batch in
+      // flight together (the dependent chain per move is adjacency word -> neighbour ids -> vertices); ties
+      // move towards the lowest index
+      for (int guard = 0; guard < G.n; ++guard) {
+        const int info = dex_ldg(m.vadj + G.adjbase + bi);
+        const int* nb = m.adj + (info >> 8);
+        const int num = info & 255;
+        int nxt = bi;
+        T nv = best;
+        for (int k0 = 0; k0 < num; k0 += 8) {
+          int j[8];
+          T t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) j[u] = (k0 + u < num) ? dex_ldg(nb + k0 + u) : bi;   // filler = current vertex: never "better"
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            dex_ldg_xyz(G.vert + 4 * j[u], vx, vy, vz);
+            t[u] = vx * lx + vy * ly + vz * lz;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const bool bt = (t[u] > nv) | ((t[u] == nv) & (j[u] < nxt));
+            nv = bt ? t[u] : nv; nxt = bt ? j[u] : nxt;
+          }
         }
-        const int j = dex_ldg(nb + k);
-        dex_ldg_xyz(G.vert + 4 * j, vx, vy, vz);
-        const T t = vx * lx + vy * ly + vz * lz;
-        const bool bt = (t > nv) | ((t == nv) & (j < nxt));
-        nv = bt ? t : nv; nxt = bt ? j : nxt;
-        ++k;
+        if (nxt == bi) break;
+        bi = nxt; best = nv;
       }
       G.last = bi;
     }
