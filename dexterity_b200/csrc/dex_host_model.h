@@ -103,6 +103,14 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       open[M.body_depth[b]] = b;
     }
   }
+  {  // children lists (world's children excluded: nothing accumulates into the world body)
+    M.body_childadr.assign(nb, 0); M.body_childnum.assign(nb, 0); M.body_child.clear();
+    for (int b = 1; b < nb; ++b) {
+      M.body_childadr[b] = (int)M.body_child.size();
+      for (int c = b + 1; c < nb; ++c) if (M.body_parent[c] == b) { M.body_child.push_back(c); M.body_childnum[b]++; }
+    }
+    if (M.body_child.empty()) M.body_child.assign(1, 0);
+  }
   {  // schedule of the 8-lanes-per-env tree kernel: round = tree depth, a lane follows a chain of first children
     const int G = 8;
     M.k0_rounds = M.maxdepth;

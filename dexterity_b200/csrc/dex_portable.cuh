@@ -79,6 +79,22 @@ DEX_DEV void dex_ldg_xyz(const double* p, double& x, double& y, double& z) {
 template <typename T> inline void dex_ldg_xyz(const T* p, T& x, T& y, T& z) { x = p[0]; y = p[1]; z = p[2]; }
 #endif
 
+// 16 consecutive reals to a 64-byte-aligned (FP32) / 128-byte-aligned (FP64) record: four STG.128 in FP32
+#if defined(__CUDACC__)
+DEX_DEV void dex_store16(float* p, const float* v) {
+  float4* q = reinterpret_cast<float4*>(p);
+  q[0] = make_float4(v[0], v[1], v[2], v[3]); q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  q[2] = make_float4(v[8], v[9], v[10], v[11]); q[3] = make_float4(v[12], v[13], v[14], v[15]);
+}
+DEX_DEV void dex_store16(double* p, const double* v) {
+  double2* q = reinterpret_cast<double2*>(p);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) q[k] = make_double2(v[2 * k], v[2 * k + 1]);
+}
+#else
+template <typename T> inline void dex_store16(T* p, const T* v) { for (int k = 0; k < 16; ++k) p[k] = v[k]; }
+#endif
+
 // ---------------------------------------------------------------------------------------
 // warp reductions (all 32 lanes must call)
 // ---------------------------------------------------------------------------------------

@@ -208,10 +208,9 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
     T* mat = s_mat[d];
     dex_body_fk<T>(m, qpos, b, s_pos[d - 1], s_quat[d - 1], s_mat[d - 1], pos, s_quat[d], mat, ref, cdof);
     {
-      T* xo = xkin + b * DEX_XKIN_BODY;
-      for (int k = 0; k < 3; ++k) xo[k] = pos[k];
-      for (int k = 0; k < 4; ++k) xo[3 + k] = s_quat[d][k];
-      for (int k = 0; k < 9; ++k) xo[7 + k] = mat[k];
+      const T rec[16] = {pos[0], pos[1], pos[2], s_quat[d][0], s_quat[d][1], s_quat[d][2], s_quat[d][3], mat[0], mat[1], mat[2],
+                         mat[3], mat[4], mat[5], mat[6], mat[7], mat[8]};
+      dex_store16(xkin + b * DEX_XKIN_BODY, rec);
     }
     // cinert about the tree reference point (mj_comPos)
     const T* rp = ref + 3 * dex_ldg(m.body_tree + b);
@@ -394,10 +393,9 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
     if (b >= 0) {
       dex_body_fk<T>(m, qpos, b, ppos, pquat, pmat, pos, quat, mat, ref, cdof);
       if (live) {
-        T* xo = xkin + b * DEX_XKIN_BODY;
-        for (int k = 0; k < 3; ++k) xo[k] = pos[k];
-        for (int k = 0; k < 4; ++k) xo[3 + k] = quat[k];
-        for (int k = 0; k < 9; ++k) xo[7 + k] = mat[k];
+        const T rec[16] = {pos[0], pos[1], pos[2], quat[0], quat[1], quat[2], quat[3], mat[0], mat[1], mat[2], mat[3], mat[4],
+                           mat[5], mat[6], mat[7], mat[8]};
+        dex_store16(xkin + b * DEX_XKIN_BODY, rec);
       }
       // cinert about the tree reference point (mj_comPos)
       const T* rp = ref + 3 * dex_ldg(m.body_tree + b);
@@ -466,8 +464,18 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
   for (int r = nround - 1; r >= 0; --r) {
     const int b = dex_ldg(m.k0_body + r * DEX_K0_G + gl);
     if (b >= 0) {
+      // subtree totals = own + the totals the children left in their slots one round ago (no atomics: the r01k
+      // profile had 22 % of K0's stall samples on shared-memory atomic adds into the palm's slot)
       T tot[16];
       for (int k = 0; k < 16; ++k) tot[k] = own[b * 16 + k];
+      {
+        const int ca = dex_ldg(m.body_childadr + b), cn = dex_ldg(m.body_childnum + b);
+        for (int c = ca; c < ca + cn; ++c) {
+          const T* oc = own + dex_ldg(m.body_child + c) * 16;
+          for (int k = 0; k < 16; ++k) tot[k] += oc[k];
+        }
+        if (cn > 0) for (int k = 0; k < 16; ++k) own[b * 16 + k] = tot[k];
+      }
       const int da = dex_ldg(m.body_dofadr + b), dn = dex_ldg(m.body_dofnum + b);
       for (int i = da; i < da + dn; ++i) {
         const T* ci = cdof[i];
@@ -485,8 +493,6 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
           if (live) { M[i * 32 + j] = s; M[j * 32 + i] = s; }
         }
       }
-      const int p = dex_ldg(m.body_parent + b);
-      if (p > 0) for (int k = 0; k < 16; ++k) dex_atomic_add(own + p * 16 + k, tot[k]);
     }
     dex_syncwarp();
   }
