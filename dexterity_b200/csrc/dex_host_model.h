@@ -103,23 +103,20 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       open[M.body_depth[b]] = b;
     }
   }
-  {  // children lists (world's children excluded: nothing accumulates into the world body)
-    M.body_childadr.assign(nb, 0); M.body_childnum.assign(nb, 0); M.body_child.clear();
-    for (int b = 1; b < nb; ++b) {
-      M.body_childadr[b] = (int)M.body_child.size();
-      for (int c = b + 1; c < nb; ++c) if (M.body_parent[c] == b) { M.body_child.push_back(c); M.body_childnum[b]++; }
-    }
-    if (M.body_child.empty()) M.body_child.assign(1, 0);
-  }
-  {  // schedule of the 8-lanes-per-env tree kernel: round = tree depth, a lane follows a chain of first children
+  // ---- schedule of the 8-lanes-per-env tree kernel (K0): round = tree depth, a lane follows a chain of first
+  //      children.  Per (round, lane) two 4-int records: {body, parent's lane, joints adr|num<<16, tree id} and
+  //      {body, dofs adr|num<<16, children adr|num<<16, 0}; per dof its ancestor chain (self first, -1 terminated).
+  //      (filled in below once the tree ids are known)
+  std::vector<int> k0_body, k0_src;
+  {
     const int G = 8;
     M.k0_rounds = M.maxdepth;
-    M.k0_body.assign(std::max(1, M.maxdepth * G), -1);
-    M.k0_src.assign(std::max(1, M.maxdepth * G), -1);
+    k0_body.assign(std::max(1, M.maxdepth * G), -1);
+    k0_src.assign(std::max(1, M.maxdepth * G), -1);
     std::vector<int> lane_of(nb, -1);
     for (int d = 1; d <= M.maxdepth && M.k0_rounds; ++d) {
-      int* rb = &M.k0_body[(d - 1) * G];
-      int* rs = &M.k0_src[(d - 1) * G];
+      int* rb = &k0_body[(d - 1) * G];
+      int* rs = &k0_src[(d - 1) * G];
       for (int pass = 0; pass < 2 && M.k0_rounds; ++pass)   // pass 0: first children keep the parent's lane
         for (int b = 1; b < nb; ++b) {
           if (M.body_depth[b] != d || lane_of[b] >= 0) continue;
@@ -131,6 +128,11 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
           rb[l] = b; rs[l] = p > 0 ? lane_of[p] : -1; lane_of[b] = l;
         }
     }
+    M.dof_anc8.assign(std::max(1, 8 * nv), -1);
+    for (int i = 0; i < nv; ++i) {
+      int t = 0;
+      for (int j = i; j >= 0; j = M.dof_parent[j]) { if (t == 8) { M.k0_rounds = 0; break; } M.dof_anc8[8 * i + t++] = j; }
+    }
   }
   std::vector<int> broot = I(DEXF_BODY_ROOT);
   std::map<int, int> tree_of_root;
@@ -141,6 +143,27 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     M.body_tree[b] = tree_of_root[broot[b]];
   }
   M.ntree = (int)tree_of_root.size();
+  {
+    std::vector<int> cadr(nb, 0), cnum(nb, 0);
+    M.body_child.clear();
+    for (int b = 1; b < nb; ++b) {   // children lists (the world's are not needed: nothing accumulates into the world body)
+      cadr[b] = (int)M.body_child.size();
+      for (int c = b + 1; c < nb; ++c) if (M.body_parent[c] == b) { M.body_child.push_back(c); cnum[b]++; }
+    }
+    if (M.body_child.empty()) M.body_child.assign(1, 0);
+    M.k0_rec.assign(k0_body.size() * 8, 0);
+    for (size_t e = 0; e < k0_body.size(); ++e) {
+      const int b = k0_body[e];
+      int* r = &M.k0_rec[8 * e];
+      r[0] = b; r[1] = k0_src[e]; r[4] = b;
+      if (b >= 0) {
+        r[2] = M.body_jntadr[b] | (M.body_jntnum[b] << 16); r[3] = M.body_tree[b];
+        r[5] = M.body_dofadr[b] | (M.body_dofnum[b] << 16); r[6] = cadr[b] | (cnum[b] << 16);
+        if (M.body_dofnum[b] == 0) r[5] = 0;
+        if (M.body_jntnum[b] == 0) r[2] = 0;
+      }
+    }
+  }
   if (M.ntree > 5) return "more than 5 kinematic trees";
   M.dof_tree.assign(nv, 0);
   for (int i = 0; i < nv; ++i) M.dof_tree[i] = M.body_tree[M.dof_body[i]];

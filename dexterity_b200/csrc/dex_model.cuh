@@ -32,7 +32,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(I, body_dofnum) X(I, body_tree) X(I, body_dofmask) X(I, body_weld)                     \
   X(R, body_pos) X(R, body_quat) X(R, body_ipos) X(R, body_mass) X(R, body_inertia6)       \
   X(R, body_xfrc) X(R, body_invweight0) X(R, body_bsphere) X(R, body_pack)                                 \
-  X(I, tree_refbody) X(I, k0_body) X(I, k0_src) X(I, body_childadr) X(I, body_childnum) X(I, body_child)                                            \
+  X(I, tree_refbody) X(I, k0_rec) X(I, dof_anc8) X(I, body_child)                                            \
   X(I, jnt_type) X(I, jnt_body) X(I, jnt_qposadr) X(I, jnt_dofadr) X(I, jnt_limited)       \
   X(R, jnt_pos) X(R, jnt_axis) X(R, jnt_range) X(R, jnt_margin) X(R, jnt_solref)           \
   X(R, jnt_solimp) X(R, qpos0)                                                             \

@@ -79,6 +79,16 @@ DEX_DEV void dex_ldg_xyz(const double* p, double& x, double& y, double& z) {
 template <typename T> inline void dex_ldg_xyz(const T* p, T& x, T& y, T& z) { x = p[0]; y = p[1]; z = p[2]; }
 #endif
 
+// four consecutive ints from a 16-byte-aligned address through the read-only path: one LDG.128
+#if defined(__CUDACC__)
+DEX_DEV void dex_ldg_int4(const int* p, int* out) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+#else
+inline void dex_ldg_int4(const int* p, int* out) { out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; }
+#endif
+
 // 16 consecutive reals to a 64-byte-aligned (FP32) / 128-byte-aligned (FP64) record: four STG.128 in FP32
 #if defined(__CUDACC__)
 DEX_DEV void dex_store16(float* p, const float* v) {

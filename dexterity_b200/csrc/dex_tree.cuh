@@ -37,8 +37,8 @@
 // Pose of body b from its parent's pose (mj_kinematics for one body).  When `ref` is given, the cdof
 // columns of the body's dofs are written to cdof[dof][6] ([angular; linear] about ref[tree]).
 template <typename T>
-DEX_DEV void dex_body_fk(const DevModel<T>& m, const T* qpos, int b, const T* ppos, const T* pquat, const T* pmat,
-                         T* pos, T* quat, T* mat, const T* ref, T (*cdof)[6]) {
+DEX_DEV void dex_body_fk(const DevModel<T>& m, const T* qpos, int b, int ja, int jn, int tree, const T* ppos, const T* pquat,
+                         const T* pmat, T* pos, T* quat, T* mat, const T* ref, T (*cdof)[6]) {
   T t[3];
   const T bp[3] = {dex_ldg(m.body_pos + 3 * b), dex_ldg(m.body_pos + 3 * b + 1), dex_ldg(m.body_pos + 3 * b + 2)};
   const T bq[4] = {dex_ldg(m.body_quat + 4 * b), dex_ldg(m.body_quat + 4 * b + 1), dex_ldg(m.body_quat + 4 * b + 2),
@@ -46,8 +46,7 @@ DEX_DEV void dex_body_fk(const DevModel<T>& m, const T* qpos, int b, const T* pp
   rot_vec(t, pmat, bp);
   pos[0] = ppos[0] + t[0]; pos[1] = ppos[1] + t[1]; pos[2] = ppos[2] + t[2];
   quat_mul(quat, pquat, bq);
-  const int ja = dex_ldg(m.body_jntadr + b), jn = dex_ldg(m.body_jntnum + b);
-  const T* rp = ref ? ref + 3 * dex_ldg(m.body_tree + b) : nullptr;
+  const T* rp = ref ? ref + 3 * tree : nullptr;
   int freedof = -1;
   for (int j = ja; j < ja + jn; ++j) {
     const int qa = dex_ldg(m.jnt_qposadr + j);
@@ -116,7 +115,8 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
     T pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int i = n - 1; i >= 0; --i) {
       T npos[3], nquat[4], nmat[9];
-      dex_body_fk<T>(m, qpos, path[i], pos, quat, mat, npos, nquat, nmat, nullptr, nullptr);
+      dex_body_fk<T>(m, qpos, path[i], dex_ldg(m.body_jntadr + path[i]), dex_ldg(m.body_jntnum + path[i]), 0, pos, quat, mat, npos,
+                     nquat, nmat, nullptr, nullptr);
       for (int k = 0; k < 3; ++k) pos[k] = npos[k];
       for (int k = 0; k < 4; ++k) quat[k] = nquat[k];
       for (int k = 0; k < 9; ++k) mat[k] = nmat[k];
@@ -206,7 +206,8 @@ DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env
     s_body[d] = b;
     T* pos = s_pos[d];
     T* mat = s_mat[d];
-    dex_body_fk<T>(m, qpos, b, s_pos[d - 1], s_quat[d - 1], s_mat[d - 1], pos, s_quat[d], mat, ref, cdof);
+    dex_body_fk<T>(m, qpos, b, dex_ldg(m.body_jntadr + b), dex_ldg(m.body_jntnum + b), dex_ldg(m.body_tree + b), s_pos[d - 1],
+                   s_quat[d - 1], s_mat[d - 1], pos, s_quat[d], mat, ref, cdof);
     {
       const T rec[16] = {pos[0], pos[1], pos[2], s_quat[d][0], s_quat[d][1], s_quat[d][2], s_quat[d][3], mat[0], mat[1], mat[2],
                          mat[3], mat[4], mat[5], mat[6], mat[7], mat[8]};
@@ -358,7 +359,8 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
     T pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int i = n - 1; i >= 0; --i) {
       T npos[3], nquat[4], nmat[9];
-      dex_body_fk<T>(m, qpos, path[i], pos, quat, mat, npos, nquat, nmat, nullptr, nullptr);
+      dex_body_fk<T>(m, qpos, path[i], dex_ldg(m.body_jntadr + path[i]), dex_ldg(m.body_jntnum + path[i]), 0, pos, quat, mat, npos,
+                     nquat, nmat, nullptr, nullptr);
       for (int k = 0; k < 3; ++k) pos[k] = npos[k];
       for (int k = 0; k < 4; ++k) quat[k] = nquat[k];
       for (int k = 0; k < 9; ++k) mat[k] = nmat[k];
@@ -375,8 +377,10 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
   T vel[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
   const int nround = m.k0_rounds;
   for (int r = 0; r < nround; ++r) {
-    const int b = dex_ldg(m.k0_body + r * DEX_K0_G + gl);
-    const int src = dex_ldg(m.k0_src + r * DEX_K0_G + gl);
+    // schedule record of this (round, lane): body, parent's lane, joints (adr | num << 16), tree id
+    int rec[4];
+    dex_ldg_int4(m.k0_rec + (r * DEX_K0_G + gl) * 8, rec);
+    const int b = rec[0], src = rec[1], ja = rec[2] & 0xffff, jn = rec[2] >> 16, btree = rec[3];
     const int sl = (lane & ~(DEX_K0_G - 1)) | (src < 0 ? gl : src);
     T ppos[3], pquat[4], pmat[9], v[6], a[6];
     for (int k = 0; k < 3; ++k) ppos[k] = dex_shfl(pos[k], sl);
@@ -391,14 +395,14 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
       a[3] = -m.gravity[0]; a[4] = -m.gravity[1]; a[5] = -m.gravity[2];
     }
     if (b >= 0) {
-      dex_body_fk<T>(m, qpos, b, ppos, pquat, pmat, pos, quat, mat, ref, cdof);
+      dex_body_fk<T>(m, qpos, b, ja, jn, btree, ppos, pquat, pmat, pos, quat, mat, ref, cdof);
       if (live) {
         const T rec[16] = {pos[0], pos[1], pos[2], quat[0], quat[1], quat[2], quat[3], mat[0], mat[1], mat[2], mat[3], mat[4],
                            mat[5], mat[6], mat[7], mat[8]};
         dex_store16(xkin + b * DEX_XKIN_BODY, rec);
       }
       // cinert about the tree reference point (mj_comPos)
-      const T* rp = ref + 3 * dex_ldg(m.body_tree + b);
+      const T* rp = ref + 3 * btree;
       const T mass = dex_ldg(m.body_mass + b);
       const T ip[3] = {dex_ldg(m.body_ipos + 3 * b), dex_ldg(m.body_ipos + 3 * b + 1), dex_ldg(m.body_ipos + 3 * b + 2)};
       T off[3], c[10];
@@ -422,7 +426,6 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
       }
       // velocity / acceleration through the body's joints (mj_comVel, mj_rne forward)
       {
-        const int ja = dex_ldg(m.body_jntadr + b), jn = dex_ldg(m.body_jntnum + b);
         for (int j = ja; j < ja + jn; ++j) {
           const int da = dex_ldg(m.jnt_dofadr + j);
           if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
@@ -462,21 +465,23 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
   }
   // ---- backward rounds: a body's slot holds its subtree totals once all deeper rounds are done
   for (int r = nround - 1; r >= 0; --r) {
-    const int b = dex_ldg(m.k0_body + r * DEX_K0_G + gl);
+    int rec[4];
+    dex_ldg_int4(m.k0_rec + (r * DEX_K0_G + gl) * 8 + 4, rec);   // body, dofs (adr | num << 16), children (adr | num << 16)
+    const int b = rec[0];
     if (b >= 0) {
       // subtree totals = own + the totals the children left in their slots one round ago (no atomics: the r01k
       // profile had 22 % of K0's stall samples on shared-memory atomic adds into the palm's slot)
       T tot[16];
       for (int k = 0; k < 16; ++k) tot[k] = own[b * 16 + k];
       {
-        const int ca = dex_ldg(m.body_childadr + b), cn = dex_ldg(m.body_childnum + b);
+        const int ca = rec[2] & 0xffff, cn = rec[2] >> 16;
         for (int c = ca; c < ca + cn; ++c) {
           const T* oc = own + dex_ldg(m.body_child + c) * 16;
           for (int k = 0; k < 16; ++k) tot[k] += oc[k];
         }
         if (cn > 0) for (int k = 0; k < 16; ++k) own[b * 16 + k] = tot[k];
       }
-      const int da = dex_ldg(m.body_dofadr + b), dn = dex_ldg(m.body_dofnum + b);
+      const int da = rec[1] & 0xffff, dn = rec[1] >> 16;
       for (int i = da; i < da + dn; ++i) {
         const T* ci = cdof[i];
         const T bias = ci[0] * tot[10] + ci[1] * tot[11] + ci[2] * tot[12] + ci[3] * tot[13] + ci[4] * tot[14] + ci[5] * tot[15];
@@ -486,10 +491,17 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
           tree[DEX_TREE_ROW_FS * 32 + i] = -dex_ldg(m.dof_damping + i) * qvel[i] - bias + act[i];  // qfrc_smooth
           for (int k = 0; k < 6; ++k) tree[k * 32 + i] = ci[k];
         }
-        for (int j = i; j >= 0; j = dex_ldg(m.dof_parent + j)) {
+        int anc[8];   // the dof and its ancestors (-1 terminated): two vector loads instead of a pointer chase
+        dex_ldg_int4(m.dof_anc8 + 8 * i, anc);
+        dex_ldg_int4(m.dof_anc8 + 8 * i + 4, anc + 4);
+        const T arm = dex_ldg(m.dof_armature + i);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int j = anc[t];
+          if (j < 0) break;
           const T* cj = cdof[j];
           T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
-          if (j == i) s += dex_ldg(m.dof_armature + i);
+          if (t == 0) s += arm;
           if (live) { M[i * 32 + j] = s; M[j * 32 + i] = s; }
         }
       }
