@@ -84,9 +84,11 @@ template <typename T> struct alignas(16) DexVec4 { T x, y, z, w; };
 // loads of row i (5 LDS.128 per 16 FMAs), the 4 x 4 diagonal block is finished with shuffles, and
 // one STS.128 per lane writes the block back; 8 warp barriers per factorisation (r01f profile: the
 // column-at-a-time version cost 3.9 k warp instructions per call, 42 % of K2).
+// `split` (a multiple of 4, or >= n): rows / columns >= split are known to be decoupled from those below it
+// (block-diagonal matrix), so their prefix dot products start at column `split`.
 // Returns 1 / L[i][i] for lane i.
 template <typename T>
-DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int* fail) {
+DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int split, int* fail) {
   const int i = dex_lane();
   T* rowi = H + i * DEX_MSTRIDE;
   bool bad = false;
@@ -97,7 +99,7 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int* fail) {
     const DexVec4<T> a = *reinterpret_cast<const DexVec4<T>*>(rowi + k0);
     T s0 = i == k0 ? hd : a.x, s1 = i == k0 + 1 ? hd : a.y, s2 = i == k0 + 2 ? hd : a.z, s3 = i == k0 + 3 ? hd : a.w;
     const T* r0 = H + k0 * DEX_MSTRIDE;
-    for (int g = 0; g < k0; g += 4) {
+    for (int g = (k0 >= split ? split : 0); g < k0; g += 4) {
       const DexVec4<T> vi = *reinterpret_cast<const DexVec4<T>*>(rowi + g);
       const DexVec4<T> v0 = *reinterpret_cast<const DexVec4<T>*>(r0 + g);
       const DexVec4<T> v1 = *reinterpret_cast<const DexVec4<T>*>(r0 + DEX_MSTRIDE + g);
@@ -414,11 +416,14 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     if (iter == 0 || sig_changed) {
       T hd = dex_chol_load(H, M, nv) + hdiag;
       dex_syncwarp();
+      bool cross = false;
+      const unsigned splitlo = m.chol_split >= 32 ? 0xffffffffu : ((1u << m.chol_split) - 1u);
       for (int c = 0; c < ncon; ++c) {
         const T* cdt = cdat + c * DEX_CDAT_STRIDE;
         const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
         if (w00 == 0) continue;  // no active row (warp-uniform)
         unsigned mask = (unsigned)*(const int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK);
+        if ((mask & splitlo) && (mask & ~splitlo)) cross = true;   // couples the trees on both sides of chol_split
         const T a0 = Jc[(3 * c) * DEX_JC_ROW + lane], a1 = Jc[(3 * c + 1) * DEX_JC_ROW + lane], a2 = Jc[(3 * c + 2) * DEX_JC_ROW + lane];
         const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
         const bool mine = isdof && ((mask >> lane) & 1u);
@@ -432,7 +437,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       }
       dex_syncwarp();
       int cfail = 0;
-      hinv = dex_chol_factor(H, hd, nv, &cfail);
+      hinv = dex_chol_factor(H, hd, nv, cross ? nv : m.chol_split, &cfail);
       if (cfail) status |= DEX_STATUS_CHOL_FAIL;
     }
     const T search = dex_chol_apply(H, nv, hinv, isdof ? -grad : T(0));
@@ -520,7 +525,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   const T ehd = dex_chol_load(H, M, ne) + (lane < ne ? h * damping : T(0));
   dex_syncwarp();
   int efail = 0;
-  const T einv = dex_chol_factor(H, ehd, ne, &efail);
+  const T einv = dex_chol_factor(H, ehd, ne, ne, &efail);
   T qacc_e = dex_chol_apply(H, ne, einv, lane < ne ? (fs + qfrc_constraint) : T(0));
   if (lane >= ne) qacc_e = qacc;
   const T qv_new = qv + h * qacc_e;

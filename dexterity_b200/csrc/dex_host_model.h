@@ -20,7 +20,7 @@
 struct HostModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
-  int k0_rounds;
+  int k0_rounds, chol_split;
   double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
@@ -172,6 +172,10 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     for (int i = 0; i < nv; ++i) if (M.dof_damping[i] > 0) tree_damped[M.dof_tree[i]] = 1;
     M.nv_euler = 0;
     for (int i = 0; i < nv; ++i) if (tree_damped[M.dof_tree[i]]) M.nv_euler = i + 1;
+  }
+  {  // largest multiple of 4 at which the dofs split into two groups of whole kinematic trees (M is block diagonal there)
+    M.chol_split = nv;
+    for (int s4 = 4; s4 < nv; s4 += 4) if (M.dof_tree[s4] != M.dof_tree[s4 - 1]) M.chol_split = s4;
   }
   M.body_dofmask.assign(nb, 0);
   for (int b = 1; b < nb; ++b) {

@@ -110,7 +110,7 @@ DEX_DEV void dex_ik_env(const DevModel<T>& m, const DexIkParams& p, const T* tar
       }
       dex_syncwarp();
       int fail = 0;
-      const T hinv = dex_chol_factor(H, hd, nv, &fail);
+      const T hinv = dex_chol_factor(H, hd, nv, nv, &fail);
       const T qdot = dex_chol_apply(H, nv, hinv, isdof ? rhs : T(0));
       // ---- integrate (dt = 1), clip to the joint range (ik_solver.py:189-194, 240-246)
       q = dx_clamp(q + qdot, lo, hi);

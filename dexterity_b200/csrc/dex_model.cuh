@@ -55,6 +55,7 @@ template <typename T>
 struct DevModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
+  int chol_split;  // first dof (multiple of 4) of a trailing group of kinematic trees that M does not couple to the dofs before it (nv if none)
   int k0_rounds;  // rounds of the 8-lanes-per-env tree kernel schedule (0 = model does not fit: thread-per-env kernel)
   T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) const int* name;

@@ -104,7 +104,7 @@ struct EmuModelT {
   void init(const HostModel& h) {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
-    dev.k0_rounds = h.k0_rounds; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
+    dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
