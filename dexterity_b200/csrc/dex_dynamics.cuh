@@ -26,7 +26,12 @@
 #define DEX_K2_OFF_CDAT (DEX_K2_OFF_H + 32 * DEX_MSTRIDE)
 #define DEX_CDAT_STRIDE 24
 #define DEX_K2_OFF_CDOT (DEX_K2_OFF_CDAT + DEX_MAXCON * DEX_CDAT_STRIDE)
+#ifdef DEX_K2_M_IN_SMEM
+#define DEX_K2_OFF_M (DEX_K2_OFF_CDOT + 96)
+#define DEX_K2_SMEM_T (DEX_K2_OFF_M + 32 * 32)
+#else
 #define DEX_K2_SMEM_T (DEX_K2_OFF_CDOT + 96)
+#endif
 #define DEX_JC_ROW 32                         // global Jc scratch: [env][3 * DEX_MAXCON][DEX_JC_ROW]
 #define DEX_JC_ENV (3 * DEX_MAXCON * DEX_JC_ROW)
 
@@ -129,10 +134,10 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int split, int* fail) {
     DexVec4<T> o;
     o.x = i > k0 ? l0 : T(0); o.y = i > k0 + 1 ? l1 : T(0); o.z = i > k0 + 2 ? l2 : T(0); o.w = i > k0 + 3 ? l3 : T(0);
     *reinterpret_cast<DexVec4<T>*>(rowi + k0) = o;
-    {  // branch-free: lane i keeps the inverse pivot of its own column
-      const int r = i - k0;
-      inv_mine = r == 0 ? i0 : (r == 1 ? i1 : (r == 2 ? i2 : (r == 3 ? i3 : inv_mine)));
-    }
+    inv_mine = i == k0 ? i0 : inv_mine;       // lane i keeps the inverse pivot of its own column (four selects)
+    inv_mine = i == k0 + 1 ? i1 : inv_mine;
+    inv_mine = i == k0 + 2 ? i2 : inv_mine;
+    inv_mine = i == k0 + 3 ? i3 : inv_mine;
     dex_syncwarp();
   }
   if (bad) *fail = 1;
@@ -209,7 +214,15 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   T* qvel = smem + DEX_K2_OFF_QVEL;
   T* vecA = smem + DEX_K2_OFF_VECA;
   T* vecB = smem + DEX_K2_OFF_VECB;
+#ifdef DEX_K2_M_IN_SMEM
+  T* M = smem + DEX_K2_OFF_M;                 // dense symmetric M staged from K0's global scratch
+  {
+    const T* Mg = st.mscr + (size_t)env * DEX_MG_ENV;
+    for (int j = 0; j < nv; ++j) M[j * 32 + lane] = Mg[j * 32 + lane];
+  }
+#else
   T* M = st.mscr + (size_t)env * DEX_MG_ENV;  // global scratch (L2 resident), symmetric, written by K0
+#endif
   T* H = smem + DEX_K2_OFF_H;
   T* Jc = st.jc + (size_t)env * DEX_JC_ENV;  // global scratch (L2 resident)
   T* cdat = smem + DEX_K2_OFF_CDAT;
