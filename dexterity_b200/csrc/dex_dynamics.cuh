@@ -366,20 +366,21 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   const int maxiter = m.iterations;
   for (;; ++iter) {
     // ---- forces, active sets, cost (PrimalUpdateConstraint)
-    T mycost = 0, fdof = 0, hdiag = 0;
+    // per-dof rows without divergent branches (lanes >= nv carry qacc = f_loss = l_sign = 0): friction loss is
+    // linear below -R f / above +R f and quadratic in between; a limit row is active while x < 0
+    T mycost = T(0.5) * qacc * Ma - qacc * fs, fdof = 0, hdiag = 0;
     int asig = 0;
-    if (isdof) {
-      mycost = T(0.5) * qacc * Ma - qacc * fs;
-      if (f_loss > 0) {
-        const T x = qacc - f_aref;
-        if (x <= -f_R * f_loss) { mycost += f_loss * (T(-0.5) * f_R * f_loss - x); fdof += f_loss; }
-        else if (x >= f_R * f_loss) { mycost += f_loss * (T(-0.5) * f_R * f_loss + x); fdof -= f_loss; }
-        else { mycost += T(0.5) * f_D * x * x; fdof -= f_D * x; hdiag += f_D; }
-      }
-      if (l_sign != 0) {
-        const T x = l_sign * qacc - l_aref;
-        if (x < 0) { mycost += T(0.5) * l_D * x * x; fdof -= l_sign * l_D * x; hdiag += l_D; }
-      }
+    {
+      const T x = qacc - f_aref, lim = f_R * f_loss;
+      const bool on = f_loss > 0, lo = x <= -lim, hi = x >= lim;
+      const T c = lo ? f_loss * (T(-0.5) * f_R * f_loss - x) : (hi ? f_loss * (T(-0.5) * f_R * f_loss + x) : T(0.5) * f_D * x * x);
+      const T f = lo ? f_loss : (hi ? -f_loss : -(f_D * x));
+      mycost += on ? c : T(0); fdof += on ? f : T(0); hdiag += (on && !lo && !hi) ? f_D : T(0);
+    }
+    {
+      const T x = l_sign * qacc - l_aref;
+      const bool on = (l_sign != 0) && (x < 0);
+      mycost += on ? T(0.5) * l_D * x * x : T(0); fdof -= on ? l_sign * l_D * x : T(0); hdiag += on ? l_D : T(0);
     }
     if (lane < ncon) {
       T* cdt = cdat + lane * DEX_CDAT_STRIDE;
@@ -471,17 +472,14 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     T alpha = 0, lo = 0, hi = -1, g0 = 0;
     for (int ls = 0; ls < 24; ++ls) {
       T g = q1 + alpha * q2, hh = q2;
-      if (isdof) {
-        if (f_loss > 0) {
-          const T x = qacc + alpha * search - f_aref;
-          if (x <= -f_R * f_loss) g -= f_loss * search;
-          else if (x >= f_R * f_loss) g += f_loss * search;
-          else { g += f_D * x * search; hh += f_D * search * search; }
-        }
-        if (l_sign != 0) {
-          const T jv = l_sign * search, x = l_sign * qacc - l_aref + alpha * jv;
-          if (x < 0) { g += l_D * x * jv; hh += l_D * jv * jv; }
-        }
+      {  // friction loss and limit rows, branch-free (same regimes as in the force update above)
+        const T x = qacc + alpha * search - f_aref, lim = f_R * f_loss;
+        const bool on = f_loss > 0, lo = x <= -lim, hi = x >= lim;
+        const T dg = lo ? -(f_loss * search) : (hi ? f_loss * search : f_D * x * search);
+        g += on ? dg : T(0); hh += (on && !lo && !hi) ? f_D * search * search : T(0);
+        const T jv = l_sign * search, xl = l_sign * qacc - l_aref + alpha * jv;
+        const bool lon = (l_sign != 0) && (xl < 0);
+        g += lon ? l_D * xl * jv : T(0); hh += lon ? l_D * jv * jv : T(0);
       }
       if (lane < ncon) {
         const T* cdt = cdat + lane * DEX_CDAT_STRIDE;
