@@ -117,19 +117,19 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int split, int* fail) {
     }
     // 4 x 4 diagonal block: column k0 + r is final once the r earlier columns of the block are applied
     T d = dex_shfl(s0, k0);
-    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
     const T i0 = dx_rsqrt(d), l0 = s0 * i0;
     s1 -= l0 * dex_shfl(l0, k0 + 1);
     d = dex_shfl(s1, k0 + 1);
-    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
     const T i1 = dx_rsqrt(d), l1 = s1 * i1;
     s2 -= l0 * dex_shfl(l0, k0 + 2) + l1 * dex_shfl(l1, k0 + 2);
     d = dex_shfl(s2, k0 + 2);
-    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
     const T i2 = dx_rsqrt(d), l2 = s2 * i2;
     s3 -= l0 * dex_shfl(l0, k0 + 3) + l1 * dex_shfl(l1, k0 + 3) + l2 * dex_shfl(l2, k0 + 3);
     d = dex_shfl(s3, k0 + 3);
-    if (!(d > Real<T>::minval())) { bad = true; d = Real<T>::minval(); }
+    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
     const T i3 = dx_rsqrt(d), l3 = s3 * i3;
     DexVec4<T> o;
     o.x = i > k0 ? l0 : T(0); o.y = i > k0 + 1 ? l1 : T(0); o.z = i > k0 + 2 ? l2 : T(0); o.w = i > k0 + 3 ? l3 : T(0);
@@ -388,7 +388,8 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       T f[4], w[4];
       for (int r = 0; r < 4; ++r) {
         const T x = cdt[CD_JAR + r];
-        if (x < 0) { f[r] = -D * x; w[r] = D; mycost += T(0.5) * D * x * x; asig |= 1 << r; } else { f[r] = 0; w[r] = 0; }
+        const bool on = x < 0;   // pyramid edge active
+        f[r] = on ? -D * x : T(0); w[r] = on ? D : T(0); mycost += on ? T(0.5) * D * x * x : T(0); asig |= on ? 1 << r : 0;
       }
       cdt[CD_F + 0] = f[0] + f[1] + f[2] + f[3];
       cdt[CD_F + 1] = mu * (f[0] - f[1]);
@@ -486,7 +487,8 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
         const T D = cdt[CD_D];
         for (int r = 0; r < 4; ++r) {
           const T jv = cdt[CD_JV + r], x = cdt[CD_JAR + r] + alpha * jv;
-          if (x < 0) { g += D * x * jv; hh += D * jv * jv; }
+          const bool on = x < 0;
+          g += on ? D * x * jv : T(0); hh += on ? D * jv * jv : T(0);
         }
       }
       g = dex_warp_sum(g);

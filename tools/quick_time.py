@@ -6,6 +6,7 @@ from dexterity_b200 import backend
 if len(sys.argv) > 1: backend.LIB_PATH = sys.argv[1]
 from dexterity_b200 import envs
 N = int(os.environ.get("NENV", 16384))
+torch.manual_seed(0); torch.cuda.manual_seed_all(0)
 env = envs.load("reorient", "state_dense", seed=12345, num_envs=N)
 lo = torch.as_tensor(env.action_spec().minimum, device=env.device); hi = torch.as_tensor(env.action_spec().maximum, device=env.device)
 env.reset()
