@@ -525,13 +525,27 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   T* bsph = gsph + DEX_MAXGEOM * 4;                 // [DEX_MAXBODY][4] world body bounding spheres
   int* cand = (int*)(bsph + DEX_MAXBODY * 4);       // DEX_MAXCAND1 ints (fits: sizeof(int) <= sizeof(T))
   int* bpl = cand + DEX_MAXCAND1;                   // DEX_MAXBPL surviving body pairs
-  {  // body poses of K0 (dex_tree.cuh): records of 16 = xpos(3) xquat(4) xmat(9)
+  {  // body poses of K0 (dex_tree.cuh): records of 16 = xpos(3) xquat(4) xmat(9), fetched as quarter records of 4
+     // with every load of the warp in flight before the first use (the r01m profile had 22 % of K1a's stall
+     // samples on this copy when it was a load-store loop)
     const T* xk = st.xkin + (size_t)env * DEX_XKIN_ENV;
-    for (int i = lane; i < m.nbody * DEX_XKIN_BODY; i += 32) {
-      const int b = i >> 4, e = i & 15;
-      const T v = xk[i];
-      if (e < 3) xpos[3 * b + e] = v;
-      else if (e >= 7) xmat[9 * b + e - 7] = v;
+    const int nq4 = m.nbody * 4;
+    T v[DEX_MAXBODY * 4 / 32][4];
+#pragma unroll
+    for (int k = 0; k < DEX_MAXBODY * 4 / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nq4) dex_ld4(xk + 4 * i, v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < DEX_MAXBODY * 4 / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nq4) {
+        const int b = i >> 2, q = i & 3;
+        if (q == 0) { xpos[3 * b] = v[k][0]; xpos[3 * b + 1] = v[k][1]; xpos[3 * b + 2] = v[k][2]; }
+        else if (q == 1) xmat[9 * b] = v[k][3];
+        else if (q == 2) { xmat[9 * b + 1] = v[k][0]; xmat[9 * b + 2] = v[k][1]; xmat[9 * b + 3] = v[k][2]; xmat[9 * b + 4] = v[k][3]; }
+        else { xmat[9 * b + 5] = v[k][0]; xmat[9 * b + 6] = v[k][1]; xmat[9 * b + 7] = v[k][2]; xmat[9 * b + 8] = v[k][3]; }
+      }
     }
   }
   dex_syncwarp();
@@ -619,7 +633,8 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
       const int p = adr + p0 + lane;
       bool ok = false;
       if (p0 + lane < num) {
-        const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
+        const int gg = dex_ldg(m.pair_gg + p);
+        const int g1 = gg & 0xffff, g2 = gg >> 16;
         const T margin = dex_ldg(m.pair_margin + p);
         T d[3] = {gsph[4 * g2] - gsph[4 * g1], gsph[4 * g2 + 1] - gsph[4 * g1 + 1], gsph[4 * g2 + 2] - gsph[4 * g1 + 2]};
         const T r2 = gsph[4 * g2 + 3];

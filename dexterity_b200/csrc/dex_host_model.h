@@ -387,6 +387,8 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       }
       M.bp_pairnum.back()++;
     }
+    M.pair_gg.assign(std::max(1, M.npair), 0);   // both geom ids in one word for the broadphase sweep
+    for (int p = 0; p < M.npair; ++p) M.pair_gg[p] = M.pair_geom1[p] | (M.pair_geom2[p] << 16);
     M.nbodypair = (int)M.bp_body1.size();
     if (M.nbodypair > 384) return "more than 384 candidate body pairs (DEX_MAXCAND1)";
     if (M.ngeom > 256) return "more than 256 geoms (DEX_MAXGEOM)";

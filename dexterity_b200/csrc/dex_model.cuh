@@ -47,7 +47,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(R, geom_pos) X(R, geom_mat) X(R, geom_size) X(R, geom_rbound) X(R, geom_aabb) X(R, geom_pack) X(R, vert)               \
   X(I, geom_adjbase) X(I, geom_cubemap) X(I, vadj) X(I, adj)                                \
   X(I, bp_body1) X(I, bp_body2) X(I, bp_pairadr) X(I, bp_pairnum)                          \
-  X(I, pair_geom1) X(I, pair_geom2) X(I, pair_condim) X(R, pair_friction) X(R, pair_solref) \
+  X(I, pair_geom1) X(I, pair_geom2) X(I, pair_gg) X(I, pair_condim) X(R, pair_friction) X(R, pair_solref) \
   X(R, pair_solimp) X(R, pair_margin) X(R, pair_gap)                                       \
   X(I, site_body) X(R, site_pos)
 
