@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T
 #ifndef DEX_NARROW_BLOCK
 #define DEX_NARROW_BLOCK 64
 #endif
-constexpr int kTreeWarps = 4;  // K0, 8-lanes-per-env form: 4 envs per warp, 16 per CTA
+#ifndef DEX_TREE_WARPS
+#define DEX_TREE_WARPS 1
+#endif
+constexpr int kTreeWarps = DEX_TREE_WARPS;  // K0, 8-lanes-per-env form: 4 envs per warp
 template <typename T>
 __global__ void __launch_bounds__(kTreeWarps * 32) k_tree8(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
