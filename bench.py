@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 NUM_ENVS_PER_GPU = 16384          # BASELINE.json configs[2] / configs[4] (131072 over 8 GPUs)
 B_ENV = 1364                      # algorithmic bytes per env-step, SURVEY.md §8(d) / BASELINE.md §3
 B_MJ = 808                        # algorithmic bytes per mj_step (state round trip)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 envs from the `ncu --set full` capture summarised in
+# profiles/r01n_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
+NCU_TRAFFIC_BYTES = {"k_dynamics": 87.43e6 + 4.87e6, "k_tree": 46.17e6 + 70.50e6}
 METRIC = "env-steps/sec, Shadow-hand cube reorient"
 UNIT = "env-steps/s"
 
@@ -244,7 +247,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": n * (env.obs_dim + 3) * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": dom,
+                         "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get(dom) if n == NUM_ENVS_PER_GPU else None, "kernel": dom,
                          "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": n * B_MJ, "peak_source": peak_src,
                          "env_step_frac": (value / world) * B_ENV / 1e9 / peak,
                          "note": "compute/latency-bound path: HBM fraction is reported for comparability"},
