@@ -222,6 +222,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   }
 #else
   T* M = st.mscr + (size_t)env * DEX_MG_ENV;  // global scratch (L2 resident), symmetric, written by K0
+  dex_prefetch_l1(M + lane * 32);             // row `lane` (128 B): the first M v product comes ~1 k instructions later
 #endif
   T* H = smem + DEX_K2_OFF_H;
   T* Jc = st.jc + (size_t)env * DEX_JC_ENV;  // global scratch (L2 resident)

@@ -79,6 +79,13 @@ DEX_DEV void dex_ldg_xyz(const double* p, double& x, double& y, double& z) {
 template <typename T> inline void dex_ldg_xyz(const T* p, T& x, T& y, T& z) { x = p[0]; y = p[1]; z = p[2]; }
 #endif
 
+// hint: bring the line at p into L1 (no register result, no stall)
+#if defined(__CUDACC__)
+DEX_DEV void dex_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+inline void dex_prefetch_l1(const void*) {}
+#endif
+
 // four consecutive ints from a 16-byte-aligned address through the read-only path: one LDG.128
 #if defined(__CUDACC__)
 DEX_DEV void dex_ldg_int4(const int* p, int* out) {
