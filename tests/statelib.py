@@ -52,6 +52,29 @@ def rollout_states(compiled, seed: int, nstates: int, every: int = 10, nsub: int
     return {k: np.array(v) for k, v in out.items()}
 
 
+def rollout_states_batch(compiled, seed: int, nenv: int = 256, snapshots: int = 16, every: int = 5,
+                         nthreads: int = 8) -> Dict[str, np.ndarray]:
+    """nenv x snapshots states from `nenv` oracle rollouts run in parallel threads (orc_step_batch): every env takes
+    `every` mj_steps with one uniform random control per snapshot; envs whose cube has fallen below the hand are
+    reset from the task's reset distribution (reference reorient.py:206-209)."""
+    rng = np.random.RandomState(seed)
+    om = orc.OracleModel(compiled)
+    lo, hi = compiled.ACT_CTRLRANGE[:, 0], compiled.ACT_CTRLRANGE[:, 1]
+    qpos = np.stack([reorient_reset(compiled, rng) for _ in range(nenv)])
+    qvel = np.zeros((nenv, compiled.nv)); warm = np.zeros((nenv, compiled.nv))
+    out = dict(qpos=[], qvel=[], ctrl=[], warm=[])
+    for _ in range(snapshots):
+        ctrl = rng.uniform(lo, hi, size=(nenv, compiled.nu))
+        om.step_batch(qpos, qvel, ctrl, warm, nsub=every, nthreads=nthreads)
+        bad = ~np.isfinite(qpos).all(axis=1) | ~np.isfinite(qvel).all(axis=1)
+        if compiled.nq >= 31:
+            bad |= qpos[:, compiled.nq - 5] < 0.03          # cube centre near the ground: the episode would have ended
+        for e in np.nonzero(bad)[0]:
+            qpos[e] = reorient_reset(compiled, rng); qvel[e] = 0; warm[e] = 0
+        out["qpos"].append(qpos.copy()); out["qvel"].append(qvel.copy()); out["ctrl"].append(ctrl.copy()); out["warm"].append(warm.copy())
+    return {k: np.concatenate(v) for k, v in out.items()}
+
+
 def oracle_step(compiled, states: Dict[str, np.ndarray], nsub: int = 1, forward_only: bool = False):
     """Oracle result for every state: next state, contacts (as sets), qacc."""
     om = orc.OracleModel(compiled)

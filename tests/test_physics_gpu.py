@@ -62,6 +62,36 @@ def test_contact_sets_match_oracle(setup):
         assert (b.status.cpu().numpy() & 6 == 0).all(), "candidate/contact buffer overflow"
 
 
+def test_contact_sets_4096_states(reorient_model):
+    """contact-pair sets and counts against the oracle on >= 4096 sampled states; they must be
+    identical on every non-degenerate state (no pair within 1e-6 of touching), FP32 product build."""
+    from dexterity_b200 import backend
+    compiled = reorient_model
+    states = statelib.rollout_states_batch(compiled, seed=31, nenv=256, snapshots=16, every=5, nthreads=8)
+    n = len(states["qpos"])
+    assert n >= 4096
+    ref = statelib.oracle_step(compiled, states, forward_only=True)
+    b = backend.PhysicsBatch(backend.PhysicsModel(compiled, 0), n, torch.float32)
+    statelib.upload(b, states)
+    b.collide()
+    torch.cuda.synchronize()
+    ncon = b.ncon.cpu().numpy()
+    con = b.contact.cpu().numpy().astype(np.float64)
+    nondeg = mism = with_contacts = 0
+    for e in range(n):
+        dist = ref["dist"][e]
+        if len(dist) and np.abs(dist).min() <= 1e-6:
+            continue
+        nondeg += 1
+        with_contacts += len(dist) > 0
+        pairs = [(int(compiled.PAIR_GEOM1[int(p)]), int(compiled.PAIR_GEOM2[int(p)])) for p in con[e, :ncon[e], 7]]
+        mism += sorted(pairs) != sorted(ref["pairs"][e])
+    print(f"contact sets: {nondeg} non-degenerate of {n} states, {with_contacts} with contacts, {mism} mismatches")
+    assert nondeg >= 0.9 * n and with_contacts >= 0.2 * n
+    assert mism == 0
+    assert (b.status.cpu().numpy() & 6 == 0).all(), "candidate/contact buffer overflow"
+
+
 def test_single_step_fp64_validation_build(setup):
     compiled, states, ref, model = setup
     b = _run(model, states, torch.float64)
