@@ -75,7 +75,7 @@ class OracleModel:
         self.nq, self.nv, self.nu = compiled.nq, compiled.nv, compiled.nu
 
     def __del__(self):
-        if getattr(self, "ptr", None):
+        if getattr(self, "ptr", None) and lib is not None:   # `lib` is already gone at interpreter shutdown
             lib().orc_model_destroy(self.ptr)
             self.ptr = None
 
