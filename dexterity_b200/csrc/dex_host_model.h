@@ -238,6 +238,21 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       o[0] = A[0]; o[1] = A[4]; o[2] = A[8]; o[3] = A[1]; o[4] = A[2]; o[5] = A[5];
     }
   }
+  // ---- packed constant records of the tree kernel K0 (vector loads instead of ~35 scalar loads per body)
+  M.body_rec.assign(24 * nb, 0.0);
+  for (int b = 0; b < nb; ++b) {
+    double* r = &M.body_rec[24 * b];
+    for (int k = 0; k < 3; ++k) { r[k] = M.body_pos[3 * b + k]; r[8 + k] = M.body_ipos[3 * b + k]; }
+    r[3] = M.body_mass[b];
+    for (int k = 0; k < 4; ++k) r[4 + k] = M.body_quat[4 * b + k];
+    for (int k = 0; k < 6; ++k) { r[12 + k] = M.body_inertia6[6 * b + k]; r[18 + k] = M.body_xfrc[6 * b + k]; }
+  }
+  M.jnt_rec.assign(std::max(1, 8 * M.njnt), 0.0); M.jnt_irec.assign(std::max(1, 4 * M.njnt), 0);
+  for (int j = 0; j < M.njnt; ++j) {
+    for (int k = 0; k < 3; ++k) { M.jnt_rec[8 * j + k] = M.jnt_axis[3 * j + k]; M.jnt_rec[8 * j + 4 + k] = M.jnt_pos[3 * j + k]; }
+    M.jnt_rec[8 * j + 3] = M.qpos0[M.jnt_qposadr[j]];
+    M.jnt_irec[4 * j] = M.jnt_type[j]; M.jnt_irec[4 * j + 1] = M.jnt_qposadr[j]; M.jnt_irec[4 * j + 2] = M.jnt_dofadr[j];
+  }
   // ---- geoms: body-frame rotation matrices and hull vertices
   {
     std::vector<double> gq = F(DEXF_GEOM_QUAT), v = F(DEXF_VERT);

@@ -11,7 +11,9 @@
 #define DEX_MAXJNT 32
 #define DEX_MAXU 32
 #define DEX_MAXTEN 8
+#ifndef DEX_MAXCON
 #define DEX_MAXCON 24      // per-env contact capacity (overflow sets a status bit)
+#endif
 #define DEX_MAXCAND 128    // per-env narrowphase candidate capacity
 #define DEX_CON_STRIDE 8   // words per stored contact: dist, pos(3), normal(3), pair id
 #define DEX_CUBEMAP_WORDS 192  // per mesh geom: 6 x 8 x 8 start vertices for the hill-climbing support, 2 per word
@@ -32,7 +34,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(I, body_dofnum) X(I, body_tree) X(I, body_dofmask) X(I, body_weld)                     \
   X(R, body_pos) X(R, body_quat) X(R, body_ipos) X(R, body_mass) X(R, body_inertia6)       \
   X(R, body_xfrc) X(R, body_invweight0) X(R, body_bsphere) X(R, body_pack)                                 \
-  X(I, tree_refbody) X(I, k0_rec) X(I, dof_anc8) X(I, body_child)                                            \
+  X(R, body_rec) X(R, jnt_rec) X(I, jnt_irec) X(I, tree_refbody) X(I, k0_rec) X(I, dof_anc8) X(I, body_child)                                            \
   X(I, jnt_type) X(I, jnt_body) X(I, jnt_qposadr) X(I, jnt_dofadr) X(I, jnt_limited)       \
   X(R, jnt_pos) X(R, jnt_axis) X(R, jnt_range) X(R, jnt_margin) X(R, jnt_solref)           \
   X(R, jnt_solimp) X(R, qpos0)                                                             \

@@ -96,6 +96,20 @@ DEX_DEV void dex_ldg_int4(const int* p, int* out) {
 inline void dex_ldg_int4(const int* p, int* out) { out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; }
 #endif
 
+// four consecutive reals from a 16-byte-aligned address through the read-only path (model constants)
+#if defined(__CUDACC__)
+DEX_DEV void dex_ldg4(const float* p, float* out) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+DEX_DEV void dex_ldg4(const double* p, double* out) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+  out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+}
+#else
+template <typename T> inline void dex_ldg4(const T* p, T* out) { out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; }
+#endif
+
 // four consecutive reals from a 16-byte (FP32) / 32-byte (FP64) aligned address: one LDG.128 in FP32
 #if defined(__CUDACC__)
 DEX_DEV void dex_ld4(const float* p, float* out) {

@@ -27,6 +27,7 @@
 #ifndef DEX_MAXDEPTH
 #define DEX_MAXDEPTH 12
 #endif
+#define DEX_BODY_REC 24   // packed per-body constants: pos(3) mass | quat(4) | ipos(3) - | inertia6 | xfrc6
 #define DEX_XKIN_BODY 16
 #define DEX_XKIN_ENV (DEX_MAXBODY * DEX_XKIN_BODY)
 #define DEX_TREE_ENV 256
@@ -40,30 +41,33 @@ template <typename T>
 DEX_DEV void dex_body_fk(const DevModel<T>& m, const T* qpos, int b, int ja, int jn, int tree, const T* ppos, const T* pquat,
                          const T* pmat, T* pos, T* quat, T* mat, const T* ref, T (*cdof)[6]) {
   T t[3];
-  const T bp[3] = {dex_ldg(m.body_pos + 3 * b), dex_ldg(m.body_pos + 3 * b + 1), dex_ldg(m.body_pos + 3 * b + 2)};
-  const T bq[4] = {dex_ldg(m.body_quat + 4 * b), dex_ldg(m.body_quat + 4 * b + 1), dex_ldg(m.body_quat + 4 * b + 2),
-                   dex_ldg(m.body_quat + 4 * b + 3)};
+  T bp[4], bq[4];   // packed body record (DevModel::body_rec): pos(3) mass | quat(4) | ...
+  dex_ldg4(m.body_rec + DEX_BODY_REC * b, bp);
+  dex_ldg4(m.body_rec + DEX_BODY_REC * b + 4, bq);
   rot_vec(t, pmat, bp);
   pos[0] = ppos[0] + t[0]; pos[1] = ppos[1] + t[1]; pos[2] = ppos[2] + t[2];
   quat_mul(quat, pquat, bq);
   const T* rp = ref ? ref + 3 * tree : nullptr;
   int freedof = -1;
   for (int j = ja; j < ja + jn; ++j) {
-    const int qa = dex_ldg(m.jnt_qposadr + j);
-    const T ax[3] = {dex_ldg(m.jnt_axis + 3 * j), dex_ldg(m.jnt_axis + 3 * j + 1), dex_ldg(m.jnt_axis + 3 * j + 2)};
-    if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+    int ji[4];   // packed joint records (DevModel::jnt_irec / jnt_rec): type, qposadr, dofadr | axis(3) qpos0 | pos(3)
+    T ax[4], jp[4];
+    dex_ldg_int4(m.jnt_irec + 4 * j, ji);
+    dex_ldg4(m.jnt_rec + 8 * j, ax);
+    dex_ldg4(m.jnt_rec + 8 * j + 4, jp);
+    const int qa = ji[1];
+    if (ji[0] == DEX_JNT_FREE) {
       pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
       quat[0] = qpos[qa + 3]; quat[1] = qpos[qa + 4]; quat[2] = qpos[qa + 5]; quat[3] = qpos[qa + 6];
       quat_normalize(quat);
-      freedof = dex_ldg(m.jnt_dofadr + j);
+      freedof = ji[2];
     } else {
-      const T jp[3] = {dex_ldg(m.jnt_pos + 3 * j), dex_ldg(m.jnt_pos + 3 * j + 1), dex_ldg(m.jnt_pos + 3 * j + 2)};
       T anchor[3];
       quat2mat(mat, quat);
       rot_vec(t, mat, jp);
       anchor[0] = pos[0] + t[0]; anchor[1] = pos[1] + t[1]; anchor[2] = pos[2] + t[2];
       if (rp) {  // hinge: [axis; axis x (ref - anchor)]
-        T* cd = cdof[dex_ldg(m.jnt_dofadr + j)];
+        T* cd = cdof[ji[2]];
         T xa[3];
         rot_vec(xa, mat, ax);
         const T off[3] = {rp[0] - anchor[0], rp[1] - anchor[1], rp[2] - anchor[2]};
@@ -71,7 +75,7 @@ DEX_DEV void dex_body_fk(const DevModel<T>& m, const T* qpos, int b, int ja, int
         cross3(cd + 3, xa, off);
       }
       T ql[4], qn[4];
-      axisangle2quat(ql, ax, qpos[qa] - dex_ldg(m.qpos0 + qa));
+      axisangle2quat(ql, ax, qpos[qa] - ax[3]);
       quat_mul(qn, quat, ql);
       quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
       quat2mat(mat, quat);
@@ -403,15 +407,17 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
       }
       // cinert about the tree reference point (mj_comPos)
       const T* rp = ref + 3 * btree;
-      const T mass = dex_ldg(m.body_mass + b);
-      const T ip[3] = {dex_ldg(m.body_ipos + 3 * b), dex_ldg(m.body_ipos + 3 * b + 1), dex_ldg(m.body_ipos + 3 * b + 2)};
+      T br[6][4];   // packed body record: pos mass | quat | ipos - | inertia6 xfrc6 (all loads in flight together)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dex_ldg4(m.body_rec + DEX_BODY_REC * b + 4 * k, br[k]);
+      const T mass = br[0][3];
+      const T ip[3] = {br[2][0], br[2][1], br[2][2]};
       T off[3], c[10];
       rot_vec(off, mat, ip);
       off[0] += pos[0] - rp[0]; off[1] += pos[1] - rp[1]; off[2] += pos[2] - rp[2];
       {
-        const T* I6 = m.body_inertia6 + 6 * b;
-        const T Ib[9] = {dex_ldg(I6), dex_ldg(I6 + 3), dex_ldg(I6 + 4), dex_ldg(I6 + 3), dex_ldg(I6 + 1), dex_ldg(I6 + 5),
-                         dex_ldg(I6 + 4), dex_ldg(I6 + 5), dex_ldg(I6 + 2)};
+        // inertia6 = xx yy zz xy xz yz at record words 12..17
+        const T Ib[9] = {br[3][0], br[3][3], br[4][0], br[3][3], br[3][1], br[4][1], br[4][0], br[4][1], br[3][2]};
         T RI[9];
         for (int rr = 0; rr < 3; ++rr) for (int cc = 0; cc < 3; ++cc)
           RI[3 * rr + cc] = mat[3 * rr] * Ib[cc] + mat[3 * rr + 1] * Ib[3 + cc] + mat[3 * rr + 2] * Ib[6 + cc];
@@ -427,8 +433,10 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
       // velocity / acceleration through the body's joints (mj_comVel, mj_rne forward)
       {
         for (int j = ja; j < ja + jn; ++j) {
-          const int da = dex_ldg(m.jnt_dofadr + j);
-          if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
+          int ji[4];
+          dex_ldg_int4(m.jnt_irec + 4 * j, ji);
+          const int da = ji[2];
+          if (ji[0] == DEX_JNT_FREE) {
             for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) v[k] += cdof[da + i][k] * qvel[da + i];
             T cdd[3][6];
             for (int i = 0; i < 3; ++i) cross_motion(cdd[i], v, cdof[da + 3 + i]);
@@ -446,8 +454,8 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
       for (int k = 0; k < 6; ++k) { vel[k] = v[k]; acc[k] = a[k]; }
       // own spatial force: I a + v x* (I v) - external force about the reference point
       {
-        const T* xf = m.body_xfrc + 6 * b;
-        const T f[3] = {dex_ldg(xf), dex_ldg(xf + 1), dex_ldg(xf + 2)};
+        // xfrc6 = force(3) torque(3) at record words 18..23
+        const T f[3] = {br[4][2], br[4][3], br[5][0]};
         T tq[3], t1[6], t2[6], t3[6];
         cross3(tq, off, f);
         mul_inert_vec(t1, c, a);
@@ -455,9 +463,9 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
         cross_force(t3, v, t2);
         T* o = own + b * 16;
         for (int k = 0; k < 10; ++k) o[k] = c[k];
-        o[10] = -(dex_ldg(xf + 3) + tq[0]) + t1[0] + t3[0];
-        o[11] = -(dex_ldg(xf + 4) + tq[1]) + t1[1] + t3[1];
-        o[12] = -(dex_ldg(xf + 5) + tq[2]) + t1[2] + t3[2];
+        o[10] = -(br[5][1] + tq[0]) + t1[0] + t3[0];
+        o[11] = -(br[5][2] + tq[1]) + t1[1] + t3[1];
+        o[12] = -(br[5][3] + tq[2]) + t1[2] + t3[2];
         o[13] = -f[0] + t1[3] + t3[3]; o[14] = -f[1] + t1[4] + t3[4]; o[15] = -f[2] + t1[5] + t3[5];
       }
     }
