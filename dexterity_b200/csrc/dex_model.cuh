@@ -12,7 +12,7 @@
 #define DEX_MAXU 32
 #define DEX_MAXTEN 8
 #ifndef DEX_MAXCON
-#define DEX_MAXCON 24      // per-env contact capacity (overflow sets a status bit)
+#define DEX_MAXCON 32      // per-env contact capacity = one lane per contact in K2 (overflow sets a status bit)
 #endif
 #define DEX_MAXCAND 128    // per-env narrowphase candidate capacity
 #define DEX_CON_STRIDE 8   // words per stored contact: dist, pos(3), normal(3), pair id

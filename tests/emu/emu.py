@@ -10,7 +10,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_DIR, "libdex_emu.so")
 _CSRC = os.path.join(_DIR, "..", "..", "dexterity_b200", "csrc")
-MAXCON, CON_STRIDE = 24, 8
+MAXCON, CON_STRIDE = 32, 8
 
 
 def build(force: bool = False) -> str:
