@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_CSRC, "libdexb200.so")
 FIELD = dict(QPOS=0, QVEL=1, CTRL=2, QACC_WARMSTART=3, TIME=4, STATUS=5, CONTACT=6, NCON=7, NITER=8,
              DBG_M=9, DBG_QFRC_SMOOTH=10, DBG_QACC=11, DBG_QFRC_CONSTRAINT=12, DBG_EFC=13,
              OBS=14, REWARD=15, DISCOUNT=16, NSLOT=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22,
-             WORK=23, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31)
+             WORK=23, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31, ORDER=32)
 STATUS_BADQACC, STATUS_CON_OVERFLOW, STATUS_CAND_OVERFLOW, STATUS_SOLVER_MAXITER, STATUS_CHOL_FAIL = 1, 2, 4, 8, 16
 
 _lib = None
@@ -115,7 +115,7 @@ class PhysicsBatch:
             STATUS=z(n, dt=torch.int32), CONTACT=z(n, maxcon, cstride), NCON=z(n, dt=torch.int32),
             NITER=z(n, dt=torch.int32), JC=torch.empty(n, 3 * maxcon, 32, dtype=dtype, device=dev),
             MSCR=z(n, 32, 32), XKIN=z(n, capacity(3) * 16), TREE=z(n, 8 * 32), STAGE=z(n, 64, 8),
-            NSLOT=z(n, dt=torch.int32))
+            NSLOT=z(n, dt=torch.int32), ORDER=z(n, dt=torch.int32))
         if debug:
             self._store.update(DBG_M=z(n, c.nv * c.nv), DBG_QFRC_SMOOTH=z(n, c.nv), DBG_QACC=z(n, c.nv),
                                DBG_QFRC_CONSTRAINT=z(n, c.nv), DBG_EFC=z(n, maxcon, 8))
@@ -123,7 +123,7 @@ class PhysicsBatch:
             self.bind(name, t)
         # global narrowphase work list: item count, fetch cursor, then (env, slot << 24 | pair) per item
         cap = max(32 * n, 4096)
-        work = z(2 + 2 * cap, dt=torch.int32)
+        work = z(4 + 2 * cap, dt=torch.int32)
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
         self.set_chunks(int(os.environ.get("DEX_CHUNKS", "1")))

@@ -41,7 +41,7 @@ constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps sp
 template <typename T>
 __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {
   const int env = st.env0 + blockIdx.x * kTreeBlock + threadIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; }  // this mj_step's work list: item count, fetch cursor
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; st.nwork[2] = 0; st.nwork[3] = 0; }  // work items, fetch cursor, order counters
   if (env >= st.nenv) return;
   dex_tree_env<T>(m, st, env);
 }
@@ -57,7 +57,7 @@ template <typename T>
 __global__ void __launch_bounds__(kTreeWarps * 32) k_tree8(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; st.nwork[2] = 0; st.nwork[3] = 0; }
   const int env_base = st.env0 + (blockIdx.x * kTreeWarps + warp) * DEX_K0_ENVS;
   if (env_base >= st.nenv) return;
   dex_tree_warp<T>(m, st, env_base, reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K0_SMEM_T);
@@ -114,13 +114,18 @@ __global__ void __launch_bounds__(kCollideWarps * 32, DEX_K1_MINB * kWarpsPerBlo
   dex_collide_env<T>(m, st, env, smem);
 }
 
+#ifndef DEX_K2_WARPS
+#define DEX_K2_WARPS 1   // single-warp CTAs: envs differ 3x in solver work, a CTA of 4 would hold its slots until the slowest is done
+#endif
+constexpr int kDynWarps = DEX_K2_WARPS;
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, DEX_K2_MINB) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
+__global__ void __launch_bounds__(kDynWarps * 32, DEX_K2_MINB * DEX_WARPS_PER_BLOCK / DEX_K2_WARPS) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
                                                                    int integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  const int env = st.env0 + blockIdx.x * kWarpsPerBlock + warp;
-  if (env >= st.nenv) return;
+  const int slot = st.env0 + blockIdx.x * kDynWarps + warp;
+  if (slot >= st.nenv) return;
+  const int env = st.order ? st.order[slot] : slot;   // K1c's heavy-first order
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
 }
@@ -286,8 +291,9 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.stage = (T*)b->ptr[DEX_FIELD_STAGE];
   st.nslot = (int*)b->ptr[DEX_FIELD_NSLOT];
   st.nwork = (int*)b->ptr[DEX_FIELD_WORK];
-  st.work = st.nwork + 2;
+  st.work = st.nwork + 4;
   st.work_cap = (int)b->stride[DEX_FIELD_WORK];
+  st.order = (int*)b->ptr[DEX_FIELD_ORDER];
   if (st.work_cap < 1) return fail(DEX_E_ARG, "DEX_FIELD_WORK must be bound with row_stride = capacity in items");
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
@@ -301,7 +307,7 @@ template <typename T>
 int set_attrs(DexBatch* b) {
   if (b->attrs_set) return DEX_OK;
   DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T))));
-  DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T))));
   // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
   DEX_CUDA(cudaFuncSetAttribute(k_tree<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   DEX_CUDA(cudaFuncSetAttribute(k_tree8<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T))));
@@ -320,7 +326,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
   int rc = set_attrs<T>(b);
   if (rc) return rc;
   const size_t smem1 = (size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T);
-  const size_t smem2 = (size_t)kWarpsPerBlock * DEX_K2_SMEM_T * sizeof(T);
+  const size_t smem2 = (size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T);
   int nchunk = b->nchunk;
   if (b->nenv < 1024 * nchunk) nchunk = 1;
   if (st.work_cap / nchunk < 64) nchunk = 1;
@@ -336,14 +342,14 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
   }
   int* const work_base = st.nwork;
   const int cap_total = st.work_cap;
-  const int cap_c = (cap_total - 2 * (nchunk - 1)) / nchunk;  // items per chunk slice (each slice has its own 2-word header)
+  const int cap_c = (cap_total - 4 * (nchunk - 1)) / nchunk;  // items per chunk slice (each slice has its own 4-word header)
   for (int c = 0; c < nchunk; ++c) {
     cudaStream_t cs = s;
     if (nchunk > 1) { cs = b->cs[c]; DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_fork, 0)); }
     st.env0 = (int)((long long)b->nenv * c / nchunk);
     st.nenv = (int)((long long)b->nenv * (c + 1) / nchunk);
-    st.nwork = work_base + (size_t)c * (2 + 2 * (size_t)cap_c);
-    st.work = st.nwork + 2;
+    st.nwork = work_base + (size_t)c * (4 + 2 * (size_t)cap_c);
+    st.work = st.nwork + 4;
     st.work_cap = cap_c;
     const int n = st.nenv - st.env0;
     const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -363,7 +369,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
         { ProfScope ps(b, 5, cs); k_narrow<T><<<ngrid, kNarrowBlock, 0, cs>>>(m, st); b->launches++; }
         { ProfScope ps(b, 6, cs); k_compact<T><<<grid, kWarpsPerBlock * 32, 0, cs>>>(m, st); b->launches++; }
       }
-      if (dynamics) { ProfScope ps(b, 2, cs); k_dynamics<T><<<grid, kWarpsPerBlock * 32, smem2, cs>>>(m, st, dbg, integrate); b->launches++; }
+      if (dynamics) { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate); b->launches++; }
     }
     if (nchunk > 1) { DEX_CUDA(cudaEventRecord(b->ev_join[c], cs)); DEX_CUDA(cudaStreamWaitEvent(s, b->ev_join[c], 0)); }
   }

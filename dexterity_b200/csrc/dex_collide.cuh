@@ -794,7 +794,10 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
 // K1c: staging slots -> contact list in slot order (warp per env).
 template <typename T>
 DEX_DEV void dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
-  if (st.skip && st.skip[env]) return;  // warp-uniform
+  if (st.skip && st.skip[env]) {   // warp-uniform; a skipped env still needs its place in K2's processing order
+    if (st.order && dex_lane() == 0) st.order[st.nenv - 1 - dex_atomic_add_ret(st.nwork + 3, 1)] = env;
+    return;
+  }
   const int lane = dex_lane();
   const int nslot = st.nslot[env];
   const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
@@ -819,7 +822,15 @@ DEX_DEV void dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int 
   }
   if (dex_ballot(overflow)) { if (lane == 0) st.status[env] |= DEX_STATUS_CON_OVERFLOW; }
   if (ncon > DEX_MAXCON) ncon = DEX_MAXCON;
-  if (lane == 0) st.ncon[env] = ncon;
+  if (lane == 0) {
+    st.ncon[env] = ncon;
+    // K2's processing order: the solver's cost grows with the contact count, so envs with contacts go first and the
+    // kernel does not end on a few long-running warps (r01n: the SMs idle 14 % of K2's duration)
+    if (st.order) {
+      if (ncon >= 2) st.order[st.env0 + dex_atomic_add_ret(st.nwork + 2, 1)] = env;
+      else st.order[st.nenv - 1 - dex_atomic_add_ret(st.nwork + 3, 1)] = env;
+    }
+  }
   (void)m;
 }
 

@@ -52,7 +52,7 @@ enum DexFieldId {
   DEX_FIELD_DBG_QACC = 11,     /* real [nenv][nv]         optional: data.qacc                       */
   DEX_FIELD_DBG_QFRC_CONSTRAINT = 12, /* real [nenv][nv]  optional                                  */
   DEX_FIELD_DBG_EFC = 13,      /* real [nenv][DEX_MAXCON][8] optional: per-contact D, aref[4], mu, imp, R */
-  DEX_FIELD_COUNT = 32
+  DEX_FIELD_COUNT = 40
 };
 
 /* Compiled-capacity constants (also exported through dex_capacity for ctypes users). */
@@ -142,7 +142,8 @@ enum DexTaskFieldId {
   DEX_FIELD_TREE = 30,         /* real [nenv][8][32] scratch: cdof (rows 0-5), qfrc_smooth (row 6), tree reference points (row 7) */
   DEX_FIELD_STAGE = 31,        /* real [nenv][64][8] scratch: contact staging slots of the collision kernels               */
   DEX_FIELD_NSLOT = 17,        /* i32  [nenv]        scratch: staging slots in use                                        */
-  DEX_FIELD_WORK = 23          /* i32  [2 + 2*cap]   scratch: narrowphase work list: item count, fetch cursor, then (env, slot<<24|pair)
+  DEX_FIELD_ORDER = 32,        /* i32  [nenv]        optional scratch: the solver's processing order (envs with contacts first)          */
+  DEX_FIELD_WORK = 23          /* i32  [4 + 2*cap]   scratch: narrowphase work list: item count, fetch cursor, 2 order counters, then (env, slot<<24|pair)
                                   pairs; bind with row_stride = cap (the capacity in items, >= nenv * 8 recommended)     */
 };
 
