@@ -115,7 +115,7 @@ class PhysicsBatch:
             STATUS=z(n, dt=torch.int32), CONTACT=z(n, maxcon, cstride), NCON=z(n, dt=torch.int32),
             NITER=z(n, dt=torch.int32), JC=torch.empty(n, 3 * maxcon, 32, dtype=dtype, device=dev),
             MSCR=z(n, 32, 32), XKIN=z(n, capacity(3) * 16), TREE=z(n, 8 * 32), STAGE=z(n, 64, 8),
-            NSLOT=z(n, dt=torch.int32), ORDER=z(n, dt=torch.int32))
+            NSLOT=z(n, dt=torch.int32), ORDER=z(8, n, dt=torch.int32))
         if debug:
             self._store.update(DBG_M=z(n, c.nv * c.nv), DBG_QFRC_SMOOTH=z(n, c.nv), DBG_QACC=z(n, c.nv),
                                DBG_QFRC_CONSTRAINT=z(n, c.nv), DBG_EFC=z(n, maxcon, 8))
@@ -123,7 +123,7 @@ class PhysicsBatch:
             self.bind(name, t)
         # global narrowphase work list: item count, fetch cursor, then (env, slot << 24 | pair) per item
         cap = max(32 * n, 4096)
-        work = z(4 + 2 * cap, dt=torch.int32)
+        work = z(16 + 2 * cap, dt=torch.int32)
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
         self.set_chunks(int(os.environ.get("DEX_CHUNKS", "1")))

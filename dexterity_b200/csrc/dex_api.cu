@@ -36,12 +36,15 @@ constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 #ifndef DEX_K2_MINB
 #define DEX_K2_MINB 5
 #endif
+#ifndef DEX_K2_CTAS
+#define DEX_K2_CTAS 22   // resident single-warp CTAs of K2 per SM (register bound 65536 / (22 * 32) = 93; measured 18: 0.449, 20: 0.451, 22: 0.421, 24: 0.432 ms)
+#endif
 
 constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps spread over all SMs
 template <typename T>
 __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {
   const int env = st.env0 + blockIdx.x * kTreeBlock + threadIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; st.nwork[2] = 0; st.nwork[3] = 0; }  // work items, fetch cursor, order counters
+  if (blockIdx.x == 0 && threadIdx.x == 0) { for (int k = 0; k < DEX_WORK_HDR; ++k) st.nwork[k] = 0; }  // work items, fetch cursor, order counters
   if (env >= st.nenv) return;
   dex_tree_env<T>(m, st, env);
 }
@@ -57,7 +60,7 @@ template <typename T>
 __global__ void __launch_bounds__(kTreeWarps * 32) k_tree8(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st.nwork[0] = 0; st.nwork[1] = 0; st.nwork[2] = 0; st.nwork[3] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { for (int k = 0; k < DEX_WORK_HDR; ++k) st.nwork[k] = 0; }
   const int env_base = st.env0 + (blockIdx.x * kTreeWarps + warp) * DEX_K0_ENVS;
   if (env_base >= st.nenv) return;
   dex_tree_warp<T>(m, st, env_base, reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K0_SMEM_T);
@@ -119,13 +122,18 @@ __global__ void __launch_bounds__(kCollideWarps * 32, DEX_K1_MINB * kWarpsPerBlo
 #endif
 constexpr int kDynWarps = DEX_K2_WARPS;
 template <typename T>
-__global__ void __launch_bounds__(kDynWarps * 32, DEX_K2_MINB * DEX_WARPS_PER_BLOCK / DEX_K2_WARPS) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
+__global__ void __launch_bounds__(kDynWarps * 32, DEX_K2_CTAS / DEX_K2_WARPS) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
                                                                    int integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int slot = st.env0 + blockIdx.x * kDynWarps + warp;
   if (slot >= st.nenv) return;
-  const int env = st.order ? st.order[slot] : slot;   // K1c's heavy-first order
+  int env = slot;
+  if (st.order) {   // K1c's lists, heaviest class first
+    int s = slot - st.env0, c = 0;
+    while (c < DEX_NCLASS - 1 && s >= st.nwork[2 + c]) { s -= st.nwork[2 + c]; ++c; }
+    env = st.order[(size_t)c * st.order_stride + st.env0 + s];
+  }
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
 }
@@ -291,9 +299,11 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.stage = (T*)b->ptr[DEX_FIELD_STAGE];
   st.nslot = (int*)b->ptr[DEX_FIELD_NSLOT];
   st.nwork = (int*)b->ptr[DEX_FIELD_WORK];
-  st.work = st.nwork + 4;
+  st.work = st.nwork + DEX_WORK_HDR;
   st.work_cap = (int)b->stride[DEX_FIELD_WORK];
   st.order = (int*)b->ptr[DEX_FIELD_ORDER];
+  st.order_stride = (int)b->stride[DEX_FIELD_ORDER];
+  if (st.order && st.order_stride < b->nenv) return fail(DEX_E_ARG, "DEX_FIELD_ORDER must be [8][row_stride >= num_envs]");
   if (st.work_cap < 1) return fail(DEX_E_ARG, "DEX_FIELD_WORK must be bound with row_stride = capacity in items");
   dbg.M = (T*)b->ptr[DEX_FIELD_DBG_M];
   dbg.qfrc_smooth = (T*)b->ptr[DEX_FIELD_DBG_QFRC_SMOOTH];
@@ -342,14 +352,14 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
   }
   int* const work_base = st.nwork;
   const int cap_total = st.work_cap;
-  const int cap_c = (cap_total - 4 * (nchunk - 1)) / nchunk;  // items per chunk slice (each slice has its own 4-word header)
+  const int cap_c = (cap_total - DEX_WORK_HDR * (nchunk - 1)) / nchunk;  // items per chunk slice (each slice has its own header)
   for (int c = 0; c < nchunk; ++c) {
     cudaStream_t cs = s;
     if (nchunk > 1) { cs = b->cs[c]; DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_fork, 0)); }
     st.env0 = (int)((long long)b->nenv * c / nchunk);
     st.nenv = (int)((long long)b->nenv * (c + 1) / nchunk);
-    st.nwork = work_base + (size_t)c * (4 + 2 * (size_t)cap_c);
-    st.work = st.nwork + 4;
+    st.nwork = work_base + (size_t)c * (DEX_WORK_HDR + 2 * (size_t)cap_c);
+    st.work = st.nwork + DEX_WORK_HDR;
     st.work_cap = cap_c;
     const int n = st.nenv - st.env0;
     const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;

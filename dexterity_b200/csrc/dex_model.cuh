@@ -92,8 +92,9 @@ struct BatchState {
   T* stage;                       // [nenv][DEX_MAXSLOT][8] contact staging slots of K1a / K1b (pair < 0 = no contact)
   int* nslot;                     // [nenv] staging slots in use
   int* work;                      // [work_cap][2] global narrowphase work list: env, slot << 24 | pair
-  int* nwork;                     // [4] work items, fetch cursor of K1b, envs in the heavy / light end of `order` (zeroed by K0 every mj_step)
-  int* order;                     // optional [nenv]: K2 processing order written by K1c, envs with >= 2 contacts first (null = identity)
+  int* nwork;                     // [8] work items, fetch cursor of K1b, envs per solver-cost class (zeroed by K0 every mj_step)
+  int* order;                     // optional [4][order_stride]: env lists per solver-cost class written by K1c (null = identity order)
+  int order_stride;
   int work_cap;
   T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
 };

@@ -142,8 +142,8 @@ enum DexTaskFieldId {
   DEX_FIELD_TREE = 30,         /* real [nenv][8][32] scratch: cdof (rows 0-5), qfrc_smooth (row 6), tree reference points (row 7) */
   DEX_FIELD_STAGE = 31,        /* real [nenv][64][8] scratch: contact staging slots of the collision kernels               */
   DEX_FIELD_NSLOT = 17,        /* i32  [nenv]        scratch: staging slots in use                                        */
-  DEX_FIELD_ORDER = 32,        /* i32  [nenv]        optional scratch: the solver's processing order (envs with contacts first)          */
-  DEX_FIELD_WORK = 23          /* i32  [4 + 2*cap]   scratch: narrowphase work list: item count, fetch cursor, 2 order counters, then (env, slot<<24|pair)
+  DEX_FIELD_ORDER = 32,        /* i32  [8][nenv]     optional scratch: env lists per solver-cost class (K2 processes the heaviest first)  */
+  DEX_FIELD_WORK = 23          /* i32  [16 + 2*cap]  scratch: narrowphase work list: item count, fetch cursor, class counters, then (env, slot<<24|pair)
                                   pairs; bind with row_stride = cap (the capacity in items, >= nenv * 8 recommended)     */
 };
 

@@ -126,11 +126,11 @@ struct EmuModel {
 // compaction (warp).  The work list is private to the calling worker thread.
 template <typename T>
 static void emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
-  std::vector<int> work(4 + 2 * DEX_MAXSLOT, 0);
+  std::vector<int> work(DEX_WORK_HDR + 2 * DEX_MAXSLOT, 0);
   BatchState<T> sl = st;
-  sl.nwork = work.data(); sl.work = work.data() + 4; sl.work_cap = DEX_MAXSLOT; sl.order = nullptr;
+  sl.nwork = work.data(); sl.work = work.data() + DEX_WORK_HDR; sl.work_cap = DEX_MAXSLOT; sl.order = nullptr;
   dex_emu::run_warp([&]() { dex_collide_env<T>(m, sl, env, smem); });
-  for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[4 + 2 * i], work[5 + 2 * i]);  // K1b is thread-per-item
+  for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[DEX_WORK_HDR + 2 * i], work[DEX_WORK_HDR + 1 + 2 * i]);  // K1b is thread-per-item
   dex_emu::run_warp([&]() { dex_compact_env<T>(m, sl, env); });
 }
 
@@ -225,13 +225,13 @@ int emu_run_steps(void* mp, int dtype, int nenv, void* qpos, int qpos_stride, vo
   if (dtype == 0) {
     BatchState<float> st = {nenv, 0, (float*)qpos, qpos_stride, (float*)qvel, qvel_stride, (float*)ctrl, ctrl_stride,
                             (float*)warm, warm_stride, (float*)time, status, (float*)contact, ncon, niter, nullptr, (float*)jc, (float*)mscr,
-                            (float*)xkin, (float*)stage, nslot, nullptr, nullptr, nullptr, 0, (float*)tree};
+                            (float*)xkin, (float*)stage, nslot, nullptr, nullptr, nullptr, 0, 0, (float*)tree};
     DynDebug<float> dbg = {(float*)dbg_M, (float*)dbg_fs, (float*)dbg_qacc, (float*)dbg_fc, (float*)dbg_efc};
     emu_run<float>(m->f.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   } else {
     BatchState<double> st = {nenv, 0, (double*)qpos, qpos_stride, (double*)qvel, qvel_stride, (double*)ctrl, ctrl_stride,
                              (double*)warm, warm_stride, (double*)time, status, (double*)contact, ncon, niter, nullptr, (double*)jc, (double*)mscr,
-                             (double*)xkin, (double*)stage, nslot, nullptr, nullptr, nullptr, 0, (double*)tree};
+                             (double*)xkin, (double*)stage, nslot, nullptr, nullptr, nullptr, 0, 0, (double*)tree};
     DynDebug<double> dbg = {(double*)dbg_M, (double*)dbg_fs, (double*)dbg_qacc, (double*)dbg_fc, (double*)dbg_efc};
     emu_run<double>(m->d.dev, st, dbg, nsub, integrate, do_collide, do_dynamics, nthreads);
   }
@@ -250,7 +250,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
                         (int)stride[DEX_FIELD_QACC_WARMSTART], (T*)f[DEX_FIELD_TIME], (unsigned*)f[DEX_FIELD_STATUS],
                         (T*)f[DEX_FIELD_CONTACT], (int*)f[DEX_FIELD_NCON], (int*)f[DEX_FIELD_NITER],
                         (const unsigned char*)f[DEX_FIELD_SKIP], (T*)f[DEX_FIELD_JC], (T*)f[DEX_FIELD_MSCR],
-                        (T*)f[DEX_FIELD_XKIN], (T*)f[DEX_FIELD_STAGE], (int*)f[DEX_FIELD_NSLOT], nullptr, nullptr, nullptr, 0,
+                        (T*)f[DEX_FIELD_XKIN], (T*)f[DEX_FIELD_STAGE], (int*)f[DEX_FIELD_NSLOT], nullptr, nullptr, nullptr, 0, 0,
                         (T*)f[DEX_FIELD_TREE]};
     TaskState<T> ts = {(const T*)f[DEX_FIELD_ACTION], (int)stride[DEX_FIELD_ACTION], (T*)f[DEX_FIELD_OBS], (T*)f[DEX_FIELD_REWARD],
                        (T*)f[DEX_FIELD_DISCOUNT], (T*)f[DEX_FIELD_GOAL], (int*)f[DEX_FIELD_TASK_I], (T*)f[DEX_FIELD_TASK_F],

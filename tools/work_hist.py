@@ -13,7 +13,7 @@ for it in range(30):
     env.step(lo + (hi - lo) * torch.rand(N, 20, device=env.device))
     if it % 10 == 9:
         w = env.physics.tensor("WORK").cpu().numpy()
-        n = int(w[0]); items = w[4:4 + 2 * n].reshape(n, 2)
+        n = int(w[0]); items = w[16:16 + 2 * n].reshape(n, 2)
         pair = items[:, 1] & 0xffffff
         box = gt[g1[pair]] == 6
         na = np.where(box, 0, vn[g1[pair]]); nb = vn[g2[pair]]

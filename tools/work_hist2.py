@@ -37,7 +37,7 @@ def segdist(p1, q1, p2, q2):
     return np.linalg.norm(c1 - c2, axis=1)
 for it in range(20):
     env.step(lo + (hi - lo) * torch.rand(N, 20, device=env.device))
-w = env.physics.tensor("WORK").cpu().numpy(); n = int(w[0]); items = w[4:4 + 2 * n].reshape(n, 2)
+w = env.physics.tensor("WORK").cpu().numpy(); n = int(w[0]); items = w[16:16 + 2 * n].reshape(n, 2)
 envi = items[:, 0]; pair = items[:, 1] & 0xffffff; slot = items[:, 1] >> 24
 stage = env.physics.tensor("STAGE").cpu().numpy()
 hit = stage[envi, slot, 7] >= 0
