@@ -30,8 +30,8 @@ NUM_ENVS_PER_GPU = 16384          # BASELINE.json configs[2] / configs[4] (13107
 B_ENV = 1364                      # algorithmic bytes per env-step, SURVEY.md §8(d) / BASELINE.md §3
 B_MJ = 808                        # algorithmic bytes per mj_step (state round trip)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 envs from the `ncu --set full` capture summarised in
-# profiles/r01n_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
-NCU_TRAFFIC_BYTES = {"k_dynamics": 87.43e6 + 4.87e6, "k_tree": 46.17e6 + 70.50e6}
+# profiles/r01q_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
+NCU_TRAFFIC_BYTES = {"k_dynamics": 91.72e6 + 7.63e6, "k_tree": 46.78e6 + 70.31e6}
 METRIC = "env-steps/sec, Shadow-hand cube reorient"
 UNIT = "env-steps/s"
 
