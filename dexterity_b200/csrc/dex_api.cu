@@ -98,11 +98,23 @@ __global__ void __launch_bounds__(kNarrowBlock, DEX_NARROW_MINB) k_narrow(DevMod
   }
 }
 
+constexpr int kCompactWarps = 8;
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_compact(DevModel<T> m, BatchState<T> st) {
-  const int env = st.env0 + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (env >= st.nenv) return;
-  dex_compact_env<T>(m, st, env);
+__global__ void __launch_bounds__(kCompactWarps * 32) k_compact(DevModel<T> m, BatchState<T> st) {
+  __shared__ int cnt[DEX_NCLASS], base[DEX_NCLASS];
+  const int lane = threadIdx.x & 31;
+  const int env = st.env0 + blockIdx.x * kCompactWarps + (threadIdx.x >> 5);
+  if (threadIdx.x < DEX_NCLASS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int cls = env < st.nenv ? dex_compact_env<T>(m, st, env) : -1;
+  if (!st.order) return;   // uniform over the grid
+  // file the env in its class list: ranks within the CTA from a shared-memory counter, one global atomic per class
+  int rank = 0;
+  if (lane == 0 && cls >= 0) rank = atomicAdd(&cnt[cls], 1);
+  __syncthreads();
+  if (threadIdx.x < DEX_NCLASS && cnt[threadIdx.x] > 0) base[threadIdx.x] = atomicAdd(st.nwork + 2 + threadIdx.x, cnt[threadIdx.x]);
+  __syncthreads();
+  if (lane == 0 && cls >= 0) st.order[(size_t)cls * st.order_stride + st.env0 + base[cls] + rank] = env;
 }
 
 // K1a: one warp (= one env) per CTA: envs differ a lot in surviving pairs, single-warp CTAs retire independently
@@ -362,7 +374,6 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
     st.work = st.nwork + DEX_WORK_HDR;
     st.work_cap = cap_c;
     const int n = st.nenv - st.env0;
-    const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int tgrid = (n + kTreeBlock - 1) / kTreeBlock;
     const int t8grid = (n + kTreeWarps * DEX_K0_ENVS - 1) / (kTreeWarps * DEX_K0_ENVS);
     const size_t smem0 = (size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T);
@@ -377,7 +388,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
       if (collide) {
         { ProfScope ps(b, 1, cs); k_collide<T><<<(n + kCollideWarps - 1) / kCollideWarps, kCollideWarps * 32, smem1, cs>>>(m, st); b->launches++; }
         { ProfScope ps(b, 5, cs); k_narrow<T><<<ngrid, kNarrowBlock, 0, cs>>>(m, st); b->launches++; }
-        { ProfScope ps(b, 6, cs); k_compact<T><<<grid, kWarpsPerBlock * 32, 0, cs>>>(m, st); b->launches++; }
+        { ProfScope ps(b, 6, cs); k_compact<T><<<(n + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, cs>>>(m, st); b->launches++; }
       }
       if (dynamics) { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate); b->launches++; }
     }

@@ -794,12 +794,11 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
 }
 
 // K1c: staging slots -> contact list in slot order (warp per env).
+// Returns the env's solver-cost class (0 = heaviest) for K2's processing order; the kernel wrapper files the env in
+// the class list (one global atomic per class and CTA).
 template <typename T>
-DEX_DEV void dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
-  if (st.skip && st.skip[env]) {   // warp-uniform; a skipped env still needs its place in K2's processing order
-    if (st.order && dex_lane() == 0) st.order[(size_t)(DEX_NCLASS - 1) * st.order_stride + st.env0 + dex_atomic_add_ret(st.nwork + 2 + DEX_NCLASS - 1, 1)] = env;
-    return;
-  }
+DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
+  if (st.skip && st.skip[env]) return DEX_NCLASS - 1;   // warp-uniform; a skipped env still needs its place in the order
   const int lane = dex_lane();
   const int nslot = st.nslot[env];
   const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
@@ -824,24 +823,15 @@ DEX_DEV void dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int 
   }
   if (dex_ballot(overflow)) { if (lane == 0) st.status[env] |= DEX_STATUS_CON_OVERFLOW; }
   if (ncon > DEX_MAXCON) ncon = DEX_MAXCON;
-  if (lane == 0) {
-    st.ncon[env] = ncon;
-    // K2's processing order: the solver's cost grows with the contact count, so envs with contacts go first and the
-    // kernel does not end on a few long-running warps (r01n: the SMs idle 14 % of K2's duration)
-    if (st.order) {   // one env list per predicted-cost class, K2 walks them heaviest first.  The predictor is the Newton
-      // iteration count of the env's previous mj_step (contacts persist), but at least contacts + 2 (mean iterations
-      // measured per contact count: 2.4, 3.5, 4.4, 5.2, 5.9, ...)
-#ifdef DEX_ORDER_BY_NITER
-      int key = st.niter ? st.niter[env] : 0;
-      key = key > ncon + 2 ? key : ncon + 2;
-#else
-      const int key = ncon + 2;
-#endif
-      const int cls = key >= 9 ? 0 : (9 - key > DEX_NCLASS - 1 ? DEX_NCLASS - 1 : 9 - key);
-      st.order[(size_t)cls * st.order_stride + st.env0 + dex_atomic_add_ret(st.nwork + 2 + cls, 1)] = env;
-    }
-  }
+  if (lane == 0) st.ncon[env] = ncon;
+  // K2's processing order: the solver's cost grows with the contact count (mean Newton iterations per contact count:
+  // 2.4, 3.5, 4.4, 5.2, 5.9, ...), so envs with contacts go first and the kernel does not end on a few long-running
+  // warps (r01n: the SMs idled 14 % of K2's duration).  Keying on the previous step's iteration count instead was
+  // slower: envs with equal contact counts also share code paths and cache lines.
+  const int key = ncon + 2;
+  const int cls = key >= 9 ? 0 : (9 - key > DEX_NCLASS - 1 ? DEX_NCLASS - 1 : 9 - key);
   (void)m;
+  return cls;
 }
 
 #endif  // DEX_COLLIDE_CUH_
