@@ -31,7 +31,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #endif
 constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 #ifndef DEX_K1_MINB
-#define DEX_K1_MINB 4
+#define DEX_K1_MINB 5
 #endif
 #ifndef DEX_K2_MINB
 #define DEX_K2_MINB 5
