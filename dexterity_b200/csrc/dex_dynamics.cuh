@@ -173,8 +173,16 @@ DEX_DEV_NOINLINE T dex_chol_apply(const T* H, int n, T inv_mine, T b) {
 template <typename T>
 DEX_DEV_NOINLINE T dex_chol_load(T* H, const T* Mg, int n) {
   const int lane = dex_lane();
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j) H[j * DEX_MSTRIDE + lane] = (lane < j && j < n) ? Mg[j * 32 + lane] : T(0);
+  // four rows per trip: lane = (row within the group, 4-column group); one 16-byte load and one 16-byte store per lane
+  const int r = lane >> 3, c4 = (lane & 7) << 2;
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += 4) {
+    const int j = j0 + r;
+    DexVec4<T> v = {T(0), T(0), T(0), T(0)};
+    if (j < n) v = *reinterpret_cast<const DexVec4<T>*>(Mg + j * 32 + c4);
+    v.x = c4 < j ? v.x : T(0); v.y = c4 + 1 < j ? v.y : T(0); v.z = c4 + 2 < j ? v.z : T(0); v.w = c4 + 3 < j ? v.w : T(0);
+    *reinterpret_cast<DexVec4<T>*>(H + j * DEX_MSTRIDE + c4) = v;
+  }
   return lane < n ? Mg[lane * 32 + lane] : T(1);
 }
 // y_i = sum_j M[j][i] x_j (M symmetric) with M in the env's global scratch (rows of 32, read coalesced

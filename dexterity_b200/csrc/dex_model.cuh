@@ -117,7 +117,11 @@ template <> struct Real<double> {
 template <typename T> DEX_DEV T dx_sqrt(T x) { return sqrt(x); }
 // reciprocal square root: one MUFU.RSQ (+ one Newton step) in FP32 instead of IEEE sqrt + divide
 #if defined(__CUDACC__)
-DEX_DEV float dx_rsqrt(float x) { float r = rsqrtf(x); return r * (1.5f - 0.5f * x * r * r); }
+DEX_DEV float dx_rsqrt(float x) {   // callers pass normal, positive x: the bare MUFU.RSQ (no denormal rescaling) + one Newton step
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * (1.5f - 0.5f * x * r * r);
+}
 DEX_DEV double dx_rsqrt(double x) { return 1.0 / sqrt(x); }
 #else
 template <typename T> inline T dx_rsqrt(T x) { return T(1) / std::sqrt(x); }
