@@ -158,6 +158,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_task_pre(DevModel<T> m,
   dex_task_pre_env<T>(m, st, ts, p, env, force_reset);
 }
 
+// one rejection round of the collision-checked prop placement (dex_place_env)
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_place(DevModel<T> m, BatchState<T> st, TaskState<T> ts, DexTaskParams p) {
+  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (env >= st.nenv) return;
+  dex_place_env<T>(m, st, ts, p, env);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_task_post(DevModel<T> m, BatchState<T> st, TaskState<T> ts,
                                                                     DexTaskParams p) {
@@ -304,6 +312,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.ncon = (int*)b->ptr[DEX_FIELD_NCON];
   st.niter = (int*)b->ptr[DEX_FIELD_NITER];
   st.skip = use_skip ? (const unsigned char*)b->ptr[DEX_FIELD_SKIP] : nullptr;
+  st.skip_mode = 0;
   st.jc = (T*)b->ptr[DEX_FIELD_JC];
   st.mscr = (T*)b->ptr[DEX_FIELD_MSCR];
   st.xkin = (T*)b->ptr[DEX_FIELD_XKIN];
@@ -430,6 +439,19 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int block = kWarpsPerBlock * 32;
   if (phases & 1) { ProfScope ps(b, 0, s); k_task_pre<T><<<grid, block, 0, s>>>(m, st, ts, b->task, force_reset); b->launches++; }
+  if ((phases & 1) && b->task.task == DEX_TASK_REORIENT && b->task.place_max_attempts > 0) {
+    // PropPlacer's rejection loop for the envs reset above: collision kernels on those envs only, then one accept /
+    // redraw decision per env and round.  Envs that are placed drop out; the launches of later rounds find no work.
+    BatchState<T> sp = st;
+    sp.skip_mode = 1;
+    for (int r = 0; r < b->task.place_max_attempts; ++r) {
+      rc = launch_physics<T>(b, m, sp, dbg, 1, true, false, 0, s);
+      if (rc) return rc;
+      ProfScope ps(b, 7, s);
+      k_place<T><<<grid, block, 0, s>>>(m, sp, ts, b->task);
+      b->launches++;
+    }
+  }
   if ((phases & 2) && !force_reset) {
     rc = launch_physics<T>(b, m, st, dbg, nsub, true, true, 1, s);
     if (rc) return rc;
@@ -556,6 +578,7 @@ int dex_task_configure(DexBatch* b, const DexTaskParams* p) {
     if (p->prop_body <= 0 || p->prop_body >= h.nbody || p->prop_geom < 0 || p->prop_geom >= h.ngeom ||
         p->ground_geom < 0 || p->ground_geom >= h.ngeom) return fail(DEX_E_ARG, "bad prop/ground ids");
     if (3 * p->nhand + 6 * p->nsite + 21 > DEX_OBS_STRIDE) return fail(DEX_E_ARG, "observation does not fit");
+    if (p->place_max_attempts < 0 || p->place_max_attempts > 200) return fail(DEX_E_ARG, "place_max_attempts must be in 0..200");
   }
   b->task = *p;
   b->task_set = true;

@@ -519,7 +519,7 @@ DEX_DEV bool dex_obb_overlap(const Xf<T>& rel, const T* pk1, const T* pk2, T mar
 
 template <typename T>
 DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
-  if (env >= st.nenv || (st.skip && st.skip[env])) return;  // warp-uniform
+  if (env >= st.nenv || dex_env_off(st, env)) return;  // warp-uniform
   const int lane = dex_lane();
   T* xpos = smem;
   T* xmat = xpos + DEX_MAXBODY * 3;
@@ -798,7 +798,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
 // the class list (one global atomic per class and CTA).
 template <typename T>
 DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
-  if (st.skip && st.skip[env]) return DEX_NCLASS - 1;   // warp-uniform; a skipped env still needs its place in the order
+  if (dex_env_off(st, env)) return DEX_NCLASS - 1;   // warp-uniform; a skipped env still needs its place in the order
   const int lane = dex_lane();
   const int nslot = st.nslot[env];
   const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;

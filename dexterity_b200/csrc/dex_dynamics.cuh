@@ -214,7 +214,7 @@ DEX_DEV_NOINLINE void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
 template <typename T>
 DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int env,
                               T* smem, int integrate) {
-  if (env >= st.nenv || (st.skip && st.skip[env])) { return; }  // warp-uniform
+  if (env >= st.nenv || dex_env_off(st, env)) { return; }  // warp-uniform
   const int lane = dex_lane();
   const int nv = m.nv;
   T* ref = smem + DEX_K2_OFF_REF;

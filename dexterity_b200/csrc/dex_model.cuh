@@ -24,6 +24,7 @@
 #define DEX_STATUS_CAND_OVERFLOW 4u
 #define DEX_STATUS_SOLVER_MAXITER 8u
 #define DEX_STATUS_CHOL_FAIL 16u
+#define DEX_STATUS_PLACEMENT 32u   // no collision-free prop pose within DexTaskParams::place_max_attempts (dm_control PropPlacer raises)
 
 enum { DEX_JNT_FREE = 0, DEX_JNT_BALL = 1, DEX_JNT_SLIDE = 2, DEX_JNT_HINGE = 3 };
 enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_BOX = 6, DEX_GEOM_MESH = 7 };
@@ -97,7 +98,16 @@ struct BatchState {
   int order_stride;
   int work_cap;
   T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
+  int skip_mode;                  // which envs a launch works on (see dex_env_off): 0 = those with skip == 0, 1 = those being placed (skip >= 2)
 };
+
+// skip[env]: 0 = stepping normally, 1 = reset during this call (physics leaves it alone), 2 + k = reset and its prop pose is
+// still being collision-checked, k rejected poses so far (the rounds of dex_place_env, dex_task.cuh).
+template <typename T> DEX_DEV bool dex_env_off(const BatchState<T>& st, int env) {
+  if (!st.skip) return false;
+  const unsigned char s = st.skip[env];
+  return st.skip_mode ? s < 2 : s != 0;
+}
 
 // ---------------------------------------------------------------------------------------
 // math helpers

@@ -111,7 +111,7 @@ DEX_DEV void dex_task_pre_env(const DevModel<T>& m, const BatchState<T>& st, con
       ti[TI_GOAL_CHANGED] = 1; ti[TI_FAILURE] = 0; ti[TI_EPISODE_LEN] = 0;
       tf[TF_SOLVE_START] = 0; tf[TF_RETURN] = 0;
       rng[2] = ctr + 3;
-      ts.skip[env] = 1;
+      ts.skip[env] = (p.task == DEX_TASK_REORIENT && p.place_max_attempts > 0) ? 2 : 1;   // 2: pose still to be collision-checked
     }
   } else {
     // GoalTask.before_step (task.py:154-165)
@@ -133,6 +133,55 @@ DEX_DEV void dex_task_pre_env(const DevModel<T>& m, const BatchState<T>& st, con
     }
     // MujocoEffector.set_control: ctrl <- command (unclipped, as upstream stores it)
     if (lane < m.nu) st.ctrl[(size_t)env * st.ctrl_stride + lane] = ts.action[(size_t)env * ts.action_stride + lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Collision-checked prop placement (dm_control initializers.PropPlacer as configured in reference
+// reorient.py:143-151: ignore_collisions=False, settle_physics=False, max_attempts_per_prop=20).
+// One rejection round for an env whose skip byte is >= 2: the collision kernels have just run on the
+// sampled pose (BatchState::skip_mode = 1); if the prop touches anything (a contact with dist <= 0
+// that involves one of its geoms, or a full contact buffer, which upstream treats as a rejected
+// pose too) a new position and orientation are drawn, else the env is marked placed (skip = 1).
+// After place_max_attempts rejected poses PropPlacer raises; here the env gets DEX_STATUS_PLACEMENT
+// and the post-step ends its episode at once, so that the next call draws again.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+DEX_DEV void dex_place_env(const DevModel<T>& m, const BatchState<T>& st, const TaskState<T>& ts,
+                           const DexTaskParams& p, int env) {
+  const int s = ts.skip[env];   // warp-uniform
+  if (s < 2) return;
+  const int lane = dex_lane();
+  int ncon = st.ncon[env];
+  if (ncon > DEX_MAXCON) ncon = DEX_MAXCON;
+  const T* cin = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
+  bool hit = (st.status[env] & (DEX_STATUS_CON_OVERFLOW | DEX_STATUS_CAND_OVERFLOW)) != 0;
+  for (int c = lane; c < ncon; c += 32) {
+    const T* cc = cin + c * DEX_CON_STRIDE;
+    const int pr = (int)cc[7];
+    const int b1 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr)), b2 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr));
+    hit = hit || ((b1 == p.prop_body || b2 == p.prop_body) && cc[0] <= 0);
+  }
+  hit = dex_ballot(hit) != 0;
+  unsigned* rng = ts.rng + (size_t)env * 4;
+  const unsigned ctr = rng[2];
+  dex_syncwarp();
+  if (!hit) { if (lane == 0) ts.skip[env] = 1; return; }
+  if (s - 1 >= p.place_max_attempts) {
+    if (lane == 0) { st.status[env] |= DEX_STATUS_PLACEMENT; ts.skip[env] = 1; }
+    return;
+  }
+  T u1[4], u2[4], pq[4];
+  dex_rand4<T>(rng, env, ctr, u1);
+  dex_rand4<T>(rng, env, ctr + 1, u2);
+  dex_uniform_quat(u1, pq);
+  T* qp = st.qpos + (size_t)env * st.qpos_stride + p.prop_qposadr;
+  if (lane < 3) qp[lane] = (T)p.spawn_lo[lane] + ((T)p.spawn_hi[lane] - (T)p.spawn_lo[lane]) * u2[lane];
+  else if (lane < 7) qp[lane] = pq[lane - 3];
+  if (lane == 0) {
+    rng[2] = ctr + 2;
+    st.status[env] &= ~(DEX_STATUS_CON_OVERFLOW | DEX_STATUS_CAND_OVERFLOW);   // they described the rejected pose
+    ts.skip[env] = (unsigned char)(s + 1);
   }
 }
 
@@ -287,7 +336,7 @@ DEX_DEV void dex_task_post_env(const DevModel<T>& m, const BatchState<T>& st, co
     ti[TI_FAILURE] = failure ? 1 : 0;
     const bool solved = successes >= p.successes_needed;
     const bool timeout = p.has_max_time && exceeded;
-    const bool physics_error = (status & DEX_STATUS_BADQACC) != 0;
+    const bool physics_error = (status & (DEX_STATUS_BADQACC | DEX_STATUS_PLACEMENT)) != 0;
     const bool over_time = time >= (T)p.time_limit;
     const bool terminate = solved || timeout || failure || physics_error || over_time;
     T reward, discount;

@@ -101,7 +101,7 @@ DEX_DEV void dex_body_fk(const DevModel<T>& m, const T* qpos, int b, int ja, int
 
 template <typename T>
 DEX_DEV void dex_tree_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
-  if (st.skip && st.skip[env]) return;
+  if (dex_env_off(st, env)) return;
   const int nv = m.nv, nb = m.nbody;
   T qpos[48], qvel[DEX_MAXDOF];
   for (int i = 0; i < m.nq; ++i) qpos[i] = st.qpos[(size_t)env * st.qpos_stride + i];
@@ -308,7 +308,8 @@ template <typename T>
 DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int env_base, T* smem) {
   const int lane = dex_lane(), gl = lane & (DEX_K0_G - 1), ge = lane / DEX_K0_G;
   const int env = env_base + ge;
-  const bool live = env < st.nenv && !(st.skip && st.skip[env]);   // dead groups compute on a valid env and write nothing
+  const bool live = env < st.nenv && !dex_env_off(st, env < st.nenv ? env : st.nenv - 1);   // dead groups compute on a valid env and write nothing
+  if (!dex_ballot(live)) return;   // nothing to do for any of the warp's envs (common in the placement rounds)
   const int envr = env < st.nenv ? env : st.nenv - 1;
   T* sm = smem + ge * DEX_K0_ENV_T;
   T* own = sm + DEX_K0_OFF_OWN;

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from dexterity_b200 import backend
+from dexterity_b200 import placement
 from dexterity_b200.model import scenes
 
 FIRST, MID, LAST = 0, 1, 2
@@ -47,7 +48,7 @@ class TaskParams(ctypes.Structure):
         ("prop_body", ctypes.c_int), ("prop_qposadr", ctypes.c_int), ("prop_dofadr", ctypes.c_int),
         ("prop_geom", ctypes.c_int), ("ground_geom", ctypes.c_int),
         ("nhand", ctypes.c_int), ("nsite", ctypes.c_int), ("site_id", ctypes.c_int * 5),
-        ("dense_reward", ctypes.c_int), ("pad0", ctypes.c_int),
+        ("dense_reward", ctypes.c_int), ("place_max_attempts", ctypes.c_int),
         ("success_threshold", ctypes.c_double), ("max_time_per_goal", ctypes.c_double), ("time_limit", ctypes.c_double),
         ("spawn_lo", ctypes.c_double * 3), ("spawn_hi", ctypes.c_double * 3),
         ("w_orientation", ctypes.c_double), ("w_success_bonus", ctypes.c_double), ("w_action_smoothing", ctypes.c_double),
@@ -99,7 +100,11 @@ class BatchedGoalEnvironment:
 
     def __init__(self, task_name: str, num_envs: int, seed: Optional[int] = None, device: int = 0,
                  dtype: torch.dtype = torch.float32, time_limit: Optional[float] = None,
-                 fall_termination: bool = True, dense_reward: bool = True) -> None:
+                 fall_termination: bool = True, dense_reward: bool = True, prop_spawn_bbox=None,
+                 place_max_attempts: Optional[int] = None) -> None:
+        """`prop_spawn_bbox` = (lower, upper) overrides the reference's spawn box (reorient.py:72-78).
+        `place_max_attempts`: draws of the collision-checked prop placement (PropPlacer); None = decide from a static
+        clearance proof of the spawn box (dexterity_b200/placement.py): 0 when no draw can collide, else 20."""
         if task_name not in ("reorient", "reach"):
             raise ValueError(f"Unknown task: {task_name}")
         self.task_name = task_name
@@ -159,8 +164,13 @@ class BatchedGoalEnvironment:
             j = c.joint_names.index("prop/")
             p.prop_body, p.prop_qposadr, p.prop_dofadr = pb, int(c.JNT_QPOSADR[j]), int(c.JNT_DOFADR[j])
             p.prop_geom, p.ground_geom = c.geom_names.index("prop/geom"), c.geom_names.index("ground")
+            spawn_lo, spawn_hi = prop_spawn_bbox if prop_spawn_bbox is not None else (cfg["spawn_lo"], cfg["spawn_hi"])
             for k in range(3):
-                p.spawn_lo[k], p.spawn_hi[k] = cfg["spawn_lo"][k], cfg["spawn_hi"][k]
+                p.spawn_lo[k], p.spawn_hi[k] = spawn_lo[k], spawn_hi[k]
+            if place_max_attempts is None:
+                place_max_attempts = placement.place_max_attempts(c, pb, spawn_lo, spawn_hi)
+            p.place_max_attempts = int(place_max_attempts)
+            self.place_max_attempts = p.place_max_attempts
             for k in ("w_orientation", "w_success_bonus", "w_action_smoothing", "orientation_eps", "bonus_threshold"):
                 setattr(p, k, cfg[k])
             layout["prop/position"] = slice(o, o + 3)

@@ -112,7 +112,10 @@ typedef struct DexTaskParams {
   int nsite;                      // fingertip sites (<= 5)
   int site_id[5];
   int dense_reward;               // reach only
-  int pad0;
+  int place_max_attempts;         // reorient: collision-checked prop placement at episode start (dm_control
+                                  // initializers.PropPlacer, reorient.py:143-151): poses rejected while the prop is in
+                                  // contact, up to this many draws (PropPlacer default 20); 0 = not checked (the caller
+                                  // has proven the spawn region contact-free, dexterity_b200/placement.py)
   double success_threshold;       // reorient.py:52 / reach.py:50
   double max_time_per_goal;       // reorient.py:68
   double time_limit;              // manipulation/__init__.py:83 (inf if None)

@@ -264,6 +264,20 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
       for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {
         const int e1 = std::min(hi, e0 + DEX_K0_ENVS);
         for (int env = e0; env < e1; ++env) dex_emu::run_warp([&]() { dex_task_pre_env<T>(dev, sb, ts, *p, env, force_reset); });
+        if (p->task == DEX_TASK_REORIENT && p->place_max_attempts > 0) {   // PropPlacer rejection rounds (dex_place_env)
+          BatchState<T> sp = sb;
+          sp.skip_mode = 1;
+          for (int r = 0; r < p->place_max_attempts; ++r) {
+            bool any = false;
+            for (int env = e0; env < e1; ++env) any = any || ts.skip[env] >= 2;
+            if (!any) break;   // the GPU path launches the remaining rounds on no work
+            emu_tree<T>(dev, sp, e0, smem.data());
+            for (int env = e0; env < e1; ++env) {
+              emu_collide<T>(dev, sp, env, smem.data());
+              dex_emu::run_warp([&]() { dex_place_env<T>(dev, sp, ts, *p, env); });
+            }
+          }
+        }
         if (!force_reset) for (int s = 0; s < nsub; ++s) {
           emu_tree<T>(dev, sb, e0, smem.data());
           for (int env = e0; env < e1; ++env) {

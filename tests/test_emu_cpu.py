@@ -125,3 +125,49 @@ def test_task_kernels_against_restatement(reorient_model, emu_model):
             fallen = bool((d.contacts()["geom"] == [c.geom_names.index("ground"), c.geom_names.index("prop/geom")]).all(axis=1).any()) \
                 if len(d.contacts()["dist"]) else False
             assert (a["TASK_I"][e, 6] == 2) == (m_.should_terminate_episode() or fallen)
+
+
+def test_prop_placement_rejects_colliding_poses(reorient_model, emu_model):
+    """dm_control PropPlacer semantics (reference reorient.py:143-151) on the device code path, run by the emulator:
+    with a spawn box that reaches into the hand, every accepted pose is contact-free according to the ORACLE, poses are
+    redrawn inside the box, and envs whose draws all collide are flagged and end their episode at the next step."""
+    c = reorient_model
+    p = _params(c)
+    p.spawn_lo[2], p.spawn_hi[2] = 0.09, 0.16           # reaches down into the palm / fingers
+    p.place_max_attempts = 20
+    n = 24
+    env = E.EmuEnv(emu_model, p, nenv=n, dtype=np.float64, seed=3)
+    env.reset()
+    a = env.a
+    assert (a["SKIP"] == 1).all()                        # every env left the placement loop
+    om = orc.OracleModel(c); d = orc.OracleData(om)
+    prop = c.geom_names.index("prop/geom")
+    flagged = (a["STATUS"] & 32) != 0
+    redrawn = a["RNG"][:, 2] > 3                         # 3 counters are used by the reset itself, 2 more per redraw
+    assert redrawn.any() and not flagged.all()
+    for e in range(n):
+        q = a["QPOS"][e, :31]
+        assert (q[24:27] >= [p.spawn_lo[0], p.spawn_lo[1], p.spawn_lo[2]]).all() and (q[24:27] <= [p.spawn_hi[0], p.spawn_hi[1], p.spawn_hi[2]]).all()
+        assert abs(np.linalg.norm(q[27:31]) - 1) < 1e-12
+        d.set_state(q, np.zeros(30), np.zeros(20), np.zeros(30)); d.forward()
+        ct = d.contacts()
+        touching = bool(len(ct["dist"]) and ((ct["geom"] == prop).any(axis=1) & (ct["dist"] <= 0)).any())
+        assert touching == bool(flagged[e]), (e, touching, flagged[e])
+    # the static proof (dexterity_b200/placement.py) agrees: this box is not provably clear, the reference's is
+    from dexterity_b200 import placement
+    pb = c.body_names.index("prop/")
+    assert placement.place_max_attempts(c, pb, list(p.spawn_lo), list(p.spawn_hi)) == 20
+    from dexterity_b200 import envs
+    assert placement.place_max_attempts(c, pb, envs.REORIENT["spawn_lo"], envs.REORIENT["spawn_hi"]) == 0
+    assert placement.spawn_clearance(c, pb, envs.REORIENT["spawn_lo"], envs.REORIENT["spawn_hi"]) > 0.01
+
+
+def test_reference_spawn_box_never_collides(reorient_model):
+    """The clearance proof's claim, sampled: no reset pose of the reference's spawn box is in contact (oracle)."""
+    c = reorient_model
+    om = orc.OracleModel(c); d = orc.OracleData(om)
+    rng = np.random.RandomState(5)
+    from tests import statelib
+    for _ in range(300):
+        d.set_state(statelib.reorient_reset(c, rng), np.zeros(30), np.zeros(20), np.zeros(30)); d.forward()
+        assert len(d.contacts()["dist"]) == 0

@@ -149,3 +149,42 @@ def test_action_noise_wrapper_clips():
     env.step(hi.expand(32, 20).clone())
     ctrl = env.physics.ctrl
     assert (ctrl <= hi + 1e-6).all() and (ctrl < hi - 1e-4).any()
+
+
+def test_collision_checked_prop_placement(reorient_model):
+    """PropPlacer semantics (reference reorient.py:143-151) on the GPU: a spawn box that reaches into the hand is not
+    provably clear, so the rejection rounds run; every env that is not flagged holds a pose the FP64 oracle finds
+    contact-free, flagged envs (20 colliding draws) end their episode on the next step.  The reference's own box is
+    provably clear and launches no rounds."""
+    from dexterity_b200 import envs
+    c = reorient_model
+    ref_env = envs.load("reorient", "state_dense", seed=1, num_envs=64)
+    assert ref_env.place_max_attempts == 0
+    n0 = ref_env.physics.launch_count
+    ref_env.reset()
+    assert ref_env.physics.launch_count - n0 == 2          # pre + post only
+    lo, hi = (-0.025, -0.155, 0.09), (0.025, -0.105, 0.16)
+    env = envs.BatchedGoalEnvironment("reorient", 512, seed=7, prop_spawn_bbox=(lo, hi))
+    assert env.place_max_attempts == 20
+    env.reset()
+    torch.cuda.synchronize()
+    assert (env._skip == 1).all()
+    qpos = env.physics.qpos.cpu().numpy().astype(np.float64)[:, :31]
+    flagged = (env.physics.status.cpu().numpy() & 32) != 0
+    redraws = (env._rng[:, 2].cpu().numpy() - 3) // 2
+    assert redraws.max() >= 1 and redraws.max() <= 19 and not flagged.all()
+    assert (qpos[:, 24:27] >= np.array(lo) - 1e-6).all() and (qpos[:, 24:27] <= np.array(hi) + 1e-6).all()
+    om = orc.OracleModel(c); d = orc.OracleData(om)
+    prop = c.geom_names.index("prop/geom")
+    mismatches = 0
+    for e in range(0, 512, 4):
+        d.set_state(qpos[e], np.zeros(30), np.zeros(20), np.zeros(30)); d.forward()
+        ct = d.contacts()
+        near = bool(len(ct["dist"]) and ((ct["geom"] == prop).any(axis=1) & (np.abs(ct["dist"]) < 1e-5)).any())
+        touching = bool(len(ct["dist"]) and ((ct["geom"] == prop).any(axis=1) & (ct["dist"] <= 0)).any())
+        if not near:                                        # FP32 vs FP64 may differ on a grazing contact
+            mismatches += touching != bool(flagged[e])
+    assert mismatches == 0
+    act = torch.zeros(512, 20, device=env.device)
+    ts = env.step(act)
+    assert (ts.step_type.cpu().numpy()[flagged] == 2).all()
