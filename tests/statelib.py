@@ -139,3 +139,26 @@ def mpr_stable_mask(compiled, states: Dict[str, np.ndarray], eps: float = 1e-7, 
                 stable[e] = False
                 break
     return stable
+
+
+def many_contact_states(compiled, seed: int, nstates: int, lo_con: int = 9, hi_con: int = 28) -> Dict[str, np.ndarray]:
+    """Static states with lo_con..hi_con contacts (a half-closed hand around a cube pushed into the palm): far
+    more contacts than the random-action rollouts visit (one on average)."""
+    rng = np.random.RandomState(seed)
+    om = orc.OracleModel(compiled)
+    d = orc.OracleData(om)
+    lo, hi = compiled.JNT_RANGE[:24, 0], compiled.JNT_RANGE[:24, 1]
+    out = dict(qpos=[], qvel=[], ctrl=[], warm=[])
+    while len(out["qpos"]) < nstates:
+        q = reorient_reset(compiled, rng)
+        f = rng.uniform(0.25, 0.6)
+        q[2:24] = lo[2:] + (hi[2:] - lo[2:]) * np.clip(f + 0.1 * rng.randn(22), 0, 1)
+        q[24:27] = [rng.uniform(-0.02, 0.02), rng.uniform(-0.14, -0.10), rng.uniform(0.10, 0.14)]
+        v = 0.1 * rng.randn(compiled.nv)
+        d.set_state(q, v, np.zeros(compiled.nu), np.zeros(compiled.nv))
+        d.forward()
+        ct = d.contacts()
+        if lo_con <= len(ct["dist"]) <= hi_con and (np.abs(ct["dist"]) > 1e-5).all():
+            out["qpos"].append(q); out["qvel"].append(v)
+            out["ctrl"].append(rng.uniform(compiled.ACT_CTRLRANGE[:, 0], compiled.ACT_CTRLRANGE[:, 1])); out["warm"].append(np.zeros(compiled.nv))
+    return {k: np.array(v) for k, v in out.items()}

@@ -197,3 +197,37 @@ def test_unbound_or_bad_calls_fail_loudly(reorient_model):
     b = backend.PhysicsBatch(model, 4)
     with pytest.raises(backend.DexError):
         backend._check(backend.lib().dex_mj_step(b.ptr, 0, None))
+
+
+def test_many_contact_states(reorient_model):
+    """9..28 contacts per env (the rollout states average one): FP64 validation build and FP32 against the oracle on
+    the states whose MPR portals agree (cube faces pressed flat on hull faces make most of these states tie-dependent)."""
+    from dexterity_b200 import backend
+    from oracle import oracle as orc
+    compiled = reorient_model
+    st = statelib.many_contact_states(compiled, seed=21, nstates=48)
+    ref = statelib.oracle_step(compiled, st, nsub=1)
+    model = backend.PhysicsModel(compiled, 0)
+    om = orc.OracleModel(compiled); d = orc.OracleData(om)
+    frames = []
+    for e in range(48):
+        d.set_state(st["qpos"][e], st["qvel"][e], st["ctrl"][e], st["warm"][e]); d.forward()
+        ct = d.contacts()
+        frames.append((ct["dist"], ct["frame"][:, 0]))
+    for dtype, tol_con, tol in ((torch.float64, 1e-9, 1e-7), (torch.float32, 2e-5, REL_TOL_F32)):
+        b = backend.PhysicsBatch(model, 48, dtype)
+        statelib.upload(b, st)
+        b.collide()
+        torch.cuda.synchronize()
+        con = b.contact.cpu().numpy().astype(np.float64)
+        ncon = b.ncon.cpu().numpy()
+        assert (ncon == ref["ncon"]).all() and ncon.min() > 8
+        same = np.array([np.abs(con[e, :ncon[e], 4:7] - frames[e][1]).max() < tol_con and
+                         np.abs(con[e, :ncon[e], 0] - frames[e][0]).max() < tol_con for e in range(48)])
+        assert same.sum() >= 8, same.sum()
+        b = _run(model, st, dtype)
+        assert (b.status.cpu().numpy() & 1 == 0).all()
+        ev = relerr(b.qvel.cpu().numpy().astype(np.float64)[:, :30], ref["qvel"])
+        eq = relerr(b.qpos.cpu().numpy().astype(np.float64)[:, :31], ref["qpos"])
+        assert (eq[same] <= tol).all(), (dtype, eq[same].max())
+        assert (ev[same] <= tol).mean() >= (1.0 if dtype == torch.float64 else 0.8), (dtype, np.sort(ev[same])[-5:])
