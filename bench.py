@@ -30,8 +30,8 @@ NUM_ENVS_PER_GPU = 16384          # BASELINE.json configs[2] / configs[4] (13107
 B_ENV = 1364                      # algorithmic bytes per env-step, SURVEY.md §8(d) / BASELINE.md §3
 B_MJ = 808                        # algorithmic bytes per mj_step (state round trip)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 envs from the `ncu --set full` capture summarised in
-# profiles/r01q_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
-NCU_TRAFFIC_BYTES = {"k_dynamics": 91.72e6 + 7.63e6, "k_tree": 46.78e6 + 70.31e6}
+# profiles/r01r_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
+NCU_TRAFFIC_BYTES = {"k_dynamics": 91.96e6 + 7.90e6, "k_tree": 46.87e6 + 69.16e6}   # profiles/r01r_summary.md (ncu --set full, per launch)
 METRIC = "env-steps/sec, Shadow-hand cube reorient"
 UNIT = "env-steps/s"
 
@@ -44,7 +44,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML polled every 5 ms from a thread
+    (the region is ~100 ms at the default step count), `nvidia-smi -lms` as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -52,17 +53,60 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.proc, self.lines, self.gpu = None, [], gpu_index
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, False
+        self.sm, self.smax, self.reasons = [], [], set()
+
+    def _nvml_loop(self):
+        N = self.nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(N, a, None) or getattr(N, b, 0)) for n, a, b in names]
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.handle, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.handle))
+                for n, b in bits:
+                    if b and (r & int(b)):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as N
+            import torch
+            N.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                self.handle = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                self.handle = N.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = [float(N.nvmlDeviceGetMaxClockInfo(self.handle, N.NVML_CLOCK_SM))]
+            self.nvml = N
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.smax) if self.smax else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +125,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_arm(steps: int, warmup: int, bounded_seconds: float = 14.0):
