@@ -178,7 +178,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_gpu(args):
@@ -303,9 +303,30 @@ def run_gpu(args):
             "clocks": clocks,
             "episode_stats": stats, "physics_errors_in_batch": nbad, "wall_s": wall,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def capture_stdout():
+    """The driver reads ONE JSON line from stdout, but libraries write there too (NCCL prints its version banner on
+    stdout at the first collective): point fd 1 at stderr for the whole run and keep the real stdout for emit()."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -318,6 +339,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
