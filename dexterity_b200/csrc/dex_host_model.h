@@ -265,7 +265,10 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       double* G = &M.geom_mat[9 * g];
       q2m(&gq[4 * g], G);
       int t = M.geom_type[g];
-      if (t != DEX_GEOM_PLANE && t != DEX_GEOM_BOX && t != DEX_GEOM_MESH) return "unsupported geom type (plane/box/mesh only)";
+      // spheres and capsules may be present (e.g. the Adroit hand) as long as no candidate pair names them: the pair
+      // check below rejects every pair type without a narrowphase
+      if (t != DEX_GEOM_PLANE && t != DEX_GEOM_BOX && t != DEX_GEOM_MESH && t != DEX_GEOM_SPHERE && t != DEX_GEOM_CAPSULE)
+        return "unsupported geom type";
       if (t == DEX_GEOM_MESH) {
         M.geom_vertadr[g] = (int)(M.vert.size() / 4);
         for (int i = 0; i < vn[g]; ++i) {

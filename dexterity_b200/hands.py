@@ -10,14 +10,17 @@ import torch
 
 
 class DexterousHand:
-    def __init__(self, compiled, prefix: str = "shadow_hand_e/") -> None:
+    def __init__(self, compiled, prefix: str = "shadow_hand_e/", fingertip_sites=None) -> None:
         c = compiled
         self.compiled, self.prefix = c, prefix
         self.joint_ids = [i for i, n in enumerate(c.joint_names) if n.startswith(prefix)]
         self.joint_names = tuple(c.joint_names[i][len(prefix):] for i in self.joint_ids)
         self.actuator_ids = [i for i, n in enumerate(c.actuator_names) if n.startswith(prefix)]
         self.actuator_names = tuple(c.actuator_names[i][len(prefix):] for i in self.actuator_ids)
-        self.fingertip_site_ids = [i for i, n in enumerate(c.site_names) if n.startswith(prefix) and n.endswith("tip_site")]
+        if fingertip_sites is None:
+            self.fingertip_site_ids = [i for i, n in enumerate(c.site_names) if n.startswith(prefix) and n.endswith("tip_site")]
+        else:   # explicit names, in the reference's order (e.g. adroit_hand_constants.py:86-92)
+            self.fingertip_site_ids = [c.site_names.index(prefix + n) for n in fingertip_sites]
         nj, na = len(self.joint_ids), len(self.actuator_ids)
         jpos = {j: k for k, j in enumerate(self.joint_ids)}
         # actuator -> joints it drives (a tendon actuator drives every joint of its fixed tendon)

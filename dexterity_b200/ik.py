@@ -34,13 +34,18 @@ _PROGRESS_THRESHOLD = 20.0
 class IKSolver:
     """Inverse kinematics solver for a dexterous hand (private kinematic model, like the reference)."""
 
-    def __init__(self, hand: Optional[hands.DexterousHand] = None, device: int = 0, seed: int = 0) -> None:
-        compiled = scenes.load_compiled("shadow_hand_only")
-        self.hand = hand or hands.DexterousHand(compiled)
+    def __init__(self, hand: Optional[hands.DexterousHand] = None, device: int = 0, seed: int = 0,
+                 hand_name: str = "shadow_hand_e") -> None:
+        """`hand_name`: "shadow_hand_e" or "adroit_hand" (reference models/hands/{shadow_hand_e,adroit_hand}.py)."""
+        if hand_name not in scenes.HANDS:
+            raise ValueError(f"Unknown hand: {hand_name}")
+        asset, prefix, tips = scenes.HANDS[hand_name]
+        compiled = scenes.load_compiled(asset)
+        self.hand = hand or hands.DexterousHand(compiled, prefix, tips)
         self.compiled = compiled
         self.model = backend.PhysicsModel(compiled, device)
         self.device = torch.device("cuda", device)
-        self._sites = [compiled.site_names.index(f"shadow_hand_e/{t}_site") for t in scenes.SHADOW_FINGERTIPS]
+        self._sites = [compiled.site_names.index(prefix + t) for t in tips]
         self._seed = seed
         self._calls = 0
         lib = backend.lib()

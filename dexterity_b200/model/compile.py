@@ -440,9 +440,13 @@ def compile_model(model: mjcf.Model, timestep: float, nconmax: int = 64,
 
     # tendons / actuators
     jid_of = {n: i for i, n in enumerate(jnames)}
-    tnames = [t.name for t in model.tendons]
+    # fixed tendons that are neither limited nor the transmission of an actuator only produce `ten_length`, which
+    # nothing on the path reads (the Adroit hand has 44 of them): they are not compiled
+    used = {a.tendon for a in model.actuators if a.tendon}
+    tendons = [t for t in model.tendons if t.limited or t.name in used]
+    tnames = [t.name for t in tendons]
     tadr, tnum, wj, wc = [], [], [], []
-    for t in model.tendons:
+    for t in tendons:
         tadr.append(len(wj))
         tnum.append(len(t.joints))
         for jn, c in t.joints:
@@ -450,11 +454,11 @@ def compile_model(model: mjcf.Model, timestep: float, nconmax: int = 64,
             wc.append(c)
     nt = len(tnames)
     A["TEN_ADR"], A["TEN_NUM"] = np.array(tadr, np.int32), np.array(tnum, np.int32)
-    A["TEN_LIMITED"] = np.array([int(t.limited) for t in model.tendons], np.int32)
-    A["TEN_RANGE"] = np.array([t.range for t in model.tendons], np.float64).reshape(nt, 2)
-    A["TEN_MARGIN"] = np.array([t.margin for t in model.tendons], np.float64)
-    A["TEN_SOLREF"] = np.array([t.solreflimit for t in model.tendons], np.float64).reshape(nt, 2)
-    A["TEN_SOLIMP"] = np.array([t.solimplimit for t in model.tendons], np.float64).reshape(nt, 5)
+    A["TEN_LIMITED"] = np.array([int(t.limited) for t in tendons], np.int32)
+    A["TEN_RANGE"] = np.array([t.range for t in tendons], np.float64).reshape(nt, 2)
+    A["TEN_MARGIN"] = np.array([t.margin for t in tendons], np.float64)
+    A["TEN_SOLREF"] = np.array([t.solreflimit for t in tendons], np.float64).reshape(nt, 2)
+    A["TEN_SOLIMP"] = np.array([t.solimplimit for t in tendons], np.float64).reshape(nt, 5)
     A["WRAP_JNT"], A["WRAP_COEF"] = np.array(wj, np.int32), np.array(wc, np.float64)
     tid_of = {n: i for i, n in enumerate(tnames)}
     acts = model.actuators

@@ -121,10 +121,39 @@ def shadow_hand_only() -> compile_lib.CompiledModel:
     return compile_lib.compile_model(scene.model, timestep=0.002, nconmax=48)
 
 
+# reference models/hands/adroit_hand_constants.py:86-92 (sites that exist in adroit_hand.xml)
+ADROIT_FINGERTIP_SITES = ("S_fftip", "S_mftip", "S_rftip", "S_lftip", "S_thtip")
+
+
+def adroit_hand_only() -> compile_lib.CompiledModel:
+    """The Adroit hand's own root model (reference models/hands/adroit_hand.py:17-29): the physics of
+    `IKSolver(AdroitHand())` and of the golden fingertip test reference models/hands/hands_test.py:195-228.
+    KINEMATICS ONLY: the 19 explicit `<contact><pair>` elements of adroit_hand.xml:231-251 (capsule-capsule and
+    box-capsule, condim 1) are not compiled (no such narrowphase in this build yet), which IK does not need; the 44
+    fixed tendons are neither limited nor actuated (the `limited` default sits in a class no tendon uses) and are dropped."""
+    scene = mjcf.Scene(mjcf.Model("ik", mjcf.Body("world", np.zeros(3), np.array([1.0, 0, 0, 0]), None),
+                                  {}, [], [], [], [], {}, {}))
+    hand = mjcf.load(_paths()["adroit"], name="adroit_hand")
+    mjcf._prefix_model(hand, "adroit_hand/")
+    scene.model.world.children = hand.world.children
+    scene.model.meshes = hand.meshes
+    scene.model.tendons, scene.model.actuators = hand.tendons, hand.actuators
+    scene.model.excludes = hand.excludes
+    scene.model.option = hand.option
+    return compile_lib.compile_model(scene.model, timestep=0.002, nconmax=48)
+
+
 _BUILDERS = {
     "reorient_shadow": reorient_scene,
     "reach_shadow": reach_shadow_scene,
     "shadow_hand_only": shadow_hand_only,
+    "adroit_hand_only": adroit_hand_only,
+}
+
+# hand name -> (hand-only compiled model, name prefix, fingertip site names)
+HANDS = {
+    "shadow_hand_e": ("shadow_hand_only", "shadow_hand_e/", tuple(t + "_site" for t in SHADOW_FINGERTIPS)),
+    "adroit_hand": ("adroit_hand_only", "adroit_hand/", ADROIT_FINGERTIP_SITES),
 }
 
 

@@ -84,3 +84,53 @@ def test_kernel_body_restarts_and_unreachable(setup):
         x, _ = ik_oracle.site_positions(c.arrays, q[i, :24].astype(np.float64), sites)
         assert np.linalg.norm(x - targets[i].reshape(5, 3), axis=1).max() <= 1e-3 + 1e-5
         assert (q[i, :24] >= c.JNT_RANGE[:, 0] - 1e-6).all() and (q[i, :24] <= c.JNT_RANGE[:, 1] + 1e-6).all()
+
+
+# reference models/hands/hands_test.py:195-228: golden fingertip positions of the Adroit hand (its own root model),
+# which IKSolver must reach within 1e-3 and FK must reproduce at the solution
+ADROIT_GOLDEN_FINGERTIPS = np.asarray([
+    [-0.003572, -0.020904, 0.371999],
+    [-0.028277, -0.036063, 0.391271],
+    [-0.052305, -0.006066, 0.393481],
+    [-0.089808, -0.042816, 0.423813],
+    [0.026246, -0.017261, 0.416314],
+])
+
+
+@pytest.fixture(scope="module")
+def adroit():
+    asset, prefix, tips = scenes.HANDS["adroit_hand"]
+    c = scenes.load_compiled(asset)
+    h = hands.DexterousHand(c, prefix, tips)
+    return c, h, h.fingertip_site_ids
+
+
+def test_adroit_model_facts(adroit):
+    """reference models/hands/adroit_hand_constants.py: 24 joints, 24 actuators (fully actuated), 5 fingertip sites."""
+    c, h, sites = adroit
+    assert (c.nq, c.nv, c.nu, len(sites)) == (24, 24, 24, 5)
+    assert h.joint_names[:3] == ("WRJ1", "WRJ0", "FFJ3") and h.joint_names[-1] == "THJ0"
+    assert h.actuator_names[0] == "A_WRJ1" and not h.underactuated
+    assert np.array_equal(h.POSITION_TO_CONTROL, np.eye(24))          # ctrl = qpos (adroit_hand.py:97-113)
+
+
+def test_adroit_golden_fingertips_restatement(adroit):
+    """The reference's golden vector through the numpy restatement of its solver."""
+    c, h, sites = adroit
+    q = ik_oracle.solve(c.arrays, sites, ADROIT_GOLDEN_FINGERTIPS, linear_tol=1e-3, early_stop=True,
+                        stop_on_first_successful_attempt=True, random_state=np.random.RandomState(0))
+    assert q is not None
+    x, _ = ik_oracle.site_positions(c.arrays, q, sites)
+    np.testing.assert_allclose(x, ADROIT_GOLDEN_FINGERTIPS, atol=1e-3)
+    assert (q >= c.JNT_RANGE[:, 0] - 1e-12).all() and (q <= c.JNT_RANGE[:, 1] + 1e-12).all()
+
+
+def test_adroit_golden_fingertips_kernel_body(adroit):
+    """The same golden vector through the k_ik kernel body (emulated), FP64 and FP32."""
+    c, h, sites = adroit
+    em = E.EmuModel(c)
+    for dtype in (np.float64, np.float32):
+        q, ok, attempts = E.emu_ik(em, _params(sites), ADROIT_GOLDEN_FINGERTIPS.reshape(1, 15), dtype=dtype)
+        assert ok[0]
+        x, _ = ik_oracle.site_positions(c.arrays, q[0, :24].astype(np.float64), sites)
+        np.testing.assert_allclose(x, ADROIT_GOLDEN_FINGERTIPS, atol=1e-3)
