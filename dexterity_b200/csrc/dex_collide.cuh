@@ -573,28 +573,44 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   //      compacted, then the bodies' AABBs as oriented boxes on dense lanes (r01d: 273 -> 61 -> 13 pairs)
   const T slack = T(1e-6);   // world-frame centres carry FP32 rounding: keep every cull conservative
   int nbp = 0;
-  for (int bp0 = 0; bp0 < m.nbodypair; bp0 += 32) {
-    const int bp = bp0 + lane;
-    bool pass = false;
-    if (bp < m.nbodypair) {
-      const int b1 = dex_ldg(m.bp_body1 + bp), b2 = dex_ldg(m.bp_body2 + bp);
-      const T r1 = bsph[4 * b1 + 3], r2 = bsph[4 * b2 + 3];
-      if (r1 < 0) {  // body 1 owns a plane (planes sort first in a pair): half-space test of body 2's sphere
-        const int gp = dex_ldg(m.pair_geom1 + dex_ldg(m.bp_pairadr + bp));
-        const T* G = m.geom_mat + 9 * gp;
-        T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
-        rot_vec(n, xmat + 9 * b1, nl);
-        T d[3] = {bsph[4 * b2] - gsph[4 * gp], bsph[4 * b2 + 1] - gsph[4 * gp + 1], bsph[4 * b2 + 2] - gsph[4 * gp + 2]};
-        pass = dot3(d, n) <= r2 + slack;
-      } else {
-        T d[3] = {bsph[4 * b2] - bsph[4 * b1], bsph[4 * b2 + 1] - bsph[4 * b1 + 1], bsph[4 * b2 + 2] - bsph[4 * b1 + 2]};
-        const T bound = r1 + r2 + slack;
-        pass = dot3(d, d) <= bound * bound;
-      }
+  // three chunks of 32 body pairs per trip, their body ids requested up front (same reason as in the geom-pair pass below)
+  for (int bp0 = 0; bp0 < m.nbodypair; bp0 += 96) {
+    int b1s[3], b2s[3];
+    bool ps[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int bp = bp0 + 32 * q + lane;
+      b1s[q] = b2s[q] = 0;
+      if (bp < m.nbodypair) { b1s[q] = dex_ldg(m.bp_body1 + bp); b2s[q] = dex_ldg(m.bp_body2 + bp); }
     }
-    const unsigned mk = dex_ballot(pass);
-    if (pass) cand[nbp + dex_popc(mk & ((1u << lane) - 1u))] = bp;   // nbodypair <= DEX_MAXCAND1 (host check)
-    nbp += dex_popc(mk);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int bp = bp0 + 32 * q + lane;
+      bool pass = false;
+      if (bp < m.nbodypair) {
+        const int b1 = b1s[q], b2 = b2s[q];
+        const T r1 = bsph[4 * b1 + 3], r2 = bsph[4 * b2 + 3];
+        if (r1 < 0) {  // body 1 owns a plane (planes sort first in a pair): half-space test of body 2's sphere
+          const int gp = dex_ldg(m.pair_geom1 + dex_ldg(m.bp_pairadr + bp));
+          const T* G = m.geom_mat + 9 * gp;
+          T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
+          rot_vec(n, xmat + 9 * b1, nl);
+          T d[3] = {bsph[4 * b2] - gsph[4 * gp], bsph[4 * b2 + 1] - gsph[4 * gp + 1], bsph[4 * b2 + 2] - gsph[4 * gp + 2]};
+          pass = dot3(d, n) <= r2 + slack;
+        } else {
+          T d[3] = {bsph[4 * b2] - bsph[4 * b1], bsph[4 * b2 + 1] - bsph[4 * b1 + 1], bsph[4 * b2 + 2] - bsph[4 * b1 + 2]};
+          const T bound = r1 + r2 + slack;
+          pass = dot3(d, d) <= bound * bound;
+        }
+      }
+      ps[q] = pass;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const unsigned mk = dex_ballot(ps[q]);
+      if (ps[q]) cand[nbp + dex_popc(mk & ((1u << lane) - 1u))] = bp0 + 32 * q + lane;   // nbodypair <= DEX_MAXCAND1 (host check)
+      nbp += dex_popc(mk);
+    }
   }
   dex_syncwarp();
   int nbpl = 0;
@@ -626,10 +642,11 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
   //      (cheap, mostly rejects); survivors are compacted so that the costlier AABB / OBB tests of pass 2 run on
   //      dense lanes (r01d: 900 pairs visited per env, 86 survive the spheres, 7 survive everything)
   int ncand = 0;
+  int adr_n = 0, num_n = 0, b1_n = 0;   // header of the next body pair, requested one trip ahead
+  if (nbpl > 0) { const int k = bpl[0]; adr_n = dex_ldg(m.bp_pairadr + k); num_n = dex_ldg(m.bp_pairnum + k); b1_n = dex_ldg(m.bp_body1 + k); }
   for (int bi = 0; bi < nbpl; ++bi) {
-    const int bpk = bpl[bi];
-    const int adr = dex_ldg(m.bp_pairadr + bpk), num = dex_ldg(m.bp_pairnum + bpk);
-    const int b1 = dex_ldg(m.bp_body1 + bpk);
+    const int adr = adr_n, num = num_n, b1 = b1_n;
+    if (bi + 1 < nbpl) { const int k = bpl[bi + 1]; adr_n = dex_ldg(m.bp_pairadr + k); num_n = dex_ldg(m.bp_pairnum + k); b1_n = dex_ldg(m.bp_body1 + k); }
     const bool plane = bsph[4 * b1 + 3] < 0;
     // DEX_K1_NCH chunks of 32 pairs per trip: all chunks' pair words are requested before any is used, so the dependent
     // global load -> shared-memory lookups of one chunk overlap those of the others (2: 0.158 -> 0.154 ms per launch)
