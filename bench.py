@@ -30,8 +30,8 @@ NUM_ENVS_PER_GPU = 16384          # BASELINE.json configs[2] / configs[4] (13107
 B_ENV = 1364                      # algorithmic bytes per env-step, SURVEY.md §8(d) / BASELINE.md §3
 B_MJ = 808                        # algorithmic bytes per mj_step (state round trip)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 envs from the `ncu --set full` capture summarised in
-# profiles/r01r_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
-NCU_TRAFFIC_BYTES = {"k_dynamics": 91.96e6 + 7.90e6, "k_tree": 46.87e6 + 69.16e6}   # profiles/r01r_summary.md (ncu --set full, per launch)
+# profiles/r01s_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size)
+NCU_TRAFFIC_BYTES = {"k_dynamics": 91.96e6 + 9.20e6, "k_tree": 46.87e6 + 69.16e6}   # profiles/r01s_summary.md (ncu --set full, per launch)
 METRIC = "env-steps/sec, Shadow-hand cube reorient"
 UNIT = "env-steps/s"
 
