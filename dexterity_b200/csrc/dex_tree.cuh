@@ -381,10 +381,12 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
   T pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   T vel[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
   const int nround = m.k0_rounds;
+  int recn[4];   // the next round's schedule record is requested one round ahead
+  dex_ldg_int4(m.k0_rec + gl * 8, recn);
   for (int r = 0; r < nround; ++r) {
     // schedule record of this (round, lane): body, parent's lane, joints (adr | num << 16), tree id
-    int rec[4];
-    dex_ldg_int4(m.k0_rec + (r * DEX_K0_G + gl) * 8, rec);
+    const int rec[4] = {recn[0], recn[1], recn[2], recn[3]};
+    if (r + 1 < nround) dex_ldg_int4(m.k0_rec + ((r + 1) * DEX_K0_G + gl) * 8, recn);
     const int b = rec[0], src = rec[1], ja = rec[2] & 0xffff, jn = rec[2] >> 16, btree = rec[3];
     const int sl = (lane & ~(DEX_K0_G - 1)) | (src < 0 ? gl : src);
     T ppos[3], pquat[4], pmat[9], v[6], a[6];
@@ -473,9 +475,10 @@ DEX_DEV void dex_tree_warp(const DevModel<T>& m, const BatchState<T>& st, int en
     dex_syncwarp();
   }
   // ---- backward rounds: a body's slot holds its subtree totals once all deeper rounds are done
+  dex_ldg_int4(m.k0_rec + ((nround - 1) * DEX_K0_G + gl) * 8 + 4, recn);
   for (int r = nround - 1; r >= 0; --r) {
-    int rec[4];
-    dex_ldg_int4(m.k0_rec + (r * DEX_K0_G + gl) * 8 + 4, rec);   // body, dofs (adr | num << 16), children (adr | num << 16)
+    const int rec[4] = {recn[0], recn[1], recn[2], recn[3]};   // body, dofs (adr | num << 16), children (adr | num << 16)
+    if (r > 0) dex_ldg_int4(m.k0_rec + ((r - 1) * DEX_K0_G + gl) * 8 + 4, recn);
     const int b = rec[0];
     if (b >= 0) {
       // subtree totals = own + the totals the children left in their slots one round ago (no atomics: the r01k
