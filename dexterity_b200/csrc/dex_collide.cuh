@@ -649,7 +649,8 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     if (bi + 1 < nbpl) { const int k = bpl[bi + 1]; adr_n = dex_ldg(m.bp_pairadr + k); num_n = dex_ldg(m.bp_pairnum + k); b1_n = dex_ldg(m.bp_body1 + k); }
     const bool plane = bsph[4 * b1 + 3] < 0;
     // DEX_K1_NCH chunks of 32 pairs per trip: all chunks' pair words are requested before any is used, so the dependent
-    // global load -> shared-memory lookups of one chunk overlap those of the others (2: 0.158 -> 0.154 ms per launch)
+    // global load -> shared-memory lookups of one chunk overlap those of the others (1 / 2 / 3 / 4 chunks: 0.158 / 0.156 / 0.156 /
+    // 0.159 ms per launch)
 #ifndef DEX_K1_NCH
 #define DEX_K1_NCH 2
 #endif

@@ -108,14 +108,9 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int split, int* fail) {
     const DexVec4<T> a = *reinterpret_cast<const DexVec4<T>*>(rowi + k0);
     T s0 = i == k0 ? hd : a.x, s1 = i == k0 + 1 ? hd : a.y, s2 = i == k0 + 2 ? hd : a.z, s3 = i == k0 + 3 ? hd : a.w;
     const T* r0 = H + k0 * DEX_MSTRIDE;
-#ifndef DEX_K2_GU
-#define DEX_K2_GU 1
-#endif
-#ifndef DEX_K2_AU
-#define DEX_K2_AU 1
-#endif
-    constexpr int kGu = DEX_K2_GU;
-#pragma unroll kGu
+    // NOT unrolled (like the substitution loops below): short run-time trip counts, and the solver is sensitive to its code
+    // footprint ("Code size": unroll 1 / 2 / 4 = 0.367 / 0.381 / 0.383 ms per launch)
+#pragma unroll 1
     for (int g = (k0 >= split ? split : 0); g < k0; g += 4) {
       const DexVec4<T> vi = *reinterpret_cast<const DexVec4<T>*>(rowi + g);
       const DexVec4<T> v0 = *reinterpret_cast<const DexVec4<T>*>(r0 + g);
@@ -162,8 +157,7 @@ DEX_DEV_NOINLINE T dex_chol_apply(const T* H, int n, T inv_mine, T b) {
   const int i = dex_lane();
   const T* rowi = H + i * DEX_MSTRIDE;
   const int n4 = (n + 3) & ~3;
-  constexpr int kAu = DEX_K2_AU;
-#pragma unroll kAu
+#pragma unroll 1
   for (int k = 0; k < n4; k += 4) {   // L y = b
     const DexVec4<T> l = *reinterpret_cast<const DexVec4<T>*>(rowi + k);
     b -= l.x * dex_shfl(b * inv_mine, k);
@@ -173,7 +167,7 @@ DEX_DEV_NOINLINE T dex_chol_apply(const T* H, int n, T inv_mine, T b) {
   }
   b *= inv_mine;
   const T* col = H + i;
-#pragma unroll kAu
+#pragma unroll 1
   for (int k = n4 - 1; k >= 0; k -= 4) {   // L^T x = y
     const T c0 = col[k * DEX_MSTRIDE], c1 = col[(k - 1) * DEX_MSTRIDE], c2 = col[(k - 2) * DEX_MSTRIDE], c3 = col[(k - 3) * DEX_MSTRIDE];
     b -= c0 * dex_shfl(b * inv_mine, k);
@@ -190,11 +184,7 @@ DEX_DEV_NOINLINE T dex_chol_load(T* H, const T* Mg, int n) {
   const int lane = dex_lane();
   // four rows per trip: lane = (row within the group, 4-column group); one 16-byte load and one 16-byte store per lane
   const int r = lane >> 3, c4 = (lane & 7) << 2;
-#ifndef DEX_K2_LD_UNROLL
-#define DEX_K2_LD_UNROLL 8
-#endif
-  constexpr int kLdUnroll = DEX_K2_LD_UNROLL;
-#pragma unroll kLdUnroll
+#pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 4) {
     const int j = j0 + r;
     DexVec4<T> v = {T(0), T(0), T(0), T(0)};
@@ -319,9 +309,6 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   int ncon = st.ncon[env];
   if (ncon > DEX_MAXCON) ncon = DEX_MAXCON;
   const T* cin = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
-#ifdef DEX_K2_CLOOP1
-#pragma unroll 1
-#endif
   for (int c = 0; c < ncon; ++c) {
     const T* cc = cin + c * DEX_CON_STRIDE;
     T frame[9] = {cc[4], cc[5], cc[6], 0, 0, 0, 0, 0, 0};
@@ -441,10 +428,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     // ---- gradient = M a - qfrc_smooth - J^T f
     T jtf = fdof;
     if (isdof) {
-    #ifdef DEX_K2_CLOOP1
-#pragma unroll 1
-#endif
-  for (int c = 0; c < ncon; ++c) {
+      for (int c = 0; c < ncon; ++c) {
         const T* cdt = cdat + c * DEX_CDAT_STRIDE;
         jtf += Jc[(3 * c) * DEX_JC_ROW + lane] * cdt[CD_F] + Jc[(3 * c + 1) * DEX_JC_ROW + lane] * cdt[CD_F + 1] +
                Jc[(3 * c + 2) * DEX_JC_ROW + lane] * cdt[CD_F + 2];
@@ -471,10 +455,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       dex_syncwarp();
       bool cross = false;
       const unsigned splitlo = m.chol_split >= 32 ? 0xffffffffu : ((1u << m.chol_split) - 1u);
-    #ifdef DEX_K2_CLOOP1
-#pragma unroll 1
-#endif
-  for (int c = 0; c < ncon; ++c) {
+      for (int c = 0; c < ncon; ++c) {
         const T* cdt = cdat + c * DEX_CDAT_STRIDE;
         const T w00 = cdt[CD_W], w01 = cdt[CD_W + 1], w02 = cdt[CD_W + 2], w11 = cdt[CD_W + 3], w22 = cdt[CD_W + 4];
         if (w00 == 0) continue;  // no active row (warp-uniform)
