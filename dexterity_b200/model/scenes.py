@@ -78,7 +78,8 @@ def _shadow_hand(scene: mjcf.Scene, name: str = "shadow_hand_e") -> mjcf.Model:
     return hand
 
 
-def reorient_scene() -> compile_lib.CompiledModel:
+def reorient_assembly():
+    """The assembled (not yet compiled) reorient scene and the arguments of its compile step."""
     scene = _standard_arena()
     hand = _shadow_hand(scene)
     scene.attach(hand, pos=SHADOW_PALM_UPRIGHT_POS, quat=SHADOW_PALM_UPRIGHT_QUAT)
@@ -88,18 +89,24 @@ def reorient_scene() -> compile_lib.CompiledModel:
     hint = mjcf.primitive_model("target_prop", "box", [REORIENT_PROP_SIZE] * 3, scene.root_defaults,
                                 contype=0, conaffinity=0)
     scene.attach(hint, pos=REORIENT_HINT_POS)
-    return compile_lib.compile_model(
-        scene.model, timestep=REORIENT_PHYSICS_TIMESTEP, nconmax=48,
-        xfrc_gravcomp_prefix="shadow_hand_e/")
+    return scene.model, dict(timestep=REORIENT_PHYSICS_TIMESTEP, nconmax=48, xfrc_gravcomp_prefix="shadow_hand_e/")
 
 
-def reach_shadow_scene() -> compile_lib.CompiledModel:
+def reorient_scene() -> compile_lib.CompiledModel:
+    model, kw = reorient_assembly()
+    return compile_lib.compile_model(model, **kw)
+
+
+def reach_shadow_assembly():
     scene = _standard_arena(ground_collides=False)
     hand = _shadow_hand(scene)
     scene.attach(hand, pos=SHADOW_PALM_UPRIGHT_POS, quat=SHADOW_PALM_UPRIGHT_QUAT)
-    return compile_lib.compile_model(
-        scene.model, timestep=REACH_PHYSICS_TIMESTEP, nconmax=48,
-        xfrc_gravcomp_prefix="shadow_hand_e/")
+    return scene.model, dict(timestep=REACH_PHYSICS_TIMESTEP, nconmax=48, xfrc_gravcomp_prefix="shadow_hand_e/")
+
+
+def reach_shadow_scene() -> compile_lib.CompiledModel:
+    model, kw = reach_shadow_assembly()
+    return compile_lib.compile_model(model, **kw)
 
 
 def shadow_hand_only() -> compile_lib.CompiledModel:
@@ -149,6 +156,9 @@ _BUILDERS = {
     "shadow_hand_only": shadow_hand_only,
     "adroit_hand_only": adroit_hand_only,
 }
+
+# scenes whose assembled MJCF can be exported (dexterity_b200/model/export.py, tools/export_task.py)
+ASSEMBLIES = {"reorient_shadow": reorient_assembly, "reach_shadow": reach_shadow_assembly}
 
 # hand name -> (hand-only compiled model, name prefix, fingertip site names)
 HANDS = {
