@@ -9,6 +9,11 @@ as tests/golden/reorient_oracle_steps.npz, and once it is committed
 path) with MuJoCo itself instead of skipping with "parity unpinned".
 
     python tools/mujoco_golden.py [--reference /path/to/dexterity] [--out tests/golden/reorient_mujoco_steps.npz]
+    python tools/mujoco_golden.py --mjcf /tmp/reorient/reorient_shadow.xml --out tests/golden/reorient_mujoco_steps_own_mjcf.npz
+
+The second form loads the flat MJCF written by tools/export_task.py (THIS build's scene assembly) into stock MuJoCo
+instead of building the reference's environment: a difference between the two outputs is a difference in scene
+assembly (PyMJCF attach, defaults), not in the engine restatement.
 
 What it does: builds the reference's own reorient environment (dexterity.manipulation.load), maps
 joints / actuators / geoms to this repo's compiled model BY NAME, and for every state of the oracle
@@ -32,18 +37,31 @@ def main() -> None:
     ap.add_argument("--reference", default=os.environ.get("DEXTERITY_REFERENCE", "/root/reference"))
     ap.add_argument("--states", default=os.path.join(ROOT, "tests", "golden", "reorient_oracle_steps.npz"))
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "reorient_mujoco_steps.npz"))
+    ap.add_argument("--mjcf", default=None, help="flat MJCF from tools/export_task.py instead of the reference's environment")
     args = ap.parse_args()
     sys.path.insert(0, args.reference)
 
     import mujoco                                   # noqa: E402  (absent in the build container)
-    from dexterity import manipulation              # noqa: E402  (the reference itself)
     from dexterity_b200.model import scenes         # noqa: E402
 
     c = scenes.load_compiled("reorient_shadow")
-    env = manipulation.load(domain_name="reorient", task_name="state_dense", seed=0)
-    env.reset()
-    physics = env.physics
-    m, d = physics.model.ptr, physics.data.ptr
+    env = None
+    if args.mjcf:
+        m = mujoco.MjModel.from_xml_path(args.mjcf)
+        d = mujoco.MjData(m)
+        mujoco.mj_forward(m, d)
+        # the hands' constant gravity compensation (reference utils/mujoco_utils.py:91-99) is not expressible in MJCF
+        for b in range(m.nbody):
+            if (mujoco.mj_id2name(m, mujoco.mjtObj.mjOBJ_BODY, b) or "").startswith("shadow_hand_e/"):
+                d.xfrc_applied[b, :3] = -m.opt.gravity * m.body_mass[b]
+        xfrc = d.xfrc_applied.copy()
+    else:
+        from dexterity import manipulation          # noqa: E402  (the reference itself)
+        env = manipulation.load(domain_name="reorient", task_name="state_dense", seed=0)
+        env.reset()
+        physics = env.physics
+        m, d = physics.model.ptr, physics.data.ptr
+        xfrc = d.xfrc_applied.copy()
 
     def name(objtype, i):
         return mujoco.mj_id2name(m, objtype, i) or ""
@@ -83,6 +101,7 @@ def main() -> None:
     qpos_reset, qvel_reset = d.qpos.copy(), d.qvel.copy()
     for i in range(n):
         mujoco.mj_resetData(m, d)
+        d.xfrc_applied[:] = xfrc
         d.qpos[:] = qpos_reset; d.qvel[:] = qvel_reset
         d.qpos[qmap] = z["qpos"][i]; d.qvel[vmap] = z["qvel"][i]
         d.ctrl[amap] = z["ctrl"][i]; d.qacc_warmstart[vmap] = z["warm"][i]
@@ -107,7 +126,7 @@ def main() -> None:
                model_geom_rbound=m.geom_rbound.copy(), model_geom_size=m.geom_size.copy(), model_body_invweight0=m.body_invweight0.copy(),
                model_dof_invweight0=m.dof_invweight0[vmap].copy(), model_body_mass=m.body_mass.copy(), model_body_inertia=m.body_inertia.copy(),
                model_opt=np.array([m.opt.timestep, m.opt.tolerance, m.opt.iterations, m.opt.solver, m.opt.cone, m.opt.integrator, m.opt.impratio]),
-               model_stat_meaninertia=np.array(m.stat.meaninertia), model_observation_keys=np.array(list(env.observation_spec().keys())))
+               model_stat_meaninertia=np.array(m.stat.meaninertia), model_observation_keys=np.array(list(env.observation_spec().keys()) if env is not None else []))
     np.savez_compressed(args.out, **out)
     print("wrote", args.out, "mujoco", mujoco.__version__, "ncon histogram", np.bincount(ncon))
 
