@@ -123,21 +123,28 @@ DEX_DEV_NOINLINE T dex_chol_factor(T* H, T hd, int n, int split, int* fail) {
       s3 -= vi.x * v3.x + vi.y * v3.y + vi.z * v3.z + vi.w * v3.w;
     }
     // 4 x 4 diagonal block: column k0 + r is final once the r earlier columns of the block are applied
-    T d = dex_shfl(s0, k0);
-    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
-    const T i0 = dx_rsqrt(d), l0 = s0 * i0;
-    s1 -= l0 * dex_shfl(l0, k0 + 1);
-    d = dex_shfl(s1, k0 + 1);
-    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
-    const T i1 = dx_rsqrt(d), l1 = s1 * i1;
-    s2 -= l0 * dex_shfl(l0, k0 + 2) + l1 * dex_shfl(l1, k0 + 2);
-    d = dex_shfl(s2, k0 + 2);
-    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
-    const T i2 = dx_rsqrt(d), l2 = s2 * i2;
-    s3 -= l0 * dex_shfl(l0, k0 + 3) + l1 * dex_shfl(l1, k0 + 3) + l2 * dex_shfl(l2, k0 + 3);
-    d = dex_shfl(s3, k0 + 3);
-    bad |= !(d > Real<T>::minval()); d = dx_max(d, Real<T>::minval());
-    const T i3 = dx_rsqrt(d), l3 = s3 * i3;
+    // The pivots' square roots are kept OFF the critical path: column k0 + r is updated with s_k S_k / d_k (the pre-pivot
+    // column values and a reciprocal) instead of l_k L_k, so a pivot's chain is shuffle -> reciprocal -> fused multiply-add;
+    // the four rsqrt's and the products l_k = s_k / sqrt(d_k) follow independently at the end (same number of shuffles;
+    // env step 3.94 -> 3.92 ms).
+    T d0 = dex_shfl(s0, k0);
+    const T a01 = dex_shfl(s0, k0 + 1), a02 = dex_shfl(s0, k0 + 2), a03 = dex_shfl(s0, k0 + 3);
+    bad |= !(d0 > Real<T>::minval()); d0 = dx_max(d0, Real<T>::minval());
+    const T q0 = s0 * dx_rcp(d0);
+    s1 -= q0 * a01; s2 -= q0 * a02; s3 -= q0 * a03;
+    T d1 = dex_shfl(s1, k0 + 1);
+    const T a12 = dex_shfl(s1, k0 + 2), a13 = dex_shfl(s1, k0 + 3);
+    bad |= !(d1 > Real<T>::minval()); d1 = dx_max(d1, Real<T>::minval());
+    const T q1 = s1 * dx_rcp(d1);
+    s2 -= q1 * a12; s3 -= q1 * a13;
+    T d2 = dex_shfl(s2, k0 + 2);
+    const T a23 = dex_shfl(s2, k0 + 3);
+    bad |= !(d2 > Real<T>::minval()); d2 = dx_max(d2, Real<T>::minval());
+    s3 -= s2 * dx_rcp(d2) * a23;
+    T d3 = dex_shfl(s3, k0 + 3);
+    bad |= !(d3 > Real<T>::minval()); d3 = dx_max(d3, Real<T>::minval());
+    const T i0 = dx_rsqrt(d0), i1 = dx_rsqrt(d1), i2 = dx_rsqrt(d2), i3 = dx_rsqrt(d3);
+    const T l0 = s0 * i0, l1 = s1 * i1, l2 = s2 * i2, l3 = s3 * i3;
     DexVec4<T> o;
     o.x = i > k0 ? l0 : T(0); o.y = i > k0 + 1 ? l1 : T(0); o.z = i > k0 + 2 ? l2 : T(0); o.w = i > k0 + 3 ? l3 : T(0);
     *reinterpret_cast<DexVec4<T>*>(rowi + k0) = o;

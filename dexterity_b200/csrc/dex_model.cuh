@@ -136,6 +136,17 @@ DEX_DEV double dx_rsqrt(double x) { return 1.0 / sqrt(x); }
 #else
 template <typename T> inline T dx_rsqrt(T x) { return T(1) / std::sqrt(x); }
 #endif
+// reciprocal: MUFU.RCP + one Newton step in FP32 (positive, normal arguments), IEEE division in FP64
+#if defined(__CUDACC__)
+DEX_DEV float dx_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * (2.0f - x * r);
+}
+DEX_DEV double dx_rcp(double x) { return 1.0 / x; }
+#else
+template <typename T> inline T dx_rcp(T x) { return T(1) / x; }
+#endif
 template <typename T> DEX_DEV T dx_abs(T x) { return x < 0 ? -x : x; }
 template <typename T> DEX_DEV T dx_min(T a, T b) { return a < b ? a : b; }
 template <typename T> DEX_DEV T dx_max(T a, T b) { return a > b ? a : b; }
