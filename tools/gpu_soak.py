@@ -16,7 +16,7 @@ for it in range(600):
     bits |= env.physics.status
     if it % 50 == 49:
         nonfinite += int((~torch.isfinite(env.physics.qpos).all(dim=1)).sum().item()) + int((~torch.isfinite(ts.reward)).sum().item())
-names = {1: "BADQACC", 2: "CON_OVERFLOW", 4: "CAND_OVERFLOW", 8: "SOLVER_MAXITER", 16: "CHOL_FAIL"}
+names = {1: "BADQACC", 2: "CON_OVERFLOW", 4: "CAND_OVERFLOW", 8: "SOLVER_MAXITER", 16: "CHOL_FAIL", 32: "PLACEMENT"}
 print("envs with status bit ever set over 600 steps:", {n: int(((bits & b) != 0).sum().item()) for b, n in names.items()})
 print("non-finite samples:", nonfinite)
 print("episode stats:", env.reduce_episode_stats())
