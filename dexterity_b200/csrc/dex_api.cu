@@ -40,6 +40,11 @@ constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 #define DEX_K2_CTAS 22   // resident single-warp CTAs of K2 per SM (register bound 65536 / (22 * 32) = 93; measured 18: 0.449, 20: 0.451, 22: 0.421, 24: 0.432 ms)
 #endif
 
+static_assert(DEX_STATUS_BIT_BADQACC == DEX_STATUS_BADQACC && DEX_STATUS_BIT_CON_OVERFLOW == DEX_STATUS_CON_OVERFLOW &&
+              DEX_STATUS_BIT_CAND_OVERFLOW == DEX_STATUS_CAND_OVERFLOW && DEX_STATUS_BIT_SOLVER_MAXITER == DEX_STATUS_SOLVER_MAXITER &&
+              DEX_STATUS_BIT_CHOL_FAIL == DEX_STATUS_CHOL_FAIL && DEX_STATUS_BIT_PLACEMENT == DEX_STATUS_PLACEMENT,
+              "public status bits (include/dexterity_b200.h) out of step with the kernels'");
+
 constexpr int kTreeBlock = 32;  // one env per THREAD; 16384 envs = 512 warps spread over all SMs
 template <typename T>
 __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T> st) {

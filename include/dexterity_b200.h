@@ -34,6 +34,17 @@ enum DexError {
   DEX_E_UNBOUND = -4    /* a tensor required by the call has not been bound */
 };
 
+/* Bits of the bound STATUS tensor (sticky until the env is reset).  BADQACC and PLACEMENT end the episode with reward 0 and
+ * discount 0 on the next post-step (dm_control's non-raising PhysicsError handling); the others are diagnostics. */
+enum DexStatusBit {
+  DEX_STATUS_BIT_BADQACC = 1,         /* mj_checkAcc: non-finite or huge qacc                                  */
+  DEX_STATUS_BIT_CON_OVERFLOW = 2,    /* more than dex_capacity(DEX_CAP_MAXCON) contacts: the rest were dropped */
+  DEX_STATUS_BIT_CAND_OVERFLOW = 4,   /* broadphase candidate / staging buffers full                           */
+  DEX_STATUS_BIT_SOLVER_MAXITER = 8,  /* Newton stopped at the model's iteration cap                           */
+  DEX_STATUS_BIT_CHOL_FAIL = 16,      /* non-positive pivot in the Hessian factorisation (clamped)             */
+  DEX_STATUS_BIT_PLACEMENT = 32       /* no contact-free prop pose within DexTaskParams.place_max_attempts     */
+};
+
 enum DexDtype { DEX_F32 = 0, DEX_F64 = 1 }; /* F64 = validation build of the same kernels */
 
 /* Bindable tensors.  Shapes are [num_envs][width] row-major with the given row stride. */
