@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_CSRC, "libdexb200.so")
 FIELD = dict(QPOS=0, QVEL=1, CTRL=2, QACC_WARMSTART=3, TIME=4, STATUS=5, CONTACT=6, NCON=7, NITER=8,
              DBG_M=9, DBG_QFRC_SMOOTH=10, DBG_QACC=11, DBG_QFRC_CONSTRAINT=12, DBG_EFC=13,
              OBS=14, REWARD=15, DISCOUNT=16, NSLOT=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22,
-             WORK=23, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31, ORDER=32)
+             WORK=23, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31, ORDER=32, TIME64=33)
 STATUS_BADQACC, STATUS_CON_OVERFLOW, STATUS_CAND_OVERFLOW, STATUS_SOLVER_MAXITER, STATUS_CHOL_FAIL = 1, 2, 4, 8, 16
 
 _lib = None
@@ -115,7 +115,7 @@ class PhysicsBatch:
             STATUS=z(n, dt=torch.int32), CONTACT=z(n, maxcon, cstride), NCON=z(n, dt=torch.int32),
             NITER=z(n, dt=torch.int32), JC=torch.empty(n, 3 * maxcon, 32, dtype=dtype, device=dev),
             MSCR=z(n, 32, 32), XKIN=z(n, capacity(3) * 16), TREE=z(n, 8 * 32), STAGE=z(n, 64, 8),
-            NSLOT=z(n, dt=torch.int32), ORDER=z(8, n, dt=torch.int32))
+            NSLOT=z(n, dt=torch.int32), ORDER=z(8, n, dt=torch.int32), TIME64=z(n, 2, dt=torch.float64))
         if debug:
             self._store.update(DBG_M=z(n, c.nv * c.nv), DBG_QFRC_SMOOTH=z(n, c.nv), DBG_QACC=z(n, c.nv),
                                DBG_QFRC_CONSTRAINT=z(n, c.nv), DBG_EFC=z(n, maxcon, 8))
@@ -133,6 +133,7 @@ class PhysicsBatch:
         self.ctrl = self._store["CTRL"][:, :c.nu]
         self.qacc_warmstart = self._store["QACC_WARMSTART"][:, :c.nv]
         self.time = self._store["TIME"]
+        self.time64 = self._store["TIME64"]   # [:, 0] data.time in double, [:, 1] the task's solve-start time
         self.status = self._store["STATUS"]
         self.contact = self._store["CONTACT"]
         self.ncon = self._store["NCON"]
@@ -155,11 +156,10 @@ class PhysicsBatch:
     def reset_to_qpos0(self) -> None:
         c = self.model.compiled
         self.qpos.copy_(torch.as_tensor(c.QPOS0, dtype=self.dtype, device=self.device).expand(self.num_envs, -1))
-        self.qvel.zero_(); self.ctrl.zero_(); self.qacc_warmstart.zero_(); self.time.zero_(); self.status.zero_()
+        self.qvel.zero_(); self.ctrl.zero_(); self.qacc_warmstart.zero_(); self.time.zero_(); self.time64.zero_(); self.status.zero_()
 
-    @staticmethod
-    def _stream() -> ctypes.c_void_p:
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def set_chunks(self, nchunk: int) -> None:
         """Env chunks that run as independent kernel pipelines on library-owned streams (1..4)."""

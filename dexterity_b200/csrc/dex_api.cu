@@ -26,6 +26,20 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(DEX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// Every entry point runs on the model's device and leaves the calling thread's current device as it found it
+// (PyTorch keeps its own notion of the current device per thread).
+struct DeviceGuard {
+  int prev = -1; cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEX_ON_DEVICE(dev)      \
+  DeviceGuard guard_(dev);      \
+  if (guard_.err != cudaSuccess) return fail(DEX_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard_.err))
+
 #ifndef DEX_WARPS_PER_BLOCK
 #define DEX_WARPS_PER_BLOCK 4
 #endif
@@ -201,7 +215,7 @@ struct DeviceArrays {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
-    dev.timestep = (T)h.timestep;
+    dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name)                                                                         \
@@ -318,6 +332,7 @@ int make_state(DexBatch* b, BatchState<T>& st, DynDebug<T>& dbg, bool need_dyn, 
   st.niter = (int*)b->ptr[DEX_FIELD_NITER];
   st.skip = use_skip ? (const unsigned char*)b->ptr[DEX_FIELD_SKIP] : nullptr;
   st.skip_mode = 0;
+  st.time64 = (double*)b->ptr[DEX_FIELD_TIME64];
   st.jc = (T*)b->ptr[DEX_FIELD_JC];
   st.mscr = (T*)b->ptr[DEX_FIELD_MSCR];
   st.xkin = (T*)b->ptr[DEX_FIELD_XKIN];
@@ -418,7 +433,7 @@ int run(DexBatch* b, const DevModel<T>& m, int nsub, bool collide, bool dynamics
   DynDebug<T> dbg;
   int rc = make_state<T>(b, st, dbg, dynamics);
   if (rc) return rc;
-  DEX_CUDA(cudaSetDevice(b->model->device));
+  DEX_ON_DEVICE(b->model->device);
   return launch_physics<T>(b, m, st, dbg, nsub, collide, dynamics, integrate, s);
 }
 
@@ -426,7 +441,7 @@ template <typename T>
 int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaStream_t s, int phases = 7) {
   if (!b->task_set) return fail(DEX_E_ARG, "dex_task_configure has not been called");
   static const int req[] = {DEX_FIELD_OBS, DEX_FIELD_REWARD, DEX_FIELD_DISCOUNT, DEX_FIELD_GOAL, DEX_FIELD_TASK_I,
-                            DEX_FIELD_TASK_F, DEX_FIELD_RNG, DEX_FIELD_ACTION, DEX_FIELD_SKIP};
+                            DEX_FIELD_TASK_F, DEX_FIELD_RNG, DEX_FIELD_ACTION, DEX_FIELD_SKIP, DEX_FIELD_TIME64};
   for (int f : req) if (!b->ptr[f]) return fail(DEX_E_UNBOUND, "required task tensor not bound: field " + std::to_string(f));
   BatchState<T> st;
   DynDebug<T> dbg;
@@ -437,9 +452,9 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
   ts.obs = (T*)b->ptr[DEX_FIELD_OBS]; ts.reward = (T*)b->ptr[DEX_FIELD_REWARD]; ts.discount = (T*)b->ptr[DEX_FIELD_DISCOUNT];
   ts.goal = (T*)b->ptr[DEX_FIELD_GOAL]; ts.task_i = (int*)b->ptr[DEX_FIELD_TASK_I]; ts.task_f = (T*)b->ptr[DEX_FIELD_TASK_F];
   ts.rng = (unsigned*)b->ptr[DEX_FIELD_RNG]; ts.skip = (unsigned char*)b->ptr[DEX_FIELD_SKIP];
-  ts.reset_mask = (const unsigned char*)b->ptr[DEX_FIELD_RESET_MASK];
+  ts.reset_mask = (unsigned char*)b->ptr[DEX_FIELD_RESET_MASK];
   ts.stats = (double*)b->ptr[DEX_FIELD_EPISODE_STATS];
-  DEX_CUDA(cudaSetDevice(b->model->device));
+  DEX_ON_DEVICE(b->model->device);
   const size_t smem3 = (size_t)kWarpsPerBlock * DEX_K3_SMEM_T * sizeof(T);
   const int grid = (b->nenv + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int block = kWarpsPerBlock * 32;
@@ -511,14 +526,13 @@ int dex_model_create(const void* blob, uint64_t nbytes, int device, DexModel** o
   std::string e = dex_host::build(blob, nbytes, m->host);
   if (!e.empty()) { delete m; return fail(DEX_E_MODEL, e); }
   m->device = device;
-  DEX_CUDA(cudaSetDevice(device));
   *out = m;
   return DEX_OK;
 }
 
 void dex_model_destroy(DexModel* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  DeviceGuard guard_(m->device);
   m->f32.release();
   m->f64.release();
   delete m;
@@ -527,7 +541,7 @@ void dex_model_destroy(DexModel* m) {
 int dex_batch_create(DexModel* model, int num_envs, int dtype, DexBatch** out) {
   if (!model || !out || num_envs < 1) return fail(DEX_E_ARG, "bad argument");
   if (dtype != DEX_F32 && dtype != DEX_F64) return fail(DEX_E_ARG, "dtype must be DEX_F32 or DEX_F64");
-  DEX_CUDA(cudaSetDevice(model->device));
+  DEX_ON_DEVICE(model->device);
   if (dtype == DEX_F32 && !model->has_f32) { int rc = model->f32.upload(model->host); if (rc) return rc; model->has_f32 = true; }
   if (dtype == DEX_F64 && !model->has_f64) { int rc = model->f64.upload(model->host); if (rc) return rc; model->has_f64 = true; }
   DexBatch* b = new (std::nothrow) DexBatch;
@@ -541,8 +555,9 @@ int dex_batch_create(DexModel* model, int num_envs, int dtype, DexBatch** out) {
 
 void dex_batch_destroy(DexBatch* b) {
   if (!b) return;
+  DeviceGuard guard_(b->model->device);
+  for (auto& v : b->ev) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }   // profiling events not yet collected
   if (b->ev_fork) {
-    cudaSetDevice(b->model->device);
     cudaEventDestroy(b->ev_fork);
     for (int c = 0; c < DEX_MAXCHUNK; ++c) { cudaStreamDestroy(b->cs[c]); cudaEventDestroy(b->ev_join[c]); }
   }
@@ -598,7 +613,7 @@ int dex_ik_solve(DexModel* model, int dtype, const void* targets, int n, const D
   if (h.nq != h.nv || h.njnt != h.nv) return fail(DEX_E_MODEL, "IK model must consist of hinge joints only");
   for (int j = 0; j < h.njnt; ++j)
     if (h.jnt_type[j] != DEX_JNT_HINGE || h.jnt_dofadr[j] != j || !h.jnt_limited[j]) return fail(DEX_E_MODEL, "IK model must consist of limited hinge joints");
-  DEX_CUDA(cudaSetDevice(model->device));
+  DEX_ON_DEVICE(model->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (dtype == DEX_F32) {
@@ -625,7 +640,7 @@ int dex_set_profiling(DexBatch* b, int on) {
 // ms[8] (total milliseconds) and count[8] (launches) for pre / broadphase / solve / post / tree / narrowphase / compaction / (reserved).
 int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
   if (!b || !ms || !count) return fail(DEX_E_ARG, "null argument");
-  DEX_CUDA(cudaSetDevice(b->model->device));
+  DEX_ON_DEVICE(b->model->device);
   DEX_CUDA(cudaDeviceSynchronize());
   for (int c = 0; c < 8; ++c) {
     for (size_t i = 0; i + 1 < b->ev[c].size(); i += 2) {

@@ -598,7 +598,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     st.qvel[(size_t)env * st.qvel_stride + lane] = qv_new;
     st.warm[(size_t)env * st.warm_stride + lane] = qacc;
   }
-  if (lane == 0) st.time[env] += h;
+  if (lane == 0) {
+    if (st.time64) { const double t = st.time64[2 * (size_t)env] + m.timestep_d; st.time64[2 * (size_t)env] = t; st.time[env] = (T)t; }
+    else st.time[env] += h;
+  }
 }
 
 #endif  // DEX_DYNAMICS_CUH_

@@ -61,6 +61,7 @@ struct DevModel {
   int chol_split;  // first dof (multiple of 4) of a trailing group of kinematic trees that M does not couple to the dofs before it (nv if none)
   int k0_rounds;  // rounds of the 8-lanes-per-env tree kernel schedule (0 = model does not fit: thread-per-env kernel)
   T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
+  double timestep_d;  // opt.timestep unrounded: data.time advances in double whatever the batch dtype
 #define DEX_X_I(name) const int* name;
 #define DEX_X_R(name) const T* name;
 #define DEX_X(t, name) DEX_X_##t(name)
@@ -99,6 +100,7 @@ struct BatchState {
   int work_cap;
   T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
   int skip_mode;                  // which envs a launch works on (see dex_env_off): 0 = those with skip == 0, 1 = those being placed (skip >= 2)
+  double* time64;                 // optional [nenv][2]: data.time accumulated in double (MuJoCo's own arithmetic), solve-start time of the goal
 };
 
 // skip[env]: 0 = stepping normally, 1 = reset during this call (physics leaves it alone), 2 + k = reset and its prop pose is

@@ -42,7 +42,7 @@ struct TaskState {
   T* task_f;                            // [nenv][TF_COUNT]
   unsigned* rng;                        // [nenv][4]: key0 key1 counter unused
   unsigned char* skip;                  // [nenv] 1 = env was reset in this call (physics skipped)
-  const unsigned char* reset_mask;      // optional [nenv]
+  unsigned char* reset_mask;            // optional [nenv]: reset requests, consumed (cleared) by the pre-step
   double* stats;                        // [ES_COUNT]
 };
 
@@ -106,7 +106,9 @@ DEX_DEV void dex_task_pre_env(const DevModel<T>& m, const BatchState<T>& st, con
     if (lane < m.nu) st.ctrl[(size_t)env * st.ctrl_stride + lane] = 0;
     if (lane < 4 && p.task == DEX_TASK_REORIENT) goal[lane] = gq[lane];
     if (lane == 0) {
+      if (ts.reset_mask) ts.reset_mask[env] = 0;   // the request is consumed: the env steps normally from the next call on
       st.time[env] = 0; st.status[env] = 0;
+      if (st.time64) { st.time64[2 * (size_t)env] = 0; st.time64[2 * (size_t)env + 1] = 0; }
       ti[TI_SUCCESSES] = 0; ti[TI_CHANGE_COUNTER] = 0; ti[TI_REGISTERED] = 0; ti[TI_EXCEEDED] = 0;
       ti[TI_GOAL_CHANGED] = 1; ti[TI_FAILURE] = 0; ti[TI_EPISODE_LEN] = 0;
       tf[TF_SOLVE_START] = 0; tf[TF_RETURN] = 0;
@@ -127,6 +129,7 @@ DEX_DEV void dex_task_pre_env(const DevModel<T>& m, const BatchState<T>& st, con
       if (change) {
         ti[TI_CHANGE_COUNTER] = 0; ti[TI_EXCEEDED] = 0; ti[TI_REGISTERED] = 0; ti[TI_GOAL_CHANGED] = 1;
         tf[TF_SOLVE_START] = st.time[env];
+        if (st.time64) st.time64[2 * (size_t)env + 1] = st.time64[2 * (size_t)env];
         rng[2] = ctr + 1;
       } else ti[TI_GOAL_CHANGED] = 0;
       ts.skip[env] = 0;
@@ -322,7 +325,10 @@ DEX_DEV void dex_task_post_env(const DevModel<T>& m, const BatchState<T>& st, co
   }
   const T act2 = dex_warp_sum(ctrl * ctrl);  // ||physics.data.ctrl||^2 (reorient.py:277)
   if (lane == 0) {
-    const T time = st.time[env];
+    // data.time and _solve_start_time in double, as the reference holds them (task.py:149,161,184): in FP32 1500 additions
+    // of 0.005 drift enough to move the 7.5 s per-goal timeout by a control step
+    const double time = st.time64 ? st.time64[2 * (size_t)env] : (double)st.time[env];
+    const double solve_start = st.time64 ? st.time64[2 * (size_t)env + 1] : (double)tf[TF_SOLVE_START];
     const unsigned status = st.status[env];
     bool all_in = true;
     for (int s = 0; s < ndist; ++s) { all_in = all_in && (dist[s] <= (T)p.success_threshold); tf[TF_GOAL_DIST + s] = dist[s]; }
@@ -330,14 +336,14 @@ DEX_DEV void dex_task_post_env(const DevModel<T>& m, const BatchState<T>& st, co
     if (all_in) {                                   // task.py:177-181
       ti[TI_CHANGE_COUNTER] += 1;
       if (!ti[TI_REGISTERED]) { successes += 1; ti[TI_REGISTERED] = 1; }
-    } else if (p.has_max_time && time - tf[TF_SOLVE_START] > (T)p.max_time_per_goal) exceeded = 1;  // :182-185
+    } else if (p.has_max_time && time - solve_start > p.max_time_per_goal) exceeded = 1;  // :182-185
     ti[TI_SUCCESSES] = successes; ti[TI_EXCEEDED] = exceeded;
     const bool failure = p.task == DEX_TASK_REORIENT && p.fall_termination && fallen;
     ti[TI_FAILURE] = failure ? 1 : 0;
     const bool solved = successes >= p.successes_needed;
     const bool timeout = p.has_max_time && exceeded;
     const bool physics_error = (status & (DEX_STATUS_BADQACC | DEX_STATUS_PLACEMENT)) != 0;
-    const bool over_time = time >= (T)p.time_limit;
+    const bool over_time = time >= p.time_limit;
     const bool terminate = solved || timeout || failure || physics_error || over_time;
     T reward, discount;
     if (p.task == DEX_TASK_REORIENT) {
@@ -348,12 +354,10 @@ DEX_DEV void dex_task_post_env(const DevModel<T>& m, const BatchState<T>& st, co
       discount = failure ? T(1) : (solved ? T(0) : T(1));   // reorient.py:222-225, task.py:195-204
     } else {
       // reach.py:196-210: mean over fingers of 0 (inside 1 cm) else -tanh^2(w d) (dense) / -1 (sparse)
-      const T wgt = T(1.4722194895832204 / 0.1) * T(1.0);  // placeholder, overwritten below
-      (void)wgt;
       T acc = 0;
       for (int s = 0; s < ndist; ++s) {
         if (dist[s] <= T(0.01)) continue;
-        if (p.dense_reward) { const T tt = tanh(T(21.83385512824716) * dist[s]); acc -= tt * tt; }
+        if (p.dense_reward) { const T tt = tanh((T)p.reach_tanh_weight * dist[s]); acc -= tt * tt; }
         else acc -= 1;
       }
       reward = acc / (T)ndist;

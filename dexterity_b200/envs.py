@@ -37,7 +37,9 @@ REORIENT = dict(
 # reference manipulation/tasks/reach.py:47-66
 REACH = dict(
     success_threshold=0.01, successes_needed=50, steps_before_changing_goal=5,
-    max_time_per_goal=150 * 0.02, control_timestep=0.02, physics_timestep=0.02)
+    max_time_per_goal=150 * 0.02, control_timestep=0.02, physics_timestep=0.02,
+    # reach.py:196-205: rewards.tanh_squared(d, margin=0.1) with the default loss_at_margin=0.95 (shared/rewards.py:18-28)
+    reward_margin=0.1, reward_loss_at_margin=0.95)
 
 
 class TaskParams(ctypes.Structure):
@@ -53,6 +55,7 @@ class TaskParams(ctypes.Structure):
         ("spawn_lo", ctypes.c_double * 3), ("spawn_hi", ctypes.c_double * 3),
         ("w_orientation", ctypes.c_double), ("w_success_bonus", ctypes.c_double), ("w_action_smoothing", ctypes.c_double),
         ("orientation_eps", ctypes.c_double), ("bonus_threshold", ctypes.c_double),
+        ("reach_tanh_weight", ctypes.c_double),
         ("seed", ctypes.c_ulonglong),
     ]
 
@@ -153,6 +156,8 @@ class BatchedGoalEnvironment:
         for i, s in enumerate(sites):
             p.site_id[i] = s
         p.dense_reward = int(dense_reward)
+        if task_name == "reach":
+            p.reach_tanh_weight = math.atanh(math.sqrt(cfg["reward_loss_at_margin"])) / cfg["reward_margin"]
         p.success_threshold = cfg["success_threshold"]
         p.max_time_per_goal = cfg["max_time_per_goal"]
         p.time_limit = float(time_limit) if time_limit else math.inf
@@ -218,7 +223,7 @@ class BatchedGoalEnvironment:
         return TimeStep(self._task_i[:, 6], self._reward, self._discount, obs)
 
     def reset(self) -> TimeStep:
-        backend._check(backend.lib().dex_env_reset(self.physics.ptr, backend.PhysicsBatch._stream()))
+        backend._check(backend.lib().dex_env_reset(self.physics.ptr, self.physics._stream()))
         return self._timestep()
 
     def step(self, action: torch.Tensor) -> TimeStep:
@@ -228,7 +233,7 @@ class BatchedGoalEnvironment:
 
     def step_bound(self) -> TimeStep:
         """Steps with whatever is already stored in `self.action_buffer` (zero-copy path)."""
-        backend._check(backend.lib().dex_env_step(self.physics.ptr, self.n_sub_steps, backend.PhysicsBatch._stream()))
+        backend._check(backend.lib().dex_env_step(self.physics.ptr, self.n_sub_steps, self.physics._stream()))
         return self._timestep()
 
     @property
@@ -294,7 +299,7 @@ class ReachEnvironment(BatchedGoalEnvironment):
 
     def _phase(self, phases: int, force_reset: int = 0) -> None:
         backend._check(backend.lib().dex_env_phase(self.physics.ptr, phases, self.n_sub_steps, force_reset,
-                                                   backend.PhysicsBatch._stream()))
+                                                   self.physics._stream()))
 
     def _sample_collision_free(self, ids: torch.Tensor) -> None:
         """DexterousHand.sample_collision_free_joint_angles (dexterous_hand.py:144-168) for envs `ids`."""

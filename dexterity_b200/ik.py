@@ -83,7 +83,7 @@ class IKSolver:
         backend._check(backend.lib().dex_ik_solve(
             self.model.ptr, 0 if dtype == torch.float32 else 1, ctypes.c_void_p(t.data_ptr()), n, ctypes.byref(p),
             ctypes.c_void_p(qout.data_ptr()), 32, ctypes.c_void_p(ok.data_ptr()), ctypes.c_void_p(attempts.data_ptr()),
-            backend.PhysicsBatch._stream()))
+            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         self.last_attempts = attempts
         q = qout[:, :self.compiled.nq]
         if single:

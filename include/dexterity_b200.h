@@ -132,6 +132,8 @@ typedef struct DexTaskParams {
   double time_limit;              // manipulation/__init__.py:83 (inf if None)
   double spawn_lo[3], spawn_hi[3];// reorient.py:72-78
   double w_orientation, w_success_bonus, w_action_smoothing, orientation_eps, bonus_threshold;  // reorient.py:49-56
+  double reach_tanh_weight;       // reach, dense reward: w of rewards.tanh_squared(d, margin=0.1, loss_at_margin=0.95) =
+                                  // atanh(sqrt(loss_at_margin)) / margin (shared/rewards.py:18-28, reach.py:196-205)
   unsigned long long seed;
 } DexTaskParams;
 
@@ -147,7 +149,8 @@ enum DexTaskFieldId {
   DEX_FIELD_RNG = 21,          /* u32  [nenv][4]     Philox key0,key1,counter,-                                 */
   DEX_FIELD_ACTION = 22,       /* real [nenv][nu]    the action passed to Environment.step                      */
   DEX_FIELD_EPISODE_STATS = 24,/* f64  [8]           sum return, sum length, episodes, successes, falls, timeouts, physics errors */
-  DEX_FIELD_RESET_MASK = 25,   /* u8   [nenv]        optional: envs to reset on the next dex_env_step           */
+  DEX_FIELD_RESET_MASK = 25,   /* u8   [nenv]        optional: envs to reset on the next dex_env_step; the pre-step
+                                  consumes the request (clears the byte) when it resets the env                       */
   DEX_FIELD_SKIP = 26,         /* u8   [nenv]        scratch: envs reset during the current call                */
   DEX_FIELD_JC = 27,           /* real [nenv][3*DEX_MAXCON][32] scratch: contact-frame Jacobians (stays in L2)       */
   DEX_FIELD_MSCR = 28,         /* real [nenv][32][32] scratch: dense mass matrix; MUST be zero-initialised by the caller (only
@@ -157,6 +160,11 @@ enum DexTaskFieldId {
   DEX_FIELD_STAGE = 31,        /* real [nenv][64][8] scratch: contact staging slots of the collision kernels               */
   DEX_FIELD_NSLOT = 17,        /* i32  [nenv]        scratch: staging slots in use                                        */
   DEX_FIELD_ORDER = 32,        /* i32  [8][nenv]     optional scratch: env lists per solver-cost class (K2 processes the heaviest first)  */
+  DEX_FIELD_TIME64 = 33,       /* f64  [nenv][2]     physics.data.time accumulated in double exactly as MuJoCo does (time += timestep
+                                  once per mj_step), and the task's _solve_start_time (task.py:149,161): the per-goal timeout and
+                                  the time limit compare THESE, so episode lengths do not depend on the batch dtype.  Required by
+                                  the env entry points, optional for dex_mj_step (without it TIME accumulates in the batch dtype);
+                                  TIME always receives the rounded value                                                          */
   DEX_FIELD_WORK = 23          /* i32  [16 + 2*cap]  scratch: narrowphase work list: item count, fetch cursor, class counters, then (env, slot<<24|pair)
                                   pairs; bind with row_stride = cap (the capacity in items, >= nenv * 8 recommended)     */
 };

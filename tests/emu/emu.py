@@ -76,7 +76,7 @@ class EmuEnv:
     """Host emulation of dex_env_reset / dex_env_step (kernel bodies run by the fiber emulator)."""
 
     FIELD = dict(QPOS=0, QVEL=1, CTRL=2, QACC_WARMSTART=3, TIME=4, STATUS=5, CONTACT=6, NCON=7, NITER=8, OBS=14, REWARD=15,
-                 DISCOUNT=16, NSLOT=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31)
+                 DISCOUNT=16, NSLOT=17, GOAL=18, TASK_I=19, TASK_F=20, RNG=21, ACTION=22, EPISODE_STATS=24, RESET_MASK=25, SKIP=26, JC=27, MSCR=28, XKIN=29, TREE=30, STAGE=31, TIME64=33)
 
     def __init__(self, model: EmuModel, params, nenv: int, dtype=np.float32, seed: int = 1):
         self.m, self.p, self.n, self.dtype = model, params, nenv, dtype
@@ -86,10 +86,11 @@ class EmuEnv:
                       NITER=z(nenv, dt=np.int32), OBS=z(nenv, 128), REWARD=z(nenv), DISCOUNT=z(nenv), GOAL=z(nenv, 16),
                       TASK_I=z(nenv, 8, dt=np.int32), TASK_F=z(nenv, 8), RNG=z(nenv, 4, dt=np.uint32), ACTION=z(nenv, 32),
                       EPISODE_STATS=z(8, dt=np.float64), RESET_MASK=z(nenv, dt=np.uint8), SKIP=z(nenv, dt=np.uint8), JC=z(nenv, 3 * MAXCON, 32), MSCR=z(nenv, 32, 32),
-                      XKIN=z(nenv, 40 * 16), TREE=z(nenv, 8 * 32), STAGE=z(nenv, 64, 8), NSLOT=z(nenv, dt=np.int32))
+                      XKIN=z(nenv, 40 * 16), TREE=z(nenv, 8 * 32), STAGE=z(nenv, 64, 8), NSLOT=z(nenv, dt=np.int32),
+                      TIME64=z(nenv, 2, dt=np.float64))
         self.a["RNG"][:, 0] = seed
-        self.ptrs = (ctypes.c_void_p * 32)()
-        self.strides = (ctypes.c_int64 * 32)()
+        self.ptrs = (ctypes.c_void_p * 40)()
+        self.strides = (ctypes.c_int64 * 40)()
         for k, arr in self.a.items():
             self.ptrs[self.FIELD[k]] = arr.ctypes.data
             self.strides[self.FIELD[k]] = arr.strides[0] // arr.itemsize if arr.ndim > 1 else 1

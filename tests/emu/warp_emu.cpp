@@ -105,7 +105,7 @@ struct EmuModelT {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
-    dev.timestep = (T)h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
+    dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
 #define DEX_X_R(name) v_##name.assign(h.name.begin(), h.name.end()); dev.name = v_##name.data();
@@ -254,8 +254,9 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
                         (T*)f[DEX_FIELD_TREE]};
     TaskState<T> ts = {(const T*)f[DEX_FIELD_ACTION], (int)stride[DEX_FIELD_ACTION], (T*)f[DEX_FIELD_OBS], (T*)f[DEX_FIELD_REWARD],
                        (T*)f[DEX_FIELD_DISCOUNT], (T*)f[DEX_FIELD_GOAL], (int*)f[DEX_FIELD_TASK_I], (T*)f[DEX_FIELD_TASK_F],
-                       (unsigned*)f[DEX_FIELD_RNG], (unsigned char*)f[DEX_FIELD_SKIP], (const unsigned char*)f[DEX_FIELD_RESET_MASK],
+                       (unsigned*)f[DEX_FIELD_RNG], (unsigned char*)f[DEX_FIELD_SKIP], (unsigned char*)f[DEX_FIELD_RESET_MASK],
                        (double*)f[DEX_FIELD_EPISODE_STATS]};
+    st.time64 = (double*)f[DEX_FIELD_TIME64];
     DynDebug<T> dbg = {nullptr, nullptr, nullptr, nullptr, nullptr};
     auto work = [&](int lo, int hi) {
       std::vector<T> smem(std::max<int>(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T), DEX_K0_SMEM_T) + 64);

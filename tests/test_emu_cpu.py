@@ -80,6 +80,29 @@ def _params(c):
     return p
 
 
+def test_reset_request_is_consumed_and_time_is_double(reorient_model, emu_model):
+    """the RESET_MASK byte is cleared by the pre-step that serves it (the env is MID on the next call), and
+    data.time advances in double (time += timestep per mj_step, as MuJoCo does) although the batch is FP32."""
+    env = E.EmuEnv(emu_model, _params(reorient_model), nenv=2, dtype=np.float32, seed=4)
+    env.reset()
+    a = env.a
+    env.step(np.zeros((2, 20)), nsub=2)
+    assert (a["TASK_I"][:, 6] == 1).all()
+    a["RESET_MASK"][0] = 1
+    env.step(np.zeros((2, 20)), nsub=2)
+    assert a["RESET_MASK"][0] == 0 and a["TASK_I"][0, 6] == 0 and a["TASK_I"][1, 6] == 1
+    assert a["TIME64"][0, 0] == 0.0 and a["TIME"][0] == 0.0
+    env.step(np.zeros((2, 20)), nsub=2)
+    assert a["TASK_I"][0, 6] == 1, "an env reset through the mask resumes MID steps without manual clearing"
+    h = reorient_model.opt("TIMESTEP")
+    t2 = (0.0 + h) + h
+    t6 = t2
+    for _ in range(4):
+        t6 += h
+    assert a["TIME64"][0, 0] == t2 and a["TIME64"][1, 0] == t6
+    assert a["TIME"][1] == np.float32(t6)
+
+
 def test_task_kernels_against_restatement(reorient_model, emu_model):
     c = reorient_model
     env = E.EmuEnv(emu_model, _params(c), nenv=6, dtype=np.float64, seed=9)

@@ -99,7 +99,22 @@ def test_dm_env_auto_reset_semantics(env):
     torch.cuda.synchronize()
     assert (ts.step_type[::2] == 0).all() and (ts.step_type[1::2] != 0).all()
     assert (env.physics.time[::2] == 0).all() and (env.physics.time[1::2] > 0).all()
-    env.request_reset(torch.zeros_like(mask))
+    # the request is consumed by the step that served it: the same envs are MID on the next call,
+    # without the caller clearing anything
+    ts = env.step(a)
+    torch.cuda.synchronize()
+    assert (env._reset_mask == 0).all()
+    assert (ts.step_type[::2] == 1).all(), "an env reset through the mask must resume MID steps on the following call"
+    assert (env.physics.time[::2] > 0).all()
+    # data.time advances in double whatever the batch dtype (MuJoCo: time += timestep once per mj_step)
+    t64 = env.physics.time64[:, 0].cpu().numpy()
+    acc, sums = 0.0, []
+    for _ in range(2 * env.n_sub_steps):
+        acc += env.physics_timestep
+        sums.append(acc)
+    assert (t64[::2] == sums[env.n_sub_steps - 1]).all()
+    still = (ts.step_type[1::2] == 1).cpu().numpy()
+    assert still.any() and (t64[1::2][still] == sums[-1]).all()
     # drive envs until some terminate (cube falls with random actions), then check LAST -> FIRST
     lo = torch.as_tensor(env.action_spec().minimum, device=env.device)
     hi = torch.as_tensor(env.action_spec().maximum, device=env.device)

@@ -40,6 +40,27 @@ def test_reach_4096_single_step_matches_oracle():
     assert np.median(ev) <= 1e-6
 
 
+def test_reach_dense_reward_matches_tanh_squared():
+    """reach/state_dense reward = mean over fingers of 0 inside 1 cm, else -tanh_squared(d, margin=0.1)
+    (reference reach.py:196-205, shared/rewards.py:18-28): compared with the oracle's restatement at the
+    goal distances the step reports; tanh^2 at the margin is the reference's loss_at_margin = 0.95."""
+    from dexterity_b200 import envs
+    from oracle import task_oracle
+    env = envs.load("reach", "state_dense", seed=321, num_envs=256)
+    env.reset()
+    ts = env.step(torch.zeros(256, 20, device=env.device))
+    torch.cuda.synchronize()
+    d = env.goal_distance.cpu().numpy().astype(np.float64)
+    mid = ts.step_type.cpu().numpy() == 1
+    assert mid.sum() > 200
+    want = np.array([task_oracle.reach_reward(d[e], dense=True) for e in range(256)])
+    got = ts.reward.cpu().numpy().astype(np.float64)
+    assert (d[mid] > 0.01).any() and (want[mid] < -1e-3).any()
+    np.testing.assert_allclose(got[mid], want[mid], rtol=2e-5, atol=2e-6)
+    w = env._params.reach_tanh_weight
+    assert abs(np.tanh(w * 0.1) ** 2 - 0.95) < 1e-12 and abs(w - 21.78272210300875) < 1e-9
+
+
 def test_reach_behaviour_like_reference():
     from dexterity_b200 import envs
     env = envs.load("reach", "state_sparse", seed=12345, num_envs=64)
