@@ -52,6 +52,7 @@ def lib() -> ctypes.CDLL:
         L.dex_launch_count.argtypes = [ctypes.c_void_p]
         L.dex_capacity.argtypes = [ctypes.c_int]
         L.dex_set_chunks.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.dex_set_solver.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -127,6 +128,8 @@ class PhysicsBatch:
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
         self.set_chunks(int(os.environ.get("DEX_CHUNKS", "1")))
+        if os.environ.get("DEX_DENSE_SOLVER"):
+            self.set_solver(dense_only=True)
         # public views with the model's true widths
         self.qpos = self._store["QPOS"][:, :c.nq]
         self.qvel = self._store["QVEL"][:, :c.nv]
@@ -164,6 +167,11 @@ class PhysicsBatch:
     def set_chunks(self, nchunk: int) -> None:
         """Env chunks that run as independent kernel pipelines on library-owned streams (1..4)."""
         _check(lib().dex_set_chunks(self._ptr, int(nchunk)))
+
+    def set_solver(self, dense_only: bool) -> None:
+        """False (default): envs whose Newton Hessian is block-arrowhead take the structured 8-lanes-per-env solver kernel,
+        the others the dense warp-per-env one; True: the dense kernel for every env."""
+        _check(lib().dex_set_solver(self._ptr, int(bool(dense_only))))
 
     def step(self, nsub: int = 1) -> None:
         """nsub x mj_step (collision, constraint solve, Euler integration)."""

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/dexterity_b200.h"
+#include "dex_arrow.cuh"
 #include "dex_collide.cuh"
 #include "dex_dynamics.cuh"
 #include "dex_host_model.h"
@@ -154,19 +155,45 @@ __global__ void __launch_bounds__(kCollideWarps * 32, DEX_K1_MINB * kWarpsPerBlo
 constexpr int kDynWarps = DEX_K2_WARPS;
 template <typename T>
 __global__ void __launch_bounds__(kDynWarps * 32, DEX_K2_CTAS / DEX_K2_WARPS) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
-                                                                   int integrate) {
+                                                                   int integrate, int nclass) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int slot = st.env0 + blockIdx.x * kDynWarps + warp;
   if (slot >= st.nenv) return;
   int env = slot;
-  if (st.order) {   // K1c's lists, heaviest class first
+  if (st.order) {   // K1c's lists, heaviest class first; `nclass` leading classes are this kernel's (the rest: k_dynamics_arrow)
     int s = slot - st.env0, c = 0;
-    while (c < DEX_NCLASS - 1 && s >= st.nwork[2 + c]) { s -= st.nwork[2 + c]; ++c; }
+    int cnt[DEX_NCLASS];   // all class counters in one go (a walk of dependent loads costs an L2 round trip per class)
+#pragma unroll
+    for (int k = 0; k < DEX_NCLASS; ++k) cnt[k] = st.nwork[2 + k];
+#pragma unroll
+    for (int k = 0; k < DEX_NCLASS; ++k) if (c == k && k < nclass && s >= cnt[k]) { s -= cnt[k]; ++c; }
+    if (c >= nclass) return;
     env = st.order[(size_t)c * st.order_stride + st.env0 + s];
   }
   T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
   dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
+}
+
+// K2A: structured solver, eight lanes per env.  Warp w takes the envs 4 w .. 4 w + 3 of the concatenated class lists
+// DEX_NCLASS_DENSE .. DEX_NCLASS - 1 (most contacts first).
+#ifndef DEX_K2A_CTAS
+#define DEX_K2A_CTAS 8    // up to 255 registers: the solver state lives in registers; with more resident warps the spills and the lost L1 cost more than the residency gains (6 / 8 / 10 / 12 / 16 / 20 CTAs per SM: 0.156 / 0.157 / 0.173 / 0.175 / 0.215 / 0.283 ms per launch)
+#endif
+template <typename T>
+__global__ void __launch_bounds__(32, DEX_K2A_CTAS) k_dynamics_arrow(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg, int integrate) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  int s = blockIdx.x * DEX_AR_ENVS + (lane >> 3), c = DEX_NCLASS_DENSE;
+  if (blockIdx.x * DEX_AR_ENVS >= st.nenv - st.env0) return;
+  int cnt[DEX_NCLASS - DEX_NCLASS_DENSE];   // the class counters in one go (a walk of dependent loads costs an L2 round trip per class)
+#pragma unroll
+  for (int k = 0; k < DEX_NCLASS - DEX_NCLASS_DENSE; ++k) cnt[k] = st.nwork[2 + DEX_NCLASS_DENSE + k];
+#pragma unroll
+  for (int k = 0; k < DEX_NCLASS - DEX_NCLASS_DENSE; ++k) if (c == DEX_NCLASS_DENSE + k && s >= cnt[k]) { s -= cnt[k]; ++c; }
+  const int env = c < DEX_NCLASS ? st.order[(size_t)c * st.order_stride + st.env0 + s] : -1;
+  if (__ballot_sync(0xffffffffu, env >= 0) == 0) return;
+  dex_arrow_warp<T>(m, st, dbg, env, reinterpret_cast<T*>(smem_raw), integrate);
 }
 
 template <typename T>
@@ -216,6 +243,9 @@ struct DeviceArrays {
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
+    dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo;
+    std::memcpy(dev.arrow_bdof, h.arrow_bdof, sizeof(dev.arrow_bdof)); std::memcpy(dev.arrow_odof, h.arrow_odof, sizeof(dev.arrow_odof));
+    std::memcpy(dev.arrow_bmask, h.arrow_bmask, sizeof(dev.arrow_bmask)); std::memcpy(dev.arrow_rowdof, h.arrow_rowdof, sizeof(dev.arrow_rowdof));
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name)                                                                         \
@@ -272,6 +302,10 @@ struct DexBatch {
   bool attrs_set = false;
   // env chunks run as independent pipelines on library-owned streams (forked from / joined to the caller's)
   bool tree_scalar = false;  // force the thread-per-env tree kernel (tests / tuning)
+  bool dense_only = false;   // force the dense solver for every env (tests / tuning)
+  // the two solver kernels work on disjoint envs: the structured one runs on a second stream, forked after K1c and joined before the next K0
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_k1c = nullptr, ev_k2a = nullptr;
   int nchunk = 1;
   cudaStream_t cs[DEX_MAXCHUNK] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[DEX_MAXCHUNK] = {nullptr, nullptr, nullptr, nullptr};
@@ -279,9 +313,9 @@ struct DexBatch {
   bool task_set = false;
   // optional per-kernel-class timing (cudaEvent pairs recorded on the launching stream)
   bool profiling = false;
-  std::vector<cudaEvent_t> ev[8];   // class: 0 pre, 1 collide, 2 dynamics, 3 post, 4 tree; pairs (start, stop)
-  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<cudaEvent_t> ev[10];   // class: 0 pre, 1 broadphase, 2 dense solve, 3 post, 4 tree, 5 narrowphase, 6 compaction, 7 structured solve, 8 placement; pairs (start, stop)
+  double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t count[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -359,6 +393,7 @@ int set_attrs(DexBatch* b) {
   if (b->attrs_set) return DEX_OK;
   DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T))));
   DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute(k_dynamics_arrow<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DEX_K2A_SMEM_T * sizeof(T))));
   // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
   DEX_CUDA(cudaFuncSetAttribute(k_tree<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   DEX_CUDA(cudaFuncSetAttribute(k_tree8<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T))));
@@ -378,6 +413,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
   if (rc) return rc;
   const size_t smem1 = (size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T);
   const size_t smem2 = (size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T);
+  const size_t smem2a = (size_t)DEX_K2A_SMEM_T * sizeof(T);
   int nchunk = b->nchunk;
   if (b->nenv < 1024 * nchunk) nchunk = 1;
   if (st.work_cap / nchunk < 64) nchunk = 1;
@@ -419,7 +455,26 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
         { ProfScope ps(b, 5, cs); k_narrow<T><<<ngrid, kNarrowBlock, 0, cs>>>(m, st); b->launches++; }
         { ProfScope ps(b, 6, cs); k_compact<T><<<(n + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, cs>>>(m, st); b->launches++; }
       }
-      if (dynamics) { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate); b->launches++; }
+      if (dynamics) {
+        // envs whose Hessian is block-arrowhead take the structured solver (K1c filed them in classes 4-7), the rest the dense one
+        const bool arrow = m.arrow_ok && st.order && collide && !b->dense_only && !dbg.M;
+        if (arrow && nchunk == 1 && !b->profiling && !getenv("DEX_SOLVER_SERIAL")) {
+          if (!b->s2) {
+            DEX_CUDA(cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking));
+            DEX_CUDA(cudaEventCreateWithFlags(&b->ev_k1c, cudaEventDisableTiming));
+            DEX_CUDA(cudaEventCreateWithFlags(&b->ev_k2a, cudaEventDisableTiming));
+          }
+          DEX_CUDA(cudaEventRecord(b->ev_k1c, cs));
+          DEX_CUDA(cudaStreamWaitEvent(b->s2, b->ev_k1c, 0));
+          k_dynamics_arrow<T><<<(n + DEX_AR_ENVS - 1) / DEX_AR_ENVS, 32, smem2a, b->s2>>>(m, st, dbg, integrate); b->launches++;
+          DEX_CUDA(cudaEventRecord(b->ev_k2a, b->s2));
+          { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, DEX_NCLASS_DENSE); b->launches++; }
+          DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_k2a, 0));
+        } else {
+        { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, arrow ? DEX_NCLASS_DENSE : DEX_NCLASS); b->launches++; }
+        if (arrow) { ProfScope ps(b, 7, cs); k_dynamics_arrow<T><<<(n + DEX_AR_ENVS - 1) / DEX_AR_ENVS, 32, smem2a, cs>>>(m, st, dbg, integrate); b->launches++; }
+        }
+      }
     }
     if (nchunk > 1) { DEX_CUDA(cudaEventRecord(b->ev_join[c], cs)); DEX_CUDA(cudaStreamWaitEvent(s, b->ev_join[c], 0)); }
   }
@@ -467,7 +522,7 @@ int run_env(DexBatch* b, const DevModel<T>& m, int nsub, int force_reset, cudaSt
     for (int r = 0; r < b->task.place_max_attempts; ++r) {
       rc = launch_physics<T>(b, m, sp, dbg, 1, true, false, 0, s);
       if (rc) return rc;
-      ProfScope ps(b, 7, s);
+      ProfScope ps(b, 8, s);
       k_place<T><<<grid, block, 0, s>>>(m, sp, ts, b->task);
       b->launches++;
     }
@@ -557,6 +612,7 @@ void dex_batch_destroy(DexBatch* b) {
   if (!b) return;
   DeviceGuard guard_(b->model->device);
   for (auto& v : b->ev) { for (cudaEvent_t e : v) cudaEventDestroy(e); v.clear(); }   // profiling events not yet collected
+  if (b->s2) { cudaStreamDestroy(b->s2); cudaEventDestroy(b->ev_k1c); cudaEventDestroy(b->ev_k2a); }
   if (b->ev_fork) {
     cudaEventDestroy(b->ev_fork);
     for (int c = 0; c < DEX_MAXCHUNK; ++c) { cudaStreamDestroy(b->cs[c]); cudaEventDestroy(b->ev_join[c]); }
@@ -567,6 +623,12 @@ void dex_batch_destroy(DexBatch* b) {
 int dex_set_tree_kernel(DexBatch* b, int scalar) {
   if (!b) return fail(DEX_E_ARG, "null batch");
   b->tree_scalar = scalar != 0;
+  return DEX_OK;
+}
+
+int dex_set_solver(DexBatch* b, int dense_only) {
+  if (!b) return fail(DEX_E_ARG, "null batch");
+  b->dense_only = dense_only != 0;
   return DEX_OK;
 }
 
@@ -637,19 +699,19 @@ int dex_set_profiling(DexBatch* b, int on) {
   return DEX_OK;
 }
 // Synchronises the device, folds the recorded event pairs into per-class totals and returns
-// ms[8] (total milliseconds) and count[8] (launches) for pre / broadphase / solve / post / tree / narrowphase / compaction / (reserved).
+// ms[8] (total milliseconds) and count[8] (launches) for pre / broadphase / dense solve / post / tree / narrowphase / compaction / structured solve.
 int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
   if (!b || !ms || !count) return fail(DEX_E_ARG, "null argument");
   DEX_ON_DEVICE(b->model->device);
   DEX_CUDA(cudaDeviceSynchronize());
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 10; ++c) {
     for (size_t i = 0; i + 1 < b->ev[c].size(); i += 2) {
       float t = 0;
       if (cudaEventElapsedTime(&t, b->ev[c][i], b->ev[c][i + 1]) == cudaSuccess) { b->ms[c] += t; b->count[c]++; }
       cudaEventDestroy(b->ev[c][i]); cudaEventDestroy(b->ev[c][i + 1]);
     }
     b->ev[c].clear();
-    ms[c] = b->ms[c]; count[c] = b->count[c];
+    if (c < 8) { ms[c] = b->ms[c]; count[c] = b->count[c]; }
     if (reset) { b->ms[c] = 0; b->count[c] = 0; }
   }
   return DEX_OK;

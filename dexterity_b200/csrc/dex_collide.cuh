@@ -27,6 +27,8 @@
 #define DEX_MAXBPL 128     // body pairs that survive the body-level culls
 #define DEX_K1_SMEM_T (DEX_MAXBODY * 16 + DEX_MAXGEOM * 4 + DEX_MAXCAND1 + DEX_MAXBPL + 8 * 4)
 #define DEX_NCLASS 8       // solver-cost classes of K2's processing order
+#define DEX_NCLASS_DENSE 4 // with the structured solver on (DevModel::arrow_ok): classes 0-3 dense kernel, 4-7 structured kernel
+#define DEX_AR_MAXCON_K1 8 // = DEX_AR_MAXCON (dex_arrow.cuh)
 #define DEX_WORK_HDR 16     // words before the first work item: count, cursor, DEX_NCLASS class counters
 #define DEX_MAXSLOT 64     // staging slots per env (one per convex-convex candidate, four per plane-box pair)
 #define DEX_STAGE_ENV (DEX_MAXSLOT * DEX_CON_STRIDE)
@@ -832,13 +834,13 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
 // the class list (one global atomic per class and CTA).
 template <typename T>
 DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
-  if (dex_env_off(st, env)) return DEX_NCLASS - 1;   // warp-uniform; a skipped env still needs its place in the order
+  if (dex_env_off(st, env)) return m.arrow_ok ? -1 : DEX_NCLASS - 1;   // warp-uniform; with the two-kernel order a skipped env is simply not listed
   const int lane = dex_lane();
   const int nslot = st.nslot[env];
   const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
   T* cout = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
   int ncon = 0;
-  bool overflow = false;
+  bool overflow = false, cross = false;
   for (int s0 = 0; s0 < nslot; s0 += 32) {
     const int sl = s0 + lane;
     T rec[DEX_CON_STRIDE];
@@ -852,6 +854,14 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
     if (valid) {
       if (idx < DEX_MAXCON) { for (int k = 0; k < DEX_CON_STRIDE; ++k) cout[idx * DEX_CON_STRIDE + k] = rec[k]; }
       else overflow = true;
+      if (m.arrow_ok) {   // does the contact join two branches of the arrowhead split (finger - finger)?
+        const int pr = (int)rec[7];
+        const unsigned mx = (unsigned)dex_ldg(m.body_dofmask + dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr))) ^
+                            (unsigned)dex_ldg(m.body_dofmask + dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr)));
+        int nbr = 0;
+        for (int a = 0; a < 5; ++a) nbr += (mx & (unsigned)m.arrow_bmask[a]) ? 1 : 0;
+        cross = cross || nbr > 1;
+      }
     }
     ncon += dex_popc(vm);
   }
@@ -862,9 +872,17 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
   // 2.4, 3.5, 4.4, 5.2, 5.9, ...), so envs with contacts go first and the kernel does not end on a few long-running
   // warps (r01n: the SMs idled 14 % of K2's duration).  Keying on the previous step's iteration count instead was
   // slower: envs with equal contact counts also share code paths and cache lines.
+  if (m.arrow_ok) {
+    // Two solver kernels: classes 0-3 = dense warp-per-env solver (dex_dynamics.cuh), classes 4-7 = structured solver with
+    // eight lanes per env (dex_arrow.cuh) for envs whose Hessian is block-arrowhead: no contact joins two branches and the
+    // contacts fit one lane each.  Within each kernel the envs with the most contacts go first; envs with equal contact
+    // counts share a warp in the structured kernel (four envs per warp run as long as the slowest).
+    const bool arrow = !dex_ballot(cross) && ncon <= DEX_AR_MAXCON_K1;
+    if (arrow) return ncon >= 4 ? 4 : (ncon >= 2 ? 5 : (ncon == 1 ? 6 : 7));
+    return ncon >= 7 ? 0 : (ncon >= 4 ? 1 : (ncon >= 2 ? 2 : 3));
+  }
   const int key = ncon + 2;
   const int cls = key >= 9 ? 0 : (9 - key > DEX_NCLASS - 1 ? DEX_NCLASS - 1 : 9 - key);
-  (void)m;
   return cls;
 }
 

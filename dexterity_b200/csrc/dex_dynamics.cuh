@@ -499,8 +499,11 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     }
     dex_syncwarp();
     const T q1 = isdof ? search * (Ma - fs) : T(0), q2 = isdof ? search * Mv : T(0);
-    T alpha = 0, lo = 0, hi = -1, g0 = 0;
-    for (int ls = 0; ls < 24; ++ls) {
+    // The first Newton step of the 1-D problem needs no row pass: at alpha = 0 the derivative is search . grad and the
+    // curvature search . H search = -search . grad (H search = -grad), so the step lands on alpha = 1 exactly.
+    const T g0 = dex_warp_sum(isdof ? search * grad : T(0));
+    T alpha = g0 < 0 ? T(1) : T(0), lo = 0, hi = -1;   // not a descent direction: alpha stays 0
+    for (int ls = 1; ls < 24 && g0 < 0; ++ls) {
       T g = q1 + alpha * q2, hh = q2;
       {  // friction loss and limit rows, branch-free (same regimes as in the force update above)
         const T x = qacc + alpha * search - f_aref, lim = f_R * f_loss;
@@ -522,15 +525,15 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       }
       g = dex_warp_sum(g);
       hh = dex_warp_sum(hh);
-      if (ls == 0) {
-        g0 = g;
-        if (!(g < 0) || !(hh > 0)) break;  // not a descent direction: alpha stays 0
-      } else if (dx_abs(g) <= (sizeof(T) == 4 ? T(1e-3) : T(1e-12)) * dx_abs(g0)) break;
+      if (dx_abs(g) <= (sizeof(T) == 4 ? T(1e-3) : T(1e-12)) * dx_abs(g0)) break;
       if (g < 0) lo = alpha; else hi = alpha;
       T next = alpha - g / hh;
       if (hi >= 0 && (next <= lo || next >= hi)) next = T(0.5) * (lo + hi);
-      if (next == alpha) break;
+      // converged in alpha: FP32 cannot push |g| below its rounding noise once g0 is small, and the outer Newton iteration
+      // absorbs an error of this size in the step length
+      const bool conv = dx_abs(next - alpha) <= (sizeof(T) == 4 ? T(1e-4) : T(1e-12)) * dx_abs(next);
       alpha = next;
+      if (conv) break;
     }
     if (alpha == 0) break;
     // MuJoCo's stopping rule "improvement * scale < tolerance", with the improvement taken from the

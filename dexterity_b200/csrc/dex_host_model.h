@@ -21,6 +21,7 @@ struct HostModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
   int k0_rounds, chol_split;
+  int arrow_ok, arrow_nmo, arrow_bdof[5][5], arrow_odof[8], arrow_bmask[5], arrow_rowdof[24];
   double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
@@ -176,6 +177,83 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
   {  // largest multiple of 4 at which the dofs split into two groups of whole kinematic trees (M is block diagonal there)
     M.chol_split = nv;
     for (int s4 = 4; s4 < nv; s4 += 4) if (M.dof_tree[s4] != M.dof_tree[s4 - 1]) M.chol_split = s4;
+  }
+  // ---- arrowhead decomposition for the structured solver (dex_arrow.cuh).  Border = every dof with two or more child
+  //      dofs plus its ancestors (the rows above the branching point), followed by the dofs of trees without branching
+  //      (a free object); the connected pieces that remain are the branches.  M couples a branch only to itself and to
+  //      its border ancestors, so H = M + diag + J^T W J is block-arrowhead as long as no contact joins two branches.
+  {
+    M.arrow_ok = 1; M.arrow_nmo = 0;
+    for (int a = 0; a < 5; ++a) { M.arrow_bmask[a] = 0; for (int k = 0; k < 5; ++k) M.arrow_bdof[a][k] = -1; }
+    for (int r = 0; r < 8; ++r) M.arrow_odof[r] = -1;
+    std::vector<int> nchild(nv, 0), isborder(nv, 0), tree_branches(M.ntree, 0);
+    for (int i = 0; i < nv; ++i) if (M.dof_parent[i] >= 0) nchild[M.dof_parent[i]]++;
+    for (int i = 0; i < nv; ++i) if (nchild[i] >= 2) { tree_branches[M.dof_tree[i]] = 1; for (int j = i; j >= 0; j = M.dof_parent[j]) isborder[j] = 1; }
+    int nbo = 0;
+    for (int i = 0; i < nv; ++i) if (isborder[i]) { if (nbo < 8) M.arrow_odof[nbo] = i; nbo++; }
+    M.arrow_nmo = nbo;
+    for (int i = 0; i < nv; ++i) if (!tree_branches[M.dof_tree[i]]) { isborder[i] = 1; if (nbo < 8) M.arrow_odof[nbo] = i; nbo++; }
+    if (nbo > 8 || M.arrow_nmo > 2 || M.arrow_nmo == 0) M.arrow_ok = 0;
+    int nbr = 0;
+    std::vector<int> branch_of(nv, -1);
+    for (int i = 0; i < nv && M.arrow_ok; ++i) {
+      if (isborder[i]) continue;
+      const int p = M.dof_parent[i];
+      int a = (p >= 0 && !isborder[p]) ? branch_of[p] : -1;
+      if (a < 0) { if (nbr == 5) { M.arrow_ok = 0; break; } a = nbr++; }
+      branch_of[i] = a;
+      int k = 0;
+      while (k < 5 && M.arrow_bdof[a][k] >= 0) ++k;
+      if (k == 5) { M.arrow_ok = 0; break; }
+      M.arrow_bdof[a][k] = i; M.arrow_bmask[a] |= 1 << i;
+    }
+    // the reduced implicit-Euler solve takes the damped trees = the branches and the leading border rows
+    for (int i = 0; i < nv && M.arrow_ok; ++i) {
+      bool lead = !isborder[i];
+      for (int r = 0; r < M.arrow_nmo; ++r) if (M.arrow_odof[r] == i) lead = true;
+      if (lead != (i < M.nv_euler)) M.arrow_ok = 0;
+    }
+    {
+      int nrow = 0;
+      for (int r = 0; r < 24; ++r) M.arrow_rowdof[r] = -1;
+      for (int i = 0; i < nv; ++i) {
+        const int j = M.dof_jnt[i];
+        const bool limited = M.jnt_limited[j] && M.jnt_type[j] >= DEX_JNT_SLIDE;
+        if (!(M.dof_frictionloss[i] > 0) && !limited) continue;
+        if (nrow < 24) M.arrow_rowdof[nrow] = i;
+        nrow++;
+      }
+      if (nrow > 24) M.arrow_ok = 0;
+    }
+    M.arrow_tab.assign(64 + 24, -1);
+    for (int g = 0; g < 8; ++g) {
+      for (int k = 0; k < 5; ++k) if (g < 5) M.arrow_tab[8 * g + k] = M.arrow_bdof[g][k];
+      M.arrow_tab[8 * g + 5] = M.arrow_odof[g];
+    }
+    for (int r = 0; r < 24; ++r) M.arrow_tab[64 + r] = M.arrow_rowdof[r];
+    M.dof_pidx.assign(std::max(1, nv), 0);   // packed position of a dof: 5 * branch + slot, or 32 + border row
+    if (M.arrow_ok) {
+      for (int a = 0; a < 5; ++a) for (int k = 0; k < 5; ++k) if (M.arrow_bdof[a][k] >= 0) M.dof_pidx[M.arrow_bdof[a][k]] = 5 * a + k;
+      for (int r = 0; r < 8; ++r) if (M.arrow_odof[r] >= 0) M.dof_pidx[M.arrow_odof[r]] = 32 + r;
+    }
+    // dof friction-loss rows are state independent up to aref = -B qvel (mj_makeImpedance at pos = margin = 0):
+    // per dof {R * frictionloss, D = 1 / R, B, 0}; {huge, 0, 0, 0} without friction loss
+    M.dof_flrow.assign(std::max(1, 4 * nv), 0.0);
+    for (int i = 0; i < nv; ++i) {
+      double* o = &M.dof_flrow[4 * i];
+      o[0] = 1e30; o[1] = 0; o[2] = 0;
+      const double fl = M.dof_frictionloss[i];
+      if (fl > 0) {
+        const double* si = &M.dof_solimp[5 * i];
+        const double* sr = &M.dof_solref[2 * i];
+        const double imp = std::min(std::max(si[0], 0.0001), 0.9999), dmax = std::min(std::max(si[1], 0.0001), 0.9999);
+        const double R = std::max(1e-15, (1 - imp) / imp * M.dof_invweight0[i]);
+        double B;
+        if (sr[0] > 0) { const double tc = std::max(sr[0], 2 * M.timestep); B = 2 / std::max(1e-15, dmax * tc); }
+        else B = -sr[1] / std::max(1e-15, dmax);
+        o[0] = R * fl; o[1] = 1 / R; o[2] = B;
+      }
+    }
   }
   M.body_dofmask.assign(nb, 0);
   for (int b = 1; b < nb; ++b) {

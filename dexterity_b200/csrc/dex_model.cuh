@@ -52,7 +52,8 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(I, bp_body1) X(I, bp_body2) X(I, bp_pairadr) X(I, bp_pairnum)                          \
   X(I, pair_geom1) X(I, pair_geom2) X(I, pair_gg) X(I, pair_condim) X(R, pair_friction) X(R, pair_solref) \
   X(R, pair_solimp) X(R, pair_margin) X(R, pair_gap)                                       \
-  X(I, site_body) X(R, site_pos)
+  X(I, site_body) X(R, site_pos)                                                           \
+  X(I, dof_pidx) X(R, dof_flrow) X(I, arrow_tab)
 
 template <typename T>
 struct DevModel {
@@ -62,6 +63,17 @@ struct DevModel {
   int k0_rounds;  // rounds of the 8-lanes-per-env tree kernel schedule (0 = model does not fit: thread-per-env kernel)
   T timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
   double timestep_d;  // opt.timestep unrounded: data.time advances in double whatever the batch dtype
+  // "arrowhead" decomposition of the dofs for the structured solver kernel (dex_arrow.cuh): up to 5 BRANCHES of up to 5 dofs
+  // (subtrees that M does not couple to each other, e.g. the fingers) and a BORDER of up to 8 dofs (the dofs above the
+  // branching point, e.g. the wrist, followed by the dofs of unbranched trees, e.g. a free object).  -1 = identity padding.
+  int arrow_ok;          // 0: the model does not fit, every env takes the dense solver
+  int arrow_nmo;         // leading border rows that M couples to the branches (<= 2); they are also the border rows with joint damping
+  int arrow_bdof[5][5];  // dof of (branch, slot), root to leaf
+  int arrow_odof[8];     // dof of border row r
+  int arrow_bmask[5];    // dof bit mask of each branch
+  int arrow_rowdof[24];  // dofs that own friction-loss / limit rows (-1 padded), dealt three to a lane in the row view
+  // the same tables as a device array for lane-indexed reads (arrow_tab): [8 lanes][8] = branch dofs 0-4, border dof 5, -, - then [24] rows
+#define DEX_AR_TAB_ROWS 64
 #define DEX_X_I(name) const int* name;
 #define DEX_X_R(name) const T* name;
 #define DEX_X(t, name) DEX_X_##t(name)

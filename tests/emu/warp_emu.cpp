@@ -8,12 +8,14 @@
 #define DEX_WARP_EMU 1
 #include <ucontext.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <thread>
 #include <vector>
 
+#include "../../dexterity_b200/csrc/dex_arrow.cuh"
 #include "../../dexterity_b200/csrc/dex_collide.cuh"
 #include "../../dexterity_b200/csrc/dex_dynamics.cuh"
 #include "../../dexterity_b200/csrc/dex_host_model.h"
@@ -105,7 +107,11 @@ struct EmuModelT {
     dev.nbody = h.nbody; dev.njnt = h.njnt; dev.nq = h.nq; dev.nv = h.nv; dev.nu = h.nu; dev.ntendon = h.ntendon;
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
-    dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep; for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
+    dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
+    dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo;
+    std::memcpy(dev.arrow_bdof, h.arrow_bdof, sizeof(dev.arrow_bdof)); std::memcpy(dev.arrow_odof, h.arrow_odof, sizeof(dev.arrow_odof));
+    std::memcpy(dev.arrow_bmask, h.arrow_bmask, sizeof(dev.arrow_bmask)); std::memcpy(dev.arrow_rowdof, h.arrow_rowdof, sizeof(dev.arrow_rowdof));
+    for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
     dev.tolerance = (T)h.tolerance; dev.mpr_tolerance = (T)h.mpr_tolerance; dev.meaninertia = (T)h.meaninertia; dev.max_margin = (T)h.max_margin;
 #define DEX_X_I(name) v_##name = h.name; dev.name = v_##name.data();
 #define DEX_X_R(name) v_##name.assign(h.name.begin(), h.name.end()); dev.name = v_##name.data();
@@ -124,14 +130,33 @@ struct EmuModel {
 
 // collision stage of one env: broadphase (warp), narrowphase (one plain call per work item),
 // compaction (warp).  The work list is private to the calling worker thread.
+static std::atomic<long> g_arrow_envs{0}, g_dense_envs{0};
+// returns the env's solver class (dex_compact_env): 4-7 = structured solver
 template <typename T>
-static void emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
+static int emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
   std::vector<int> work(DEX_WORK_HDR + 2 * DEX_MAXSLOT, 0);
   BatchState<T> sl = st;
   sl.nwork = work.data(); sl.work = work.data() + DEX_WORK_HDR; sl.work_cap = DEX_MAXSLOT; sl.order = nullptr;
   dex_emu::run_warp([&]() { dex_collide_env<T>(m, sl, env, smem); });
   for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[DEX_WORK_HDR + 2 * i], work[DEX_WORK_HDR + 1 + 2 * i]);  // K1b is thread-per-item
-  dex_emu::run_warp([&]() { dex_compact_env<T>(m, sl, env); });
+  int cls = -1;
+  dex_emu::run_warp([&]() { const int c = dex_compact_env<T>(m, sl, env); if (dex_lane() == 0) cls = c; });
+  return cls;
+}
+
+// K2 for the envs e0 .. e1-1 with their solver classes: the structured solver for classes >= DEX_NCLASS_DENSE (one warp
+// for the four envs, as on the GPU), the dense solver for the rest.  DEX_EMU_DENSE=1 forces the dense solver.
+template <typename T>
+static void emu_solve(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int e0, int e1, const int* cls, T* smem,
+                      int integrate) {
+  int quad[4] = {-1, -1, -1, -1};
+  const bool use_arrow = m.arrow_ok && !getenv("DEX_EMU_DENSE");
+  bool any = false;
+  for (int env = e0; env < e1; ++env) {
+    if (use_arrow && cls[env - e0] >= DEX_NCLASS_DENSE) { quad[env - e0] = env; any = true; g_arrow_envs++; }
+    else { dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem, integrate); }); g_dense_envs++; }
+  }
+  if (any) dex_emu::run_warp([&]() { dex_arrow_warp<T>(m, st, dbg, quad[dex_lane() >> 3], smem, integrate); });
 }
 
 // K0 for the envs e0 .. e0+3: the 8-lanes-per-env warp form when the model has a schedule, else one
@@ -146,16 +171,16 @@ template <typename T>
 static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int nsub, int integrate, int do_collide,
                     int do_dynamics, int nthreads) {
   auto work = [&](int lo, int hi) {
-    std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K0_SMEM_T) + 64);
+    std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), std::max<int>(DEX_K0_SMEM_T, DEX_K2A_SMEM_T)) + 64);
     BatchState<T> sb = st;
     sb.nenv = hi;   // the 4-env tree warps must not spill into another worker's range
     for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {
       for (int s = 0; s < nsub; ++s) {
         emu_tree<T>(m, sb, e0, smem.data());
-        for (int env = e0; env < std::min(hi, e0 + DEX_K0_ENVS); ++env) {
-          if (do_collide) emu_collide<T>(m, sb, env, smem.data());
-          if (do_dynamics) dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, sb, dbg, env, smem.data(), integrate); });
-        }
+        int cls[DEX_K0_ENVS] = {0, 0, 0, 0};
+        const int e1 = std::min(hi, e0 + DEX_K0_ENVS);
+        for (int env = e0; env < e1; ++env) if (do_collide) cls[env - e0] = emu_collide<T>(m, sb, env, smem.data());
+        if (do_dynamics) emu_solve<T>(m, sb, dbg, e0, e1, cls, smem.data(), integrate);
       }
     }
   };
@@ -176,6 +201,10 @@ void* emu_model_create(const void* blob, uint64_t nbytes, char* err, int errlen)
 }
 void emu_model_destroy(void* m) { delete (EmuModel*)m; }
 int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
+void emu_solver_counts(long* out, int reset) { out[0] = g_arrow_envs; out[1] = g_dense_envs; if (reset) { g_arrow_envs = 0; g_dense_envs = 0; } }
+#ifdef DEX_EMU_STATS
+void emu_ls_stats(long* out) { out[0] = dex_emu_ls_count; out[1] = dex_emu_newton_count; dex_emu_ls_count = 0; dex_emu_newton_count = 0; }
+#endif
 int emu_k0_rounds(void* m) { return ((EmuModel*)m)->host.k0_rounds; }
 
 // Hill-climbing support function of K1b against an exhaustive scan, for every mesh geom and `ndir` random
@@ -259,7 +288,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
     st.time64 = (double*)f[DEX_FIELD_TIME64];
     DynDebug<T> dbg = {nullptr, nullptr, nullptr, nullptr, nullptr};
     auto work = [&](int lo, int hi) {
-      std::vector<T> smem(std::max<int>(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T), DEX_K0_SMEM_T) + 64);
+      std::vector<T> smem(std::max<int>(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T), std::max<int>(DEX_K0_SMEM_T, DEX_K2A_SMEM_T)) + 64);
       BatchState<T> sb = st;
       sb.nenv = hi;
       for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {
@@ -281,10 +310,10 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
         }
         if (!force_reset) for (int s = 0; s < nsub; ++s) {
           emu_tree<T>(dev, sb, e0, smem.data());
-          for (int env = e0; env < e1; ++env) {
-            emu_collide<T>(dev, sb, env, smem.data());
-            dex_emu::run_warp([&]() { dex_dynamics_env<T>(dev, sb, dbg, env, smem.data(), 1); });
-          }
+          int cls[DEX_K0_ENVS] = {0, 0, 0, 0};
+          for (int env = e0; env < e1; ++env) cls[env - e0] = sb.skip && sb.skip[env] ? -1 : emu_collide<T>(dev, sb, env, smem.data());
+          for (int env = e0; env < e1; ++env) if (cls[env - e0] < 0) cls[env - e0] = 0;   // skipped envs: the dense body returns at once
+          emu_solve<T>(dev, sb, dbg, e0, e1, cls, smem.data(), 1);
         }
         for (int env = e0; env < e1; ++env) dex_emu::run_warp([&]() { dex_task_post_env<T>(dev, sb, ts, *p, env, smem.data()); });
       }

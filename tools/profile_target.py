@@ -3,6 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from dexterity_b200 import backend
+if os.environ.get("DEX_LIB"): backend.LIB_PATH = os.environ["DEX_LIB"]
 from dexterity_b200.model import scenes
 from tests import statelib
 
