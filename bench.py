@@ -236,7 +236,7 @@ def run_gpu(args):
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = env.physics.launch_count - launches0
-    ms4 = (ctypes.c_double * 8)(); cnt4 = (ctypes.c_int64 * 8)()
+    ms4 = (ctypes.c_double * 10)(); cnt4 = (ctypes.c_int64 * 10)()
     backend._check(lib.dex_get_kernel_times(env.physics.ptr, ms4, cnt4, 1))
     lib.dex_set_profiling(env.physics.ptr, 0)
     clocks = sampler.stop() if rank == 0 else None

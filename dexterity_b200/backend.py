@@ -128,8 +128,8 @@ class PhysicsBatch:
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
         self.set_chunks(int(os.environ.get("DEX_CHUNKS", "1")))
-        if os.environ.get("DEX_DENSE_SOLVER"):
-            self.set_solver(dense_only=True)
+        if os.environ.get("DEX_SOLVER_MODE"):
+            self.set_solver(int(os.environ["DEX_SOLVER_MODE"]))
         # public views with the model's true widths
         self.qpos = self._store["QPOS"][:, :c.nq]
         self.qvel = self._store["QVEL"][:, :c.nv]
@@ -168,10 +168,10 @@ class PhysicsBatch:
         """Env chunks that run as independent kernel pipelines on library-owned streams (1..4)."""
         _check(lib().dex_set_chunks(self._ptr, int(nchunk)))
 
-    def set_solver(self, dense_only: bool) -> None:
-        """False (default): envs whose Newton Hessian is block-arrowhead take the structured 8-lanes-per-env solver kernel,
-        the others the dense warp-per-env one; True: the dense kernel for every env."""
-        _check(lib().dex_set_solver(self._ptr, int(bool(dense_only))))
+    def set_solver(self, mode: int) -> None:
+        """0: dense warp-per-env solver for every env; 1 (default): envs without contacts take the structured
+        8-lanes-per-env solver kernel; 2: also envs with <= 8 contacts of which <= 2 join two fingers."""
+        _check(lib().dex_set_solver(self._ptr, int(mode)))
 
     def step(self, nsub: int = 1) -> None:
         """nsub x mj_step (collision, constraint solve, Euler integration)."""

@@ -180,20 +180,24 @@ __global__ void __launch_bounds__(kDynWarps * 32, DEX_K2_CTAS / DEX_K2_WARPS) k_
 #ifndef DEX_K2A_CTAS
 #define DEX_K2A_CTAS 8    // up to 255 registers: the solver state lives in registers; with more resident warps the spills and the lost L1 cost more than the residency gains (6 / 8 / 10 / 12 / 16 / 20 CTAs per SM: 0.156 / 0.157 / 0.173 / 0.175 / 0.215 / 0.283 ms per launch)
 #endif
-template <typename T>
-__global__ void __launch_bounds__(32, DEX_K2A_CTAS) k_dynamics_arrow(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg, int integrate) {
+#ifndef DEX_K2L_CTAS
+#define DEX_K2L_CTAS 12
+#endif
+// CON = true: classes [c0, c1) are envs with contacts (full form); CON = false: contact-free envs (class DEX_NCLASS - 1)
+template <typename T, bool CON>
+__global__ void __launch_bounds__(32, CON ? DEX_K2A_CTAS : DEX_K2L_CTAS) k_dynamics_arrow(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg, int integrate,
+                                                                                           int c0, int c1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  int s = blockIdx.x * DEX_AR_ENVS + (lane >> 3), c = DEX_NCLASS_DENSE;
-  if (blockIdx.x * DEX_AR_ENVS >= st.nenv - st.env0) return;
-  int cnt[DEX_NCLASS - DEX_NCLASS_DENSE];   // the class counters in one go (a walk of dependent loads costs an L2 round trip per class)
+  int s = blockIdx.x * DEX_AR_ENVS + (lane >> 3), c = c0;
+  int cnt[DEX_NCLASS];   // the class counters in one go (a walk of dependent loads costs an L2 round trip per class)
 #pragma unroll
-  for (int k = 0; k < DEX_NCLASS - DEX_NCLASS_DENSE; ++k) cnt[k] = st.nwork[2 + DEX_NCLASS_DENSE + k];
+  for (int k = 0; k < DEX_NCLASS; ++k) cnt[k] = st.nwork[2 + k];
 #pragma unroll
-  for (int k = 0; k < DEX_NCLASS - DEX_NCLASS_DENSE; ++k) if (c == DEX_NCLASS_DENSE + k && s >= cnt[k]) { s -= cnt[k]; ++c; }
-  const int env = c < DEX_NCLASS ? st.order[(size_t)c * st.order_stride + st.env0 + s] : -1;
+  for (int k = 0; k < DEX_NCLASS; ++k) if (c == k && k < c1 && s >= cnt[k]) { s -= cnt[k]; ++c; }
+  const int env = c < c1 ? st.order[(size_t)c * st.order_stride + st.env0 + s] : -1;
   if (__ballot_sync(0xffffffffu, env >= 0) == 0) return;
-  dex_arrow_warp<T>(m, st, dbg, env, reinterpret_cast<T*>(smem_raw), integrate);
+  dex_arrow_warp<T, CON>(m, st, dbg, env, reinterpret_cast<T*>(smem_raw), integrate);
 }
 
 template <typename T>
@@ -243,7 +247,7 @@ struct DeviceArrays {
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
-    dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo;
+    dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo; dev.arrow_omask = h.arrow_omask;
     std::memcpy(dev.arrow_bdof, h.arrow_bdof, sizeof(dev.arrow_bdof)); std::memcpy(dev.arrow_odof, h.arrow_odof, sizeof(dev.arrow_odof));
     std::memcpy(dev.arrow_bmask, h.arrow_bmask, sizeof(dev.arrow_bmask)); std::memcpy(dev.arrow_rowdof, h.arrow_rowdof, sizeof(dev.arrow_rowdof));
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
@@ -302,7 +306,8 @@ struct DexBatch {
   bool attrs_set = false;
   // env chunks run as independent pipelines on library-owned streams (forked from / joined to the caller's)
   bool tree_scalar = false;  // force the thread-per-env tree kernel (tests / tuning)
-  bool dense_only = false;   // force the dense solver for every env (tests / tuning)
+  int solver_mode = 1;       // 0 dense solver only, 1 structured solver for contact-free envs, 2 also for block-arrowhead envs with contacts
+  bool solver_serial = false;
   // the two solver kernels work on disjoint envs: the structured one runs on a second stream, forked after K1c and joined before the next K0
   cudaStream_t s2 = nullptr;
   cudaEvent_t ev_k1c = nullptr, ev_k2a = nullptr;
@@ -393,7 +398,8 @@ int set_attrs(DexBatch* b) {
   if (b->attrs_set) return DEX_OK;
   DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T))));
   DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T))));
-  DEX_CUDA(cudaFuncSetAttribute(k_dynamics_arrow<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DEX_K2A_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute((k_dynamics_arrow<T, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DEX_K2A_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute((k_dynamics_arrow<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DEX_K2L_SMEM_T * sizeof(T))));
   // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
   DEX_CUDA(cudaFuncSetAttribute(k_tree<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   DEX_CUDA(cudaFuncSetAttribute(k_tree8<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T))));
@@ -413,7 +419,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
   if (rc) return rc;
   const size_t smem1 = (size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T);
   const size_t smem2 = (size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T);
-  const size_t smem2a = (size_t)DEX_K2A_SMEM_T * sizeof(T);
+  const size_t smem2a = (size_t)DEX_K2A_SMEM_T * sizeof(T), smem2l = (size_t)DEX_K2L_SMEM_T * sizeof(T);
   int nchunk = b->nchunk;
   if (b->nenv < 1024 * nchunk) nchunk = 1;
   if (st.work_cap / nchunk < 64) nchunk = 1;
@@ -456,9 +462,15 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
         { ProfScope ps(b, 6, cs); k_compact<T><<<(n + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, cs>>>(m, st); b->launches++; }
       }
       if (dynamics) {
-        // envs whose Hessian is block-arrowhead take the structured solver (K1c filed them in classes 4-7), the rest the dense one
-        const bool arrow = m.arrow_ok && st.order && collide && !b->dense_only && !dbg.M;
-        if (arrow && nchunk == 1 && !b->profiling && !getenv("DEX_SOLVER_SERIAL")) {
+        // Solver kernels by K1c class (dex_compact_env): class 7 = envs without contacts -> structured solver, contact-free form;
+        // classes 4-6 = block-arrowhead Hessian with contacts -> structured solver, full form (solver_mode 2) or dense;
+        // classes 0-3 -> dense warp-per-env solver.  The kernels work on disjoint envs; the dense one runs on a second stream.
+        const int mode = (m.arrow_ok && st.order && collide && !dbg.M && !dbg.efc) ? b->solver_mode : 0;
+        const int ndense = mode == 0 ? DEX_NCLASS : (mode == 1 ? DEX_NCLASS - 1 : DEX_NCLASS_DENSE);
+        const int agrid = (n + DEX_AR_ENVS - 1) / DEX_AR_ENVS;
+        const bool fork = mode != 0 && nchunk == 1 && !b->solver_serial;
+        cudaStream_t sa = cs;
+        if (fork) {
           if (!b->s2) {
             DEX_CUDA(cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking));
             DEX_CUDA(cudaEventCreateWithFlags(&b->ev_k1c, cudaEventDisableTiming));
@@ -466,14 +478,13 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
           }
           DEX_CUDA(cudaEventRecord(b->ev_k1c, cs));
           DEX_CUDA(cudaStreamWaitEvent(b->s2, b->ev_k1c, 0));
-          k_dynamics_arrow<T><<<(n + DEX_AR_ENVS - 1) / DEX_AR_ENVS, 32, smem2a, b->s2>>>(m, st, dbg, integrate); b->launches++;
-          DEX_CUDA(cudaEventRecord(b->ev_k2a, b->s2));
-          { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, DEX_NCLASS_DENSE); b->launches++; }
-          DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_k2a, 0));
-        } else {
-        { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, arrow ? DEX_NCLASS_DENSE : DEX_NCLASS); b->launches++; }
-        if (arrow) { ProfScope ps(b, 7, cs); k_dynamics_arrow<T><<<(n + DEX_AR_ENVS - 1) / DEX_AR_ENVS, 32, smem2a, cs>>>(m, st, dbg, integrate); b->launches++; }
+          sa = b->s2;
         }
+        if (mode == 2) { ProfScope ps(b, 7, sa); k_dynamics_arrow<T, true><<<agrid, 32, smem2a, sa>>>(m, st, dbg, integrate, DEX_NCLASS_DENSE, DEX_NCLASS - 1); b->launches++; }
+        if (mode != 0) { ProfScope ps(b, 9, sa); k_dynamics_arrow<T, false><<<agrid, 32, smem2l, sa>>>(m, st, dbg, integrate, DEX_NCLASS - 1, DEX_NCLASS); b->launches++; }
+        if (fork) DEX_CUDA(cudaEventRecord(b->ev_k2a, b->s2));
+        { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, ndense); b->launches++; }
+        if (fork) DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_k2a, 0));
       }
     }
     if (nchunk > 1) { DEX_CUDA(cudaEventRecord(b->ev_join[c], cs)); DEX_CUDA(cudaStreamWaitEvent(s, b->ev_join[c], 0)); }
@@ -626,9 +637,9 @@ int dex_set_tree_kernel(DexBatch* b, int scalar) {
   return DEX_OK;
 }
 
-int dex_set_solver(DexBatch* b, int dense_only) {
-  if (!b) return fail(DEX_E_ARG, "null batch");
-  b->dense_only = dense_only != 0;
+int dex_set_solver(DexBatch* b, int mode) {
+  if (!b || mode < 0 || mode > 2) return fail(DEX_E_ARG, "solver mode must be 0, 1 or 2");
+  b->solver_mode = mode;
   return DEX_OK;
 }
 
@@ -699,7 +710,8 @@ int dex_set_profiling(DexBatch* b, int on) {
   return DEX_OK;
 }
 // Synchronises the device, folds the recorded event pairs into per-class totals and returns
-// ms[8] (total milliseconds) and count[8] (launches) for pre / broadphase / dense solve / post / tree / narrowphase / compaction / structured solve.
+// ms[10] (total milliseconds) and count[10] (launches) for pre / broadphase / dense solve / post / tree / narrowphase / compaction /
+// structured solve (full form) / prop placement / structured solve (contact-free form).
 int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
   if (!b || !ms || !count) return fail(DEX_E_ARG, "null argument");
   DEX_ON_DEVICE(b->model->device);
@@ -711,7 +723,7 @@ int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
       cudaEventDestroy(b->ev[c][i]); cudaEventDestroy(b->ev[c][i + 1]);
     }
     b->ev[c].clear();
-    if (c < 8) { ms[c] = b->ms[c]; count[c] = b->count[c]; }
+    ms[c] = b->ms[c]; count[c] = b->count[c];
     if (reset) { b->ms[c] = 0; b->count[c] = 0; }
   }
   return DEX_OK;

@@ -12,12 +12,27 @@
 //    H = |       ...        ...  |      B_a  (8 x 5) = M_oa        + sum_c Jo^T W Ja
 //        | B_0   ...  B_4   H_oo |      H_oo (8 x 8) = M_oo + diag + sum_c Jo^T W Jo
 //
-// unless a contact joins two different branches (finger - finger); K1c (dex_compact_env) sends such envs, and envs with
-// more than DEX_AR_MAXCON contacts, to the dense warp-per-env solver (dex_dynamics.cuh) instead.  The factorisation is
-// L_a = chol(H_aa) and P_a = B_a L_a^-T per branch (all branches at once, one lane each, in registers), the Schur
-// complement S = H_oo - sum_a P_a P_a^T and its Cholesky factor (lane = border row, shuffles).  Against the dense
-// 30 x 30 factorisation with lane = row this cuts the sequential pivot chain from 30 to 5 + 8, and, because an env only
-// needs eight lanes, every warp instruction serves four envs.
+// plus a low-rank term for every CROSS contact, one that joins two different branches (finger - finger): with U the contact's
+// three frame rows and E its active pyramid edges, H = H0 + sum D (U^T e)(U^T e)^T, applied through the Woodbury identity in
+// edge space: Z = H0^-1 U^T (three arrowhead solves per cross contact), G = U Z, S = diag(1 / D) + E^T G E (SPD, at most
+// 2 x 4 edges, Cholesky with lane = edge), x = x0 - Z E S^-1 E^T U x0.  K1c (dex_compact_env) sends envs with more than
+// DEX_AR_MAXCROSS cross contacts or more than DEX_AR_MAXCON contacts to the dense warp-per-env solver (dex_dynamics.cuh).
+// The arrowhead factorisation is L_a = chol(H_aa) and P_a = B_a L_a^-T per branch (all branches at once, one lane each, in
+// registers), the Schur complement S = H_oo - sum_a P_a P_a^T and its Cholesky factor (lane = border row, shuffles).
+// Against the dense 30 x 30 factorisation with lane = row this cuts the sequential pivot chain from 30 to 5 + 8, and, because
+// an env only needs eight lanes, every warp instruction serves four envs: 3-6 k warp instructions per env and mj_step
+// instead of the dense kernel's 15 k.
+//
+// Two forms (template parameter CON of dex_arrow_warp): the full one, and the form for envs WITHOUT contacts, where all
+// contact code drops out, the free object's acceleration is M^-1 qfrc_smooth and the Schur complement is 2 x 2.
+//
+// What it buys (B200, 16 384 envs, profiles/r02*): the contact-free form runs its half of the envs in 0.066 ms per launch.
+// The full form needs 0.3 ms for the 44 % of envs it can take, no faster than the dense kernel on the same envs although
+// it issues a third of the instructions: its unrolled Newton body (3 k SASS instructions, 48 KB) overflows the 32 KB
+// instruction cache (26 % of the stall cycles wait for instructions), it needs ~240 registers (8 warps per SM; capping the
+// registers spills and is slower), and the stage as a whole is bounded by its slowest env (19 contacts, 14 Newton
+// iterations: 0.22 ms alone), which only the dense kernel takes.  The default therefore routes only the contact-free envs
+// here (dex_set_solver mode 1); mode 2 adds the full form.
 //
 // Lane roles inside a group of eight (g = lane & 7), all views live on the same lanes at different times:
 //   branch view  : lane g < 5 owns branch g (dof slots 0..4 of its per-dof register arrays)
@@ -34,12 +49,10 @@
 
 #include "dex_dynamics.cuh"
 
-#ifdef DEX_EMU_STATS
-static long dex_emu_ls_count = 0, dex_emu_newton_count = 0;
-#endif
 #define DEX_AR_G 8
 #define DEX_AR_ENVS 4
 #define DEX_AR_MAXCON 8      // contacts per env the structured solver takes (one lane per contact)
+#define DEX_AR_MAXCROSS 2    // of which contacts that join two branches (handled as a low-rank correction)
 #define DEX_AR_JC_CON 48     // contact-frame Jacobian of one contact in shared memory: [3 rows][16]: branch slots 0-4, border rows at 8-15
 
 // shared memory per env (units of T)
@@ -55,15 +68,24 @@ enum {
   AR_FR = AR_QS + 40,           // [40]     force of the dof's own rows (friction loss + limit), packed
   AR_HR = AR_FR + 40,           // [40]     their contribution to the diagonal of H, packed
   AR_CI = AR_HR + 40,           // [8]      per contact (int): its branch, -1 = border only
-  AR_JC = AR_CI + 8 + 16,       // [8 contacts][3 rows][16]  contact-frame Jacobians: branch slots at 0-4, border rows at 8-15 (16-byte aligned)
-  AR_ENV_T = AR_JC + DEX_AR_MAXCON * DEX_AR_JC_CON   // 1096 = 8 (mod 32)
+  AR_ENV_LITE_T = AR_CI + 8 + 16,   // = AR_JC: the contact-free form of the kernel (CON = false) stops here; 712 = 8 (mod 32)
+  AR_JC = AR_CI + 8 + 16,       // [8 contacts][3 rows][16]  contact-frame Jacobians: first branch at 0-4; border rows, or the second branch of a
+                                //          cross contact, at 8-15 (16-byte aligned)
+  // low-rank part of the Hessian: contacts that join two branches (DEX_AR_MAXCROSS per env), see "cross contacts" below
+  AR_Z = AR_JC + DEX_AR_MAXCON * DEX_AR_JC_CON,   // [6][40]  Z = H0^-1 U^T, one packed vector per frame row of a cross contact
+  AR_G = AR_Z + 6 * 40,         // [6][8]   G = U Z
+  AR_SL = AR_G + 48,            // [8][8]   Cholesky factor of the edge-space system, L[g][j] at j * 8 + g
+  AR_SI = AR_SL + 64,           // [8]      1 / L[g][g]
+  AR_TV = AR_SI + 8,            // [8]      U x0 going in, E y coming out (6 used)
+  AR_CX = AR_TV + 8,            // [8][4]   per contact: mu, D, active-edge mask (int), -
+  AR_XC = AR_CX + 32,           // [8]      int: contact index of cross slot 0, 1 (-1 = none)
+  AR_ENV_T = AR_XC + 8 + 8      // 1512 = 8 (mod 32)
 };
+static_assert(AR_ENV_LITE_T % 32 == 8, "env slices must be 8 (mod 32) words apart");
 static_assert(AR_ENV_T % 32 == 8, "env slices must be 8 (mod 32) words apart");
 #define DEX_K2A_SMEM_T (DEX_AR_ENVS * AR_ENV_T)
+#define DEX_K2L_SMEM_T (DEX_AR_ENVS * AR_ENV_LITE_T)
 
-template <typename T> struct ArLanes {
-  int lane, g, base;   // lane, lane in group, first lane of the group
-};
 template <typename T> DEX_DEV T ar_gsum(T v) {   // sum over the group of eight
   v += dex_shfl_xor(v, 1); v += dex_shfl_xor(v, 2); v += dex_shfl_xor(v, 4);
   return v;
@@ -78,6 +100,40 @@ DEX_DEV bool ar_gany(bool p, int base) { return ((dex_ballot(p) >> base) & 0xffu
 // Out: Ha = L_a with Li = 1 / diag(L_a); P^T area = P^T; Ho = row g of L_S, Lc[j] = L_S[j][g] (column g), Si = 1 / L_S[g][g].
 // NR = border rows that take part (8, or DevModel::arrow_nmo = 2 for the implicit-damping solve, where the rest is decoupled).
 // ------------------------------------------------------------------------------------------------------------------
+// Cholesky of an SPD matrix of order NR <= 8 spread over the group, lane g = row g (R[j], j <= g, are used): column sweep with
+// shuffles.  Leaves row g of L in R and 1 / L[g][g] in inv.
+template <typename T, int NR>
+DEX_DEV void ar_chol_rows(int g, int base, T (&R)[8], T& inv, bool& bad) {
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    T d = dex_shfl(R[j], base | j);
+    bad |= !(d > Real<T>::minval());
+    d = dx_max(d, Real<T>::minval());
+    const T iv = dx_rsqrt(d);
+    const T l = R[j] * iv;   // L[g][j] for g >= j
+    R[j] = l;
+    inv = g == j ? iv : inv;
+#pragma unroll
+    for (int i = j + 1; i < NR; ++i) R[i] -= l * dex_shfl(l, base | i);
+  }
+}
+// L L^T x = z with lane g holding row g (R) and column g (C) of L and inv = 1 / L[g][g]; z / x are lane g's entries.
+template <typename T, int NR>
+DEX_DEV T ar_tri_solve(int g, int base, const T (&R)[8], const T (&C)[8], T inv, T z) {
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    const T yj = dex_shfl(z * inv, base | j);
+    z -= (g > j ? R[j] : T(0)) * yj;
+  }
+  z *= inv;
+#pragma unroll
+  for (int j = NR - 1; j >= 0; --j) {
+    const T xj = dex_shfl(z * inv, base | j);
+    z -= (g < j ? C[j] : T(0)) * xj;
+  }
+  return z * inv;
+}
+
 template <typename T, int NR>
 DEX_DEV void ar_factor(T* sm, int g, int base, T (&Ha)[15], T (&Li)[5], T (&Ho)[8], T (&Lc)[8], T& Si, bool& bad) {
   const bool isb = g < 5;
@@ -143,19 +199,7 @@ DEX_DEV void ar_factor(T* sm, int g, int base, T (&Ha)[15], T (&Li)[5], T (&Ho)[
       for (int j = 0; j < NR; ++j) Ho[j] -= mine * row[j];
     }
   }
-  // ---- Cholesky of S, column sweep with shuffles (lane j owns row j)
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    T d = dex_shfl(Ho[j], base | j);
-    bad |= !(d > Real<T>::minval());
-    d = dx_max(d, Real<T>::minval());
-    const T inv = dx_rsqrt(d);
-    const T l = Ho[j] * inv;   // L[g][j] for g >= j
-    Ho[j] = l;
-    Si = g == j ? inv : Si;
-#pragma unroll
-    for (int i = j + 1; i < NR; ++i) Ho[i] -= l * dex_shfl(l, base | i);
-  }
+  ar_chol_rows<T, NR>(g, base, Ho, Si, bad);
   // column g of L_S through shared memory (the back substitution walks columns)
   {
     T* ls = sm + AR_LS;
@@ -191,19 +235,7 @@ DEX_DEV void ar_solve(T* sm, int g, int base, const T (&Ha)[15], const T (&Li)[5
     for (int p = 0; p < 25; ++p) z -= pt[p * 8 + (g < NR ? g : 0)] * xs[p];
     if (g >= NR) z = 0;
   }
-  // L_S w = z, L_S^T x_o = w
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const T yj = dex_shfl(z * Si, base | j);
-    z -= (g > j ? Ho[j] : T(0)) * yj;
-  }
-  z *= Si;
-#pragma unroll
-  for (int j = NR - 1; j >= 0; --j) {
-    const T xj = dex_shfl(z * Si, base | j);
-    z -= (g < j ? Lc[j] : T(0)) * xj;
-  }
-  z *= Si;
+  z = ar_tri_solve<T, NR>(g, base, Ho, Lc, Si, z);   // L_S w = z, L_S^T x_o = w
   if (g < NR) { x[5] = z; xs[32 + g] = z; }
   dex_syncwarp();
   // L_a^T x_a = y_a - P_a^T x_o
@@ -264,15 +296,15 @@ DEX_DEV void ar_mulM(T* sm, int g, int nmo, const T (&x)[6], T (&y)[6]) {
   dex_syncwarp();
 }
 
-// d[3] = Jc x for the lane's own contact (contact view).  x is read from xs (packed).
+// d[3] = Jc x for the lane's own contact (contact view); x is a packed vector in shared memory.  a = first branch (-1 = none),
+// a2 = second branch of a cross contact (-1 = the columns 8-15 are the border rows).
 template <typename T>
-DEX_DEV void ar_contact_dot(const T* sm, const T* jc, int a, T* d) {
-  const T* xs = sm + AR_XS;
+DEX_DEV void ar_contact_dot(const T* xs, const T* jc, int a, int a2, T* d) {
   T xa[5], xo[8];
 #pragma unroll
   for (int k = 0; k < 5; ++k) xa[k] = a >= 0 ? xs[5 * a + k] : T(0);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) xo[r] = xs[32 + r];
+  for (int r = 0; r < 8; ++r) xo[r] = a2 >= 0 ? (r < 5 ? xs[5 * a2 + r] : T(0)) : xs[32 + r];
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     T ja[8], jo[8];
@@ -323,12 +355,17 @@ DEX_DEV_NOINLINE void ar_limit_row(const ArLimitTabs<T> m, int i, const T* qpos,
 // lanes (in the dof view three lanes hold one dof and padding).  Rows read qacc / search from the packed arrays in shared
 // memory and hand their force and Hessian diagonal back the same way.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
+// CON = false: the form for envs WITHOUT contacts (about half of them at any time).  All contact code drops out at compile
+// time; the border rows beyond the leading arrow_nmo (the free object) carry no constraint at all, so their acceleration is
+// M_oo^-1 qfrc_smooth, computed once, and the Newton iteration runs on the branches and the leading border rows only (a 2 x 2
+// Schur complement).  The loop body then fits the 32 KB instruction cache, which the full form does not.
+template <typename T, bool CON>
 DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int myenv, T* smem, int integrate) {
+  constexpr int NRN = CON ? 8 : 2;   // border rows of the Newton system
   const int lane = dex_lane(), g = lane & 7, base = lane & ~7;
   const bool live = myenv >= 0;
   const int env = live ? myenv : 0;   // dead groups compute on env 0 and write nothing
-  T* sm = smem + (lane >> 3) * AR_ENV_T;
+  T* sm = smem + (lane >> 3) * (CON ? AR_ENV_T : AR_ENV_LITE_T);
   const bool isb = g < 5;
   const T h = m.timestep;
   unsigned status = 0;
@@ -407,14 +444,34 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
       moo[r * 8] = (i >= 0 && j >= 0) ? Mg[i * 32 + j] : (r == g ? T(1) : T(0));
     }
   }
+  if (!CON) {
+    // unconstrained border rows (beyond the leading arrow_nmo): qacc = M_oo^-1 qfrc_smooth, once (M_oo is block diagonal
+    // between the two groups of rows, so the full 8 x 8 solve yields them; its leading rows are not used)
+    T R8[8], C8[8], inv8 = 1;
+    bool bad8 = false;
+    const T* moo = sm + AR_MOO + g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) R8[j] = moo[j * 8];
+    ar_chol_rows<T, 8>(g, base, R8, inv8, bad8);
+    T* ls = sm + AR_LS;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ls[j * 8 + g] = R8[j];
+    dex_syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) C8[j] = ls[g * 8 + j];
+    const T a = ar_tri_solve<T, 8>(g, base, R8, C8, inv8, fs[5]);
+    if (g >= m.arrow_nmo) { qacc[5] = a; sm[AR_QS + 32 + g] = a; }
+    if (bad8) status |= DEX_STATUS_CHOL_FAIL;
+    dex_syncwarp();
+  }
   // ------------------------------------------------------------------ contacts (contact view: lane g = contact g)
-  int ncon = live ? st.ncon[env] : 0;
+  int ncon = (CON && live) ? st.ncon[env] : 0;
   if (ncon > DEX_AR_MAXCON) ncon = DEX_AR_MAXCON;   // K1c never sends such an env here
-  const int ncmax = dex_warp_max(ncon);              // warp-uniform loop bound
-  const bool hasc = g < ncon;
+  const int ncmax = CON ? dex_warp_max(ncon) : 0;    // warp-uniform loop bound
+  const bool hasc = CON && g < ncon;
   T c_mu = 0, c_D = 0, c_aref[4] = {0, 0, 0, 0}, c_kp = 0, c_B = 0;
-  int c_a = -1;
-  {
+  int c_a = -1, c_a2 = -1;   // branches of the contact: none / one (plus the border) / two (a cross contact)
+  if (CON) {
     // set-up records in the (still unused) P^T area: [contact][16] = frame(9) pos(3) m1 m2 branch -
     T* rec = sm + AR_PT + g * 16;
     if (hasc) {
@@ -428,11 +485,11 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
       const unsigned m1 = (unsigned)dex_ldg(m.body_dofmask + b1), m2 = (unsigned)dex_ldg(m.body_dofmask + b2);
       const unsigned mx = m1 ^ m2;
 #pragma unroll
-      for (int a = 0; a < 5; ++a) if (mx & (unsigned)m.arrow_bmask[a]) c_a = a;
+      for (int a = 4; a >= 0; --a) if (mx & (unsigned)m.arrow_bmask[a]) { c_a2 = c_a; c_a = a; }   // c_a < c_a2
       for (int q = 0; q < 9; ++q) rec[q] = frame[q];
       rec[9] = c8[1]; rec[10] = c8[2]; rec[11] = c8[3];
       int* ri = reinterpret_cast<int*>(rec + 12);
-      ri[0] = (int)m1; ri[1] = (int)m2; ri[2] = c_a;
+      ri[0] = (int)m1; ri[1] = (int)m2; ri[2] = c_a; ri[3] = c_a2;
       // impedance, regulariser and the spring-damper of the four pyramid rows
       c_mu = dex_ldg(m.pair_friction + 5 * pr);
       const T cmargin = dex_ldg(m.pair_margin + pr) - dex_ldg(m.pair_gap + pr);
@@ -451,11 +508,25 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
         e[0] = c_D; e[5] = c_mu; e[6] = imp; e[7] = Rpy;
       }
     }
-    reinterpret_cast<int*>(sm + AR_CI)[g] = c_a;
+    reinterpret_cast<int*>(sm + AR_CI)[g] = (c_a & 15) | ((c_a2 & 15) << 4);   // 15 = none
+    sm[AR_CX + 4 * g] = c_mu; sm[AR_CX + 4 * g + 1] = c_D;
+    reinterpret_cast<int*>(sm + AR_CX + 4 * g + 2)[0] = 0;
   }
+  // cross contacts get the slots 0 .. nx-1 in contact order
+  int nx = 0;
+  if (CON) {
+    const unsigned xm = (dex_ballot(hasc && c_a2 >= 0) >> base) & 0xffu;
+    nx = dex_popc(xm);
+    int* xc = reinterpret_cast<int*>(sm + AR_XC);
+    if (g < DEX_AR_MAXCROSS) xc[g] = -1;
+    dex_syncwarp();
+    if (hasc && c_a2 >= 0) { const int rank = dex_popc(xm & ((1u << g) - 1u)); if (rank < DEX_AR_MAXCROSS) xc[rank] = g; }
+    if (nx > DEX_AR_MAXCROSS) nx = DEX_AR_MAXCROSS;   // K1c never sends such an env here
+  }
+  const int nxmax = CON ? dex_warp_max(nx) : 0;   // warp-uniform: 0 = no env of this warp has a cross contact
   dex_syncwarp();
   // contact-frame Jacobians: branch lane = the 5 columns of its branch, every lane = border column g
-  {
+  if (CON) {
     T cdo[6] = {0, 0, 0, 0, 0, 0}, refo[3] = {0, 0, 0};
     const int io = dofs[5];
     if (io >= 0) {
@@ -470,7 +541,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
       dex_ld4(rec, fr); dex_ld4(rec + 4, fr + 4); dex_ld4(rec + 8, fr + 8);
       const int* ri = reinterpret_cast<const int*>(rec + 12);
       const unsigned m1 = (unsigned)ri[0], m2 = (unsigned)ri[1];
-      const int ca = ri[2];
+      const int ca = ri[2], ca2 = ri[3];
       T* jc = Jc + c * DEX_AR_JC_CON;
       {   // border column
         T j0 = 0, j1 = 0, j2 = 0;
@@ -483,14 +554,14 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
             j0 = sgn * dot3(fr, v); j1 = sgn * dot3(fr + 3, v); j2 = sgn * dot3(fr + 6, v);
           }
         }
-        jc[8 + g] = j0; jc[16 + 8 + g] = j1; jc[32 + 8 + g] = j2;
+        if (ca2 < 0) { jc[8 + g] = j0; jc[16 + 8 + g] = j1; jc[32 + 8 + g] = j2; }   // a cross contact has no border part: its columns 8-15 hold the second branch
       }
       if (isb) {   // branch columns (zero when the contact is not on this branch)
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int i = dofs[k];
           T j0 = 0, j1 = 0, j2 = 0;
-          if (ca == g && i >= 0) {
+          if ((ca == g || ca2 == g) && i >= 0) {
             const T sgn = T((m2 >> i) & 1u) - T((m1 >> i) & 1u);
             if (sgn != 0) {
               T cd[6];
@@ -504,6 +575,10 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
             }
           }
           if (ca == g || (ca < 0 && g == 0)) { jc[k] = j0; jc[16 + k] = j1; jc[32 + k] = j2; }   // border-only contacts: lane 0 writes the zeros
+          if (ca2 == g) {
+            jc[8 + k] = j0; jc[16 + 8 + k] = j1; jc[32 + 8 + k] = j2;
+            if (k < 3) { jc[13 + k] = 0; jc[16 + 13 + k] = 0; jc[32 + 13 + k] = 0; }
+          }
         }
       }
     }
@@ -513,7 +588,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
   T jar[4] = {0, 0, 0, 0};
   {
     T d[3] = {0, 0, 0};
-    if (hasc) ar_contact_dot(sm, Jc + g * DEX_AR_JC_CON, c_a, d);   // xs = qvel
+    if (hasc) ar_contact_dot(sm + AR_XS, Jc + g * DEX_AR_JC_CON, c_a, c_a2, d);   // xs = qvel
     c_aref[0] = -c_B * (d[0] + c_mu * d[1]) - c_kp; c_aref[1] = -c_B * (d[0] - c_mu * d[1]) - c_kp;
     c_aref[2] = -c_B * (d[0] + c_mu * d[2]) - c_kp; c_aref[3] = -c_B * (d[0] - c_mu * d[2]) - c_kp;
     if (dbg.efc && live && hasc) {
@@ -526,7 +601,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
     // ar_mulM stores the border entries of its argument in xs and leaves the branch entries alone
     ar_mulM(sm, g, m.arrow_nmo, qacc, Ma);
     if (hasc) {
-      ar_contact_dot(sm, Jc + g * DEX_AR_JC_CON, c_a, d);
+      ar_contact_dot(sm + AR_XS, Jc + g * DEX_AR_JC_CON, c_a, c_a2, d);
       jar[0] = d[0] + c_mu * d[1] - c_aref[0]; jar[1] = d[0] - c_mu * d[1] - c_aref[1];
       jar[2] = d[0] + c_mu * d[2] - c_aref[2]; jar[3] = d[0] - c_mu * d[2] - c_aref[3];
     }
@@ -570,7 +645,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
       sig |= (on && rw_lD[q] != 0) ? 2 << (2 * q) : 0;
       if (rw_p[q] >= 0) { sm[AR_FR + p] = f; sm[AR_HR + p] = hd; }
     }
-    {
+    if (CON) {
       T f[4], w[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -580,6 +655,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
         mycost += on ? T(0.5) * c_D * x * x : T(0);
         sig |= on ? 1 << (8 + r) : 0;
       }
+      reinterpret_cast<int*>(sm + AR_CX + 4 * g + 2)[0] = (sig >> 8) & 15;   // active pyramid edges (read by the cross-contact correction)
       T* cf = sm + AR_CF + g * 8;
       cf[0] = f[0] + f[1] + f[2] + f[3]; cf[1] = c_mu * (f[0] - f[1]); cf[2] = c_mu * (f[2] - f[3]);
       cf[3] = w[0] + w[1] + w[2] + w[3]; cf[4] = c_mu * (w[0] - w[1]); cf[5] = c_mu * (w[2] - w[3]);
@@ -596,14 +672,17 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
       const T* cf = sm + AR_CF + c * 8;
       const T f0 = cf[0], f1 = cf[1], f2 = cf[2];
       const T* jc = Jc + c * DEX_AR_JC_CON;
-      grad[5] -= jc[8 + g] * f0 + jc[16 + 8 + g] * f1 + jc[32 + 8 + g] * f2;
-      if (reinterpret_cast<const int*>(sm + AR_CI)[c] == g) {
+      const int ci = reinterpret_cast<const int*>(sm + AR_CI)[c], ca = ci & 15, ca2 = ci >> 4;   // 15 = none
+      if (ca2 == 15) grad[5] -= jc[8 + g] * f0 + jc[16 + 8 + g] * f1 + jc[32 + 8 + g] * f2;
+      if (ca == g || ca2 == g) {
+        const T* jb = jc + (ca == g ? 0 : 8);
         T a0[5], a1[5], a2[5];
-        dex_ld4(jc, a0); a0[4] = jc[4]; dex_ld4(jc + 16, a1); a1[4] = jc[20]; dex_ld4(jc + 32, a2); a2[4] = jc[36];
+        dex_ld4(jb, a0); a0[4] = jb[4]; dex_ld4(jb + 16, a1); a1[4] = jb[20]; dex_ld4(jb + 32, a2); a2[4] = jb[36];
 #pragma unroll
         for (int k = 0; k < 5; ++k) grad[k] -= a0[k] * f0 + a1[k] * f1 + a2[k] * f2;
       }
     }
+    if (!CON && g >= m.arrow_nmo) grad[5] = 0;   // unconstrained rows sit at their minimum already
     T g2 = 0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) g2 += grad[k] * grad[k];
@@ -648,6 +727,8 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
         const T* cf = sm + AR_CF + c * 8;
         const T w00 = cf[3], w01 = cf[4], w02 = cf[5], w11 = cf[6], w22 = cf[7];
         if (w00 == 0) continue;   // no active edge (uniform within the group)
+        const int ci = reinterpret_cast<const int*>(sm + AR_CI)[c];
+        if ((ci >> 4) != 15) continue;   // a cross contact is not part of the arrowhead matrix: low-rank correction below
         const T* jc = Jc + c * DEX_AR_JC_CON;
         T o0[8], o1[8], o2[8];   // border columns of the three frame rows
         dex_ld4(jc + 8, o0); dex_ld4(jc + 12, o0 + 4); dex_ld4(jc + 24, o1); dex_ld4(jc + 28, o1 + 4);
@@ -658,7 +739,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
 #pragma unroll
           for (int j = 0; j < 8; ++j) Ho[j] += t0 * o0[j] + t1 * o1[j] + t2 * o2[j];
         }
-        if (reinterpret_cast<const int*>(sm + AR_CI)[c] == g) {   // branch block and coupling (only this lane touches these rows of P^T)
+        if ((ci & 15) == g) {   // branch block and coupling (only this lane touches these rows of P^T)
           T a0[5], a1[5], a2[5];
           dex_ld4(jc, a0); a0[4] = jc[4]; dex_ld4(jc + 16, a1); a1[4] = jc[20]; dex_ld4(jc + 32, a2); a2[4] = jc[36];
           T* pt = sm + AR_PT + (5 * g) * 8;
@@ -677,14 +758,126 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
         }
       }
       bool bad = false;
-      ar_factor<T, 8>(sm, g, base, Ha, Li, Ho, Lc, Si, bad);
+      ar_factor<T, NRN>(sm, g, base, Ha, Li, Ho, Lc, Si, bad);
+      // ---- cross contacts: H = H0 + sum over their active pyramid edges D (U^T e)(U^T e)^T with U the contact's three frame
+      // rows.  Woodbury in edge space: Z = H0^-1 U^T (three arrowhead solves per cross contact), G = U Z, and the SPD system
+      // S = diag(1 / D) + E^T G E over the (at most 2 x 4) edges, factorised with lane = edge (lane 4 j + r: edge r of slot j).
+      if (nxmax > 0) {
+        const int* xc = reinterpret_cast<const int*>(sm + AR_XC);
+        const int myslot = (hasc && c_a2 >= 0) ? (xc[0] == g ? 0 : 1) : -1;
+#pragma unroll 1
+        for (int i = 0; i < 3 * nxmax; ++i) {
+          const int j = i / 3, q = i - 3 * j;
+          const int c = xc[j];
+          T rhs[6] = {0, 0, 0, 0, 0, 0};
+          if (c >= 0) {
+            const int ci = reinterpret_cast<const int*>(sm + AR_CI)[c];
+            if ((ci & 15) == g || (ci >> 4) == g) {
+              const T* jb = Jc + c * DEX_AR_JC_CON + q * 16 + ((ci & 15) == g ? 0 : 8);
+#pragma unroll
+              for (int k = 0; k < 5; ++k) rhs[k] = jb[k];
+            }
+          }
+          ar_solve<T, 8>(sm, g, base, Ha, Li, Ho, Lc, Si, rhs);
+          T* z = sm + AR_Z + i * 40;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) if (k == 5 || isb) z[k < 5 ? 5 * g + k : 32 + g] = rhs[k];
+          dex_syncwarp();
+          if (myslot >= 0) {   // column i of G: the frame rows of this lane's cross contact against Z_i
+            T d[3];
+            ar_contact_dot(z, Jc + g * DEX_AR_JC_CON, c_a, c_a2, d);
+#pragma unroll
+            for (int qq = 0; qq < 3; ++qq) sm[AR_G + (3 * myslot + qq) * 8 + i] = d[qq];
+          }
+        }
+        dex_syncwarp();
+        // S row of this lane's edge
+        const int ej = g >> 2, er = g & 3;
+        const int ec = xc[ej];
+        T mu[2];   // per slot: friction (the edge vectors (1, +-mu, 0), (1, 0, +-mu) are built from it)
+        int act[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = xc[j];
+          mu[j] = c >= 0 ? sm[AR_CX + 4 * c] : T(0);
+          act[j] = c >= 0 ? reinterpret_cast<const int*>(sm + AR_CX + 4 * c + 2)[0] : 0;
+        }
+        const bool eon = ec >= 0 && (((ej == 0 ? act[0] : act[1]) >> er) & 1);
+        const T em = ej == 0 ? mu[0] : mu[1];
+        const T ev1 = er == 0 ? em : (er == 1 ? -em : T(0)), ev2 = er == 2 ? em : (er == 3 ? -em : T(0));
+        T t6[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const T* gr = sm + AR_G + (3 * ej) * 8 + i;
+          t6[i] = eon ? gr[0] + ev1 * gr[8] + ev2 * gr[16] : T(0);
+        }
+        T Se[8];
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) {
+          const int j2 = gg >> 2, r2 = gg & 3;
+          const bool on2 = eon && ((act[j2] >> r2) & 1);
+          const T m2 = mu[j2];
+          const T v = t6[3 * j2] + (r2 == 0 ? m2 : (r2 == 1 ? -m2 : T(0))) * t6[3 * j2 + 1] + (r2 == 2 ? m2 : (r2 == 3 ? -m2 : T(0))) * t6[3 * j2 + 2];
+          Se[gg] = on2 ? v : T(0);
+        }
+        {
+          const T dinv = ec >= 0 ? T(1) / dx_max(sm[AR_CX + 4 * ec + 1], Real<T>::minval()) : T(1);
+#pragma unroll
+          for (int gg = 0; gg < 8; ++gg) if (gg == g) Se[gg] += eon ? dinv : T(1);   // an inactive edge keeps an identity row
+        }
+        T sinv = 1;
+        ar_chol_rows<T, 8>(g, base, Se, sinv, bad);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[AR_SL + j * 8 + g] = Se[j];
+        sm[AR_SI + g] = sinv;
+        dex_syncwarp();
+      }
       if (bad && !done) status |= DEX_STATUS_CHOL_FAIL;
     }
     // ---- search = -H^-1 grad
     T search[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) search[k] = -grad[k];
-    ar_solve<T, 8>(sm, g, base, Ha, Li, Ho, Lc, Si, search);
+    ar_solve<T, NRN>(sm, g, base, Ha, Li, Ho, Lc, Si, search);
+    if (!CON && g >= m.arrow_nmo) search[5] = 0;
+    if (nxmax > 0) {   // x = x0 - Z E S^-1 E^T U x0
+      const int* xc = reinterpret_cast<const int*>(sm + AR_XC);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k == 5 || isb) sm[AR_XS + (k < 5 ? 5 * g + k : 32 + g)] = search[k];
+      dex_syncwarp();
+      if (hasc && c_a2 >= 0) {
+        T d[3];
+        ar_contact_dot(sm + AR_XS, Jc + g * DEX_AR_JC_CON, c_a, c_a2, d);
+        const int slot = xc[0] == g ? 0 : 1;
+        sm[AR_TV + 3 * slot] = d[0]; sm[AR_TV + 3 * slot + 1] = d[1]; sm[AR_TV + 3 * slot + 2] = d[2];
+      }
+      dex_syncwarp();
+      const int ej = g >> 2, er = g & 3;
+      const int ec = xc[ej];
+      const T em = ec >= 0 ? sm[AR_CX + 4 * ec] : T(0);
+      const bool eon = ec >= 0 && ((reinterpret_cast<const int*>(sm + AR_CX + 4 * (ec >= 0 ? ec : 0) + 2)[0] >> er) & 1);
+      const T ev1 = er == 0 ? em : (er == 1 ? -em : T(0)), ev2 = er == 2 ? em : (er == 3 ? -em : T(0));
+      T r = eon ? sm[AR_TV + 3 * ej] + ev1 * sm[AR_TV + 3 * ej + 1] + ev2 * sm[AR_TV + 3 * ej + 2] : T(0);
+      T SR[8], SC[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { SR[j] = sm[AR_SL + j * 8 + g]; SC[j] = sm[AR_SL + g * 8 + j]; }
+      const T y = ar_tri_solve<T, 8>(g, base, SR, SC, sm[AR_SI + g], r);
+      // E y: sum over the four edges of each slot
+      T v0 = eon ? y : T(0), v1 = v0 * ev1, v2 = v0 * ev2;
+      v0 += dex_shfl_xor(v0, 1); v1 += dex_shfl_xor(v1, 1); v2 += dex_shfl_xor(v2, 1);
+      v0 += dex_shfl_xor(v0, 2); v1 += dex_shfl_xor(v1, 2); v2 += dex_shfl_xor(v2, 2);
+      dex_syncwarp();
+      if (er == 0) { sm[AR_TV + 3 * ej] = v0; sm[AR_TV + 3 * ej + 1] = v1; sm[AR_TV + 3 * ej + 2] = v2; }
+      dex_syncwarp();
+#pragma unroll 1
+      for (int i = 0; i < 3 * nxmax; ++i) {
+        const T vi = sm[AR_TV + i];
+        const T* z = sm + AR_Z + i * 40;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k == 5 || isb) search[k] -= z[k < 5 ? 5 * g + k : 32 + g] * vi;
+      }
+      dex_syncwarp();
+    }
 
     // ---- exact line search along `search` (PrimalSearch)
     T Mv[6];
@@ -694,7 +887,7 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
     T jv[4] = {0, 0, 0, 0};
     if (hasc) {
       T d[3];
-      ar_contact_dot(sm, Jc + g * DEX_AR_JC_CON, c_a, d);
+      ar_contact_dot(sm + AR_XS, Jc + g * DEX_AR_JC_CON, c_a, c_a2, d);
       jv[0] = d[0] + c_mu * d[1]; jv[1] = d[0] - c_mu * d[1]; jv[2] = d[0] + c_mu * d[2]; jv[3] = d[0] - c_mu * d[2];
     }
     T q1 = 0, q2 = 0;
@@ -754,14 +947,8 @@ DEX_DEV void dex_arrow_warp(const DevModel<T>& m, const BatchState<T>& st, const
           alpha = next;
         }
       }
-#ifdef DEX_EMU_STATS
-      if (!lsdone && g == 0) dex_emu_ls_count++;
-#endif
       if (dex_ballot(!lsdone) == 0) break;
     }
-#ifdef DEX_EMU_STATS
-    if (!done && g == 0) dex_emu_newton_count++;
-#endif
     if (done) alpha = 0;
     if (!done) {
       if (alpha == 0) done = true;

@@ -29,6 +29,7 @@
 #define DEX_NCLASS 8       // solver-cost classes of K2's processing order
 #define DEX_NCLASS_DENSE 4 // with the structured solver on (DevModel::arrow_ok): classes 0-3 dense kernel, 4-7 structured kernel
 #define DEX_AR_MAXCON_K1 8 // = DEX_AR_MAXCON (dex_arrow.cuh)
+#define DEX_AR_MAXCROSS_K1 2 // = DEX_AR_MAXCROSS
 #define DEX_WORK_HDR 16     // words before the first work item: count, cursor, DEX_NCLASS class counters
 #define DEX_MAXSLOT 64     // staging slots per env (one per convex-convex candidate, four per plane-box pair)
 #define DEX_STAGE_ENV (DEX_MAXSLOT * DEX_CON_STRIDE)
@@ -840,7 +841,8 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
   const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
   T* cout = st.contact + (size_t)env * DEX_MAXCON * DEX_CON_STRIDE;
   int ncon = 0;
-  bool overflow = false, cross = false;
+  bool overflow = false, cross_bad = false;
+  int ncross = 0;
   for (int s0 = 0; s0 < nslot; s0 += 32) {
     const int sl = s0 + lane;
     T rec[DEX_CON_STRIDE];
@@ -851,6 +853,7 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
     }
     const unsigned vm = dex_ballot(valid);
     const int idx = ncon + dex_popc(vm & ((1u << lane) - 1u));
+    bool cross = false;
     if (valid) {
       if (idx < DEX_MAXCON) { for (int k = 0; k < DEX_CON_STRIDE; ++k) cout[idx * DEX_CON_STRIDE + k] = rec[k]; }
       else overflow = true;
@@ -860,9 +863,11 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
                             (unsigned)dex_ldg(m.body_dofmask + dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr)));
         int nbr = 0;
         for (int a = 0; a < 5; ++a) nbr += (mx & (unsigned)m.arrow_bmask[a]) ? 1 : 0;
-        cross = cross || nbr > 1;
+        cross = nbr == 2 && !(mx & (unsigned)m.arrow_omask);   // the structured solver takes these as a low-rank correction
+        cross_bad = cross_bad || (nbr > 1 && !cross);
       }
     }
+    ncross += dex_popc(dex_ballot(cross));
     ncon += dex_popc(vm);
   }
   if (dex_ballot(overflow)) { if (lane == 0) st.status[env] |= DEX_STATUS_CON_OVERFLOW; }
@@ -874,12 +879,12 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
   // slower: envs with equal contact counts also share code paths and cache lines.
   if (m.arrow_ok) {
     // Two solver kernels: classes 0-3 = dense warp-per-env solver (dex_dynamics.cuh), classes 4-7 = structured solver with
-    // eight lanes per env (dex_arrow.cuh) for envs whose Hessian is block-arrowhead: no contact joins two branches and the
-    // contacts fit one lane each.  Within each kernel the envs with the most contacts go first; envs with equal contact
+    // eight lanes per env (dex_arrow.cuh) for envs whose Hessian is block-arrowhead plus at most two contacts that join two
+    // branches (a low-rank correction), with at most one contact per lane.  Within each kernel the envs with the most contacts go first; envs with equal contact
     // counts share a warp in the structured kernel (four envs per warp run as long as the slowest).
-    const bool arrow = !dex_ballot(cross) && ncon <= DEX_AR_MAXCON_K1;
-    if (arrow) return ncon >= 4 ? 4 : (ncon >= 2 ? 5 : (ncon == 1 ? 6 : 7));
-    return ncon >= 7 ? 0 : (ncon >= 4 ? 1 : (ncon >= 2 ? 2 : 3));
+    const bool arrow = !dex_ballot(cross_bad) && ncross <= DEX_AR_MAXCROSS_K1 && ncon <= DEX_AR_MAXCON_K1;
+    if (arrow) return ncross > 0 ? 4 : (ncon >= 3 ? 5 : (ncon >= 1 ? 6 : 7));   // envs with cross contacts share warps: their correction costs every env of the warp
+    return ncon >= 12 ? 0 : (ncon >= 9 ? 1 : (ncon >= 4 ? 2 : 3));
   }
   const int key = ncon + 2;
   const int cls = key >= 9 ? 0 : (9 - key > DEX_NCLASS - 1 ? DEX_NCLASS - 1 : 9 - key);

@@ -21,7 +21,7 @@ struct HostModel {
   int nbody, njnt, nq, nv, nu, ntendon, ngeom, npair, nsite, nbodypair, ntree, maxdepth;
   int nconmax, iterations, mpr_iterations, nv_euler;
   int k0_rounds, chol_split;
-  int arrow_ok, arrow_nmo, arrow_bdof[5][5], arrow_odof[8], arrow_bmask[5], arrow_rowdof[24];
+  int arrow_ok, arrow_nmo, arrow_bdof[5][5], arrow_odof[8], arrow_bmask[5], arrow_rowdof[24], arrow_omask;
   double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
@@ -225,6 +225,8 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
       }
       if (nrow > 24) M.arrow_ok = 0;
     }
+    M.arrow_omask = 0;
+    for (int r = 0; r < 8; ++r) if (M.arrow_odof[r] >= 0) M.arrow_omask |= 1 << M.arrow_odof[r];
     M.arrow_tab.assign(64 + 24, -1);
     for (int g = 0; g < 8; ++g) {
       for (int k = 0; k < 5; ++k) if (g < 5) M.arrow_tab[8 * g + k] = M.arrow_bdof[g][k];

@@ -71,6 +71,7 @@ struct DevModel {
   int arrow_bdof[5][5];  // dof of (branch, slot), root to leaf
   int arrow_odof[8];     // dof of border row r
   int arrow_bmask[5];    // dof bit mask of each branch
+  int arrow_omask;       // dof bit mask of the border
   int arrow_rowdof[24];  // dofs that own friction-loss / limit rows (-1 padded), dealt three to a lane in the row view
   // the same tables as a device array for lane-indexed reads (arrow_tab): [8 lanes][8] = branch dofs 0-4, border dof 5, -, - then [24] rows
 #define DEX_AR_TAB_ROWS 64

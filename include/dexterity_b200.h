@@ -104,10 +104,11 @@ int dex_set_chunks(DexBatch* batch, int nchunk);
  * its schedule, 1 = always one thread per env.  Both compute the same quantities. */
 int dex_set_tree_kernel(DexBatch* batch, int thread_per_env);
 
-/* Chooses the constraint-solver kernels: 0 (default) = envs whose Newton Hessian is block-arrowhead (no contact joins two
- * fingers, at most 8 contacts) take the structured eight-lanes-per-env solver and the rest the dense warp-per-env solver,
- * 1 = the dense solver for every env.  Both minimise the same cost to the same tolerance. */
-int dex_set_solver(DexBatch* batch, int dense_only);
+/* Chooses the constraint-solver kernels.  0 = the dense warp-per-env solver for every env; 1 (default) = envs without
+ * contacts take the structured eight-lanes-per-env solver (contact-free form), the rest the dense one; 2 = in addition, envs
+ * with at most 8 contacts of which at most 2 join two fingers take the structured solver's full form.  All minimise the same
+ * cost to the same tolerance. */
+int dex_set_solver(DexBatch* batch, int mode);
 
 /* Number of this library's kernels launched since batch creation (bench `gpu_launches`). */
 int64_t dex_launch_count(const DexBatch* batch);
@@ -220,10 +221,10 @@ int dex_ik_solve(DexModel* model, int dtype, const void* targets_dev, int n, con
 
 /* Per-kernel-class device timing for the benchmark's roofline block: when enabled every launch is
  * bracketed by a cudaEvent pair on the launching stream.  dex_get_kernel_times synchronises and
- * returns total milliseconds and launch counts in arrays of 8: {pre-step, broadphase, dense solve, post-step, tree,
- * narrowphase, contact compaction, structured solve}. */
+ * returns total milliseconds and launch counts in arrays of 10: {pre-step, broadphase, dense solve, post-step, tree,
+ * narrowphase, contact compaction, structured solve (full form), prop placement, structured solve (contact-free form)}. */
 int dex_set_profiling(DexBatch* batch, int on);
-int dex_get_kernel_times(DexBatch* batch, double* ms8, int64_t* count8, int reset);
+int dex_get_kernel_times(DexBatch* batch, double* ms10, int64_t* count10, int reset);
 
 const char* dex_last_error(void);
 

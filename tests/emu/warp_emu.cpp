@@ -108,7 +108,7 @@ struct EmuModelT {
     dev.ngeom = h.ngeom; dev.npair = h.npair; dev.nsite = h.nsite; dev.nbodypair = h.nbodypair; dev.ntree = h.ntree;
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
-    dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo;
+    dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo; dev.arrow_omask = h.arrow_omask;
     std::memcpy(dev.arrow_bdof, h.arrow_bdof, sizeof(dev.arrow_bdof)); std::memcpy(dev.arrow_odof, h.arrow_odof, sizeof(dev.arrow_odof));
     std::memcpy(dev.arrow_bmask, h.arrow_bmask, sizeof(dev.arrow_bmask)); std::memcpy(dev.arrow_rowdof, h.arrow_rowdof, sizeof(dev.arrow_rowdof));
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
@@ -149,14 +149,19 @@ static int emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T
 template <typename T>
 static void emu_solve(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int e0, int e1, const int* cls, T* smem,
                       int integrate) {
-  int quad[4] = {-1, -1, -1, -1};
-  const bool use_arrow = m.arrow_ok && !getenv("DEX_EMU_DENSE");
-  bool any = false;
+  // DEX_EMU_SOLVER: 0 dense only, 1 contact-free envs structured, 2 (default here) also the block-arrowhead envs with contacts
+  int quad[4] = {-1, -1, -1, -1}, quadl[4] = {-1, -1, -1, -1};
+  const char* ms = getenv("DEX_EMU_SOLVER");
+  const int mode = !m.arrow_ok || getenv("DEX_EMU_DENSE") || dbg.M || dbg.efc ? 0 : (ms ? atoi(ms) : 2);   // M / efc dumps: dense kernel only, as on the GPU
+  bool any = false, anyl = false;
   for (int env = e0; env < e1; ++env) {
-    if (use_arrow && cls[env - e0] >= DEX_NCLASS_DENSE) { quad[env - e0] = env; any = true; g_arrow_envs++; }
+    const int c = cls[env - e0];
+    if (mode >= 1 && c == DEX_NCLASS - 1) { quadl[env - e0] = env; anyl = true; g_arrow_envs++; }
+    else if (mode >= 2 && c >= DEX_NCLASS_DENSE) { quad[env - e0] = env; any = true; g_arrow_envs++; }
     else { dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem, integrate); }); g_dense_envs++; }
   }
-  if (any) dex_emu::run_warp([&]() { dex_arrow_warp<T>(m, st, dbg, quad[dex_lane() >> 3], smem, integrate); });
+  if (any) dex_emu::run_warp([&]() { dex_arrow_warp<T, true>(m, st, dbg, quad[dex_lane() >> 3], smem, integrate); });
+  if (anyl) dex_emu::run_warp([&]() { dex_arrow_warp<T, false>(m, st, dbg, quadl[dex_lane() >> 3], smem, integrate); });
 }
 
 // K0 for the envs e0 .. e0+3: the 8-lanes-per-env warp form when the model has a schedule, else one
@@ -202,9 +207,6 @@ void* emu_model_create(const void* blob, uint64_t nbytes, char* err, int errlen)
 void emu_model_destroy(void* m) { delete (EmuModel*)m; }
 int emu_k2_smem_words() { return DEX_K2_SMEM_T; }
 void emu_solver_counts(long* out, int reset) { out[0] = g_arrow_envs; out[1] = g_dense_envs; if (reset) { g_arrow_envs = 0; g_dense_envs = 0; } }
-#ifdef DEX_EMU_STATS
-void emu_ls_stats(long* out) { out[0] = dex_emu_ls_count; out[1] = dex_emu_newton_count; dex_emu_ls_count = 0; dex_emu_newton_count = 0; }
-#endif
 int emu_k0_rounds(void* m) { return ((EmuModel*)m)->host.k0_rounds; }
 
 // Hill-climbing support function of K1b against an exhaustive scan, for every mesh geom and `ndir` random

@@ -62,6 +62,57 @@ def test_kernel_bodies_fp32_match_oracle(reorient_model, emu_model, states):
     assert np.median(rel) < 1e-5 and (rel < 1e-4).mean() >= 0.8
 
 
+def _finger_of_body(c):
+    """branch id of every body of the Shadow hand (0-4 = ff mf rf lf th), -1 for the rest"""
+    out = []
+    for name in c.body_names:
+        tag = name.split("/")[-1][:2]
+        out.append({"ff": 0, "mf": 1, "rf": 2, "lf": 3, "th": 4}.get(tag, -1) if name.startswith("shadow_hand_e/") else -1)
+    return np.array(out)
+
+
+def test_structured_solver_forms_match_dense_kernel_and_oracle(reorient_model, emu_model, monkeypatch):
+    """K2 has three kernel bodies: the dense warp-per-env solver, and the structured eight-lanes-per-env solver
+    (dex_arrow.cuh) in its full and its contact-free form.  On contact-rich states, including states where a contact
+    joins two fingers (the low-rank correction), all minimise the same cost: in FP64 they agree to rounding with each
+    other and with the oracle, Newton iteration for Newton iteration."""
+    c = reorient_model
+    st = statelib.rollout_states_batch(c, seed=21, nenv=48, snapshots=6, every=7, nthreads=8)
+    ref = statelib.oracle_step(c, st, nsub=1)
+    fb = _finger_of_body(c)
+    cross = np.array([any(fb[c.GEOM_BODY[g1]] >= 0 and fb[c.GEOM_BODY[g2]] >= 0 and fb[c.GEOM_BODY[g1]] != fb[c.GEOM_BODY[g2]]
+                          for g1, g2 in pairs) for pairs in ref["pairs"]])
+    assert cross.sum() >= 10 and (ref["ncon"] == 0).sum() >= 20 and ((ref["ncon"] > 0) & ~cross).sum() >= 20
+    cnt = (ctypes.c_long * 2)()
+    emu_model.lib.emu_solver_counts.argtypes = [ctypes.POINTER(ctypes.c_long), ctypes.c_int]
+    outs = {}
+    for mode in (0, 1, 2):
+        monkeypatch.setenv("DEX_EMU_SOLVER", str(mode))
+        emu_model.lib.emu_solver_counts(cnt, 1)
+        outs[mode] = emu_model.run(st["qpos"], st["qvel"], st["ctrl"], st["warm"], nsub=1, dtype=np.float64)
+        emu_model.lib.emu_solver_counts(cnt, 1)
+        n = len(st["qpos"])
+        if mode == 0: assert cnt[0] == 0
+        if mode == 1: assert cnt[0] == (ref["ncon"] == 0).sum()
+        if mode == 2: assert cnt[0] >= 0.9 * n and cnt[0] > (~cross).sum() - 8, "cross-contact envs must take the structured solver too"
+        assert (outs[mode]["status"] == 0).all() and (outs[mode]["ncon"] == ref["ncon"]).all()
+    scale = np.maximum(1, np.abs(outs[0]["qvel"]).max(axis=1))
+    for mode in (1, 2):
+        d = np.abs(outs[mode]["qvel"] - outs[0]["qvel"]).max(axis=1) / scale
+        assert d.max() < 1e-10, (mode, d.max())
+        assert (outs[mode]["niter"] == outs[0]["niter"]).mean() > 0.98
+        assert np.abs(outs[mode]["warm"] - outs[0]["warm"]).max() < 1e-7 * max(1.0, np.abs(outs[0]["warm"]).max())
+    # and against the oracle (MPR tie states excepted, as everywhere)
+    rel = np.abs(outs[2]["qvel"] - ref["qvel"]).max(axis=1) / np.maximum(1, np.abs(ref["qvel"]).max(axis=1))
+    assert np.median(rel) < 1e-12 and (rel < 1e-6).mean() > 0.97
+    # FP32, the product precision: same statistics as the dense kernel
+    monkeypatch.setenv("DEX_EMU_SOLVER", "2")
+    f32 = emu_model.run(st["qpos"], st["qvel"], st["ctrl"], st["warm"], nsub=1, dtype=np.float32)
+    rel32 = np.abs(f32["qvel"] - ref["qvel"]).max(axis=1) / np.maximum(1, np.abs(ref["qvel"]).max(axis=1))
+    assert np.median(rel32) < 1e-6 and (rel32 <= 1e-4).mean() > 0.95 and (f32["status"] == 0).all()
+    assert (rel32[cross] <= 1e-4).mean() > 0.85
+
+
 def _params(c):
     from dexterity_b200 import envs
     p = envs.TaskParams()

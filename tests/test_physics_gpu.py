@@ -191,6 +191,46 @@ def test_kernel_forms_and_env_chunks_agree(setup):
     assert dq.median() < 1e-6 and (dq < 1e-4).float().mean() > 0.98
 
 
+def test_solver_kernels_agree(reorient_model):
+    """K2 is three kernels (dexterity_b200.h, dex_set_solver): the dense warp-per-env solver, and the structured
+    eight-lanes-per-env solver in its full and its contact-free form.  Whichever kernel an env is routed to, it minimises the
+    same cost to the same tolerance: on 4096 rollout states the modes agree with each other to FP32 rounding (FP64: to
+    1e-10) and each is within the north-star tolerance of the oracle; mode 2 must route most envs to the structured kernel."""
+    from dexterity_b200 import backend
+    compiled = reorient_model
+    states = statelib.rollout_states_batch(compiled, seed=77, nenv=256, snapshots=16, every=5, nthreads=8)
+    n = len(states["qpos"])
+    ref = statelib.oracle_step(compiled, states, nsub=1)
+    model = backend.PhysicsModel(compiled, 0)
+    stable = statelib.mpr_stable_mask(compiled, states)
+    for dtype, tol_modes in ((torch.float64, 1e-10), (torch.float32, 5e-5)):
+        outs = {}
+        for mode in (0, 1, 2):
+            b = backend.PhysicsBatch(model, n, dtype)
+            b.set_solver(mode)
+            statelib.upload(b, states)
+            launches0 = b.launch_count
+            b.step(1)
+            torch.cuda.synchronize()
+            assert b.launch_count - launches0 == 5 + mode     # tree, broadphase, narrowphase, compaction, dense solver (+ structured forms)
+            assert (b.status.cpu().numpy() & 1 == 0).all()
+            outs[mode] = (b.qpos.cpu().numpy().astype(np.float64), b.qvel.cpu().numpy().astype(np.float64), b.niter.cpu().numpy(),
+                          b.ncon.cpu().numpy())
+        for mode in (1, 2):
+            assert (outs[mode][3] == outs[0][3]).all()
+            dv = relerr(outs[mode][1], outs[0][1])
+            frac = (dv <= tol_modes).mean()
+            print(f"solver mode {mode} vs dense ({dtype}): median {np.median(dv):.2e}, share within {tol_modes:g}: {frac:.4f}, "
+                  f"mean Newton iterations {outs[mode][2].mean():.3f} vs {outs[0][2].mean():.3f}")
+            assert frac >= (0.999 if dtype == torch.float64 else 0.97), (mode, dtype, frac)
+            ev = relerr(outs[mode][1], ref["qvel"])
+            eq = relerr(outs[mode][0], ref["qpos"])
+            tol = REL_TOL_F32 if dtype == torch.float32 else 1e-6
+            ok = (ev <= tol) & (eq <= tol)
+            assert ok[stable].mean() >= 0.985, (mode, dtype, ok[stable].mean())
+            assert abs(outs[mode][2].mean() - outs[0][2].mean()) < 0.05
+
+
 def test_unbound_or_bad_calls_fail_loudly(reorient_model):
     from dexterity_b200 import backend
     model = backend.PhysicsModel(reorient_model, 0)

@@ -22,9 +22,9 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 lib.dex_set_profiling(env.physics.ptr, 1)
 for _ in range(5): env.step(lo + (hi - lo) * torch.rand(N, 20, device=env.device))
-ms8 = (ctypes.c_double * 8)(); c8 = (ctypes.c_int64 * 8)()
+ms8 = (ctypes.c_double * 10)(); c8 = (ctypes.c_int64 * 10)()
 lib.dex_get_kernel_times(env.physics.ptr, ms8, c8, 1)
-names = ["pre", "collide", "solve", "post", "tree", "k5", "k6", "arrow"]
-per = " ".join("%s=%.3f" % (names[i], ms8[i] / max(1, c8[i])) for i in range(8) if c8[i])
+names = ["pre", "collide", "solve", "post", "tree", "k5", "k6", "arrow", "place", "lite"]
+per = " ".join("%s=%.3f" % (names[i], ms8[i] / max(1, c8[i])) for i in range(10) if c8[i])
 print(sys.argv[1:], "env step %.3f ms -> %.3e env-steps/s niter %.2f ncon %.2f | per launch ms: %s" % (
     ms, N / ms * 1e3, env.physics.niter.float().mean().item(), env.physics.ncon.float().mean().item(), per))
