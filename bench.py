@@ -274,8 +274,11 @@ def run_gpu(args):
         value = total_envs * args.steps / (dev_ms_max * 1e-3)
         e2e_value = total_envs * args.steps / (e2e_ms_max * 1e-3)
         peak, peak_src = measured_peaks()
-        names = ["task_pre", "k_collide", "k_dynamics", "task_post", "k_tree", "k_narrow", "k_compact"]
-        per = {names[c]: (ms4[c] / max(1, cnt4[c]), cnt4[c]) for c in range(7)}
+        # k_dynamics = dense warp-per-env solver (envs with contacts), k_dynamics_arrow = structured eight-lanes-per-env solver
+        # (contact-free envs); the two run concurrently on two streams, so their event times overlap
+        names = ["task_pre", "k_collide", "k_dynamics", "task_post", "k_tree", "k_narrow", "k_compact", "k_dynamics_arrow_full",
+                 "k_place", "k_dynamics_arrow"]
+        per = {names[c]: (ms4[c] / max(1, cnt4[c]), cnt4[c]) for c in range(10) if cnt4[c] or c < 7}
         dom = max(("k_tree", "k_collide", "k_narrow", "k_dynamics"), key=lambda k_: per[k_][0])
         dom_ms = per[dom][0]
         achieved = n * B_MJ / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

@@ -128,8 +128,8 @@ class PhysicsBatch:
         _check(lib().dex_bind(self._ptr, FIELD["WORK"], ctypes.c_void_p(work.data_ptr()), cap))
         self._store["WORK"] = work
         self.set_chunks(int(os.environ.get("DEX_CHUNKS", "1")))
-        if os.environ.get("DEX_SOLVER_MODE"):
-            self.set_solver(int(os.environ["DEX_SOLVER_MODE"]))
+        if os.environ.get("DEX_SOLVER_MODE") or os.environ.get("DEX_SOLVER_SERIAL"):
+            self.set_solver(int(os.environ.get("DEX_SOLVER_MODE", "1")))
         # public views with the model's true widths
         self.qpos = self._store["QPOS"][:, :c.nq]
         self.qvel = self._store["QVEL"][:, :c.nv]

@@ -640,6 +640,7 @@ int dex_set_tree_kernel(DexBatch* b, int scalar) {
 int dex_set_solver(DexBatch* b, int mode) {
   if (!b || mode < 0 || mode > 2) return fail(DEX_E_ARG, "solver mode must be 0, 1 or 2");
   b->solver_mode = mode;
+  b->solver_serial = getenv("DEX_SOLVER_SERIAL") != nullptr;   // profiling aid: all solver kernels on the caller's stream
   return DEX_OK;
 }
 

@@ -217,16 +217,54 @@ DEX_DEV_NOINLINE T dex_matvec(const T* Mg, const T* x, int nv) {
   }
   return i < nv ? s0 + s1 : T(0);
 }
-// out[t] = Jc[t] . x for the 3*ncon contact-frame Jacobian rows.  Jc is the env's global (L2) scratch,
-// read coalesced with lane = dof; xi is this lane's component of x.
+// out[t] = Jc[t] . x for the 3*ncon contact-frame Jacobian rows.  Lane = ROW (rows t, t + 32, t + 64): every lane walks its own
+// row of the env's global (L2 / L1) scratch with 16-byte loads against x in shared memory (32 entries, zero beyond nv).
+// 48 instructions per 32 rows; the earlier lane = dof form (three rows per round, one warp reduction each) cost 40 per
+// CONTACT, which made the envs with 10-20 contacts the stragglers of the whole launch (r02 niter probe).
 template <typename T>
-DEX_DEV_NOINLINE void dex_contact_dots(const T* Jc, T xi, int nrows, T* out) {
+DEX_DEV_NOINLINE void dex_contact_dots(const T* Jc, const T* xs, int nrows, T* out) {
   const int lane = dex_lane();
 #pragma unroll 1
-  for (int t = 0; t < nrows; t += 3) {   // one contact (3 frame rows) per round, reductions interleaved
-    T s0 = Jc[t * DEX_JC_ROW + lane] * xi, s1 = Jc[(t + 1) * DEX_JC_ROW + lane] * xi, s2 = Jc[(t + 2) * DEX_JC_ROW + lane] * xi;
-    dex_warp_sum3(s0, s1, s2);
-    if (lane == 0) { out[t] = s0; out[t + 1] = s1; out[t + 2] = s2; }
+  for (int t0 = 0; t0 < nrows; t0 += 32) {
+    const int t = t0 + lane;
+    const T* row = Jc + (t < nrows ? t : 0) * DEX_JC_ROW;
+    T s = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      T a[4], x[4];
+      dex_ld4(row + j, a); dex_ld4(xs + j, x);
+      s += a[0] * x[0] + a[1] * x[1] + a[2] * x[2] + a[3] * x[3];
+    }
+    if (t < nrows) out[t] = s;
+  }
+  dex_syncwarp();
+}
+
+// H += Jc^T W Jc for one contact, strictly lower triangle of the warp's tile (the diagonal lives in registers, the caller
+// adds it).  The contact touches n = popc(mask) dofs, i.e. n (n - 1) / 2 entries below the diagonal; they are dealt out 32
+// to a round, lane p taking the pair (r, s), r > s, of the mask's dof list and fetching t = W a of dof r and a of dof s with
+// six shuffles.  With the usual 13 dofs (finger chain, wrist, object) that is three rounds instead of the 13 trips, one per
+// dof, of the earlier "every row walks the whole mask" loop.  `scratch`: 32 ints of shared memory (the dof list).
+template <typename T>
+DEX_DEV void dex_contact_hessian(T* H, unsigned mask, T a0, T a1, T a2, T t0, T t1, T t2, int* scratch) {
+  const int lane = dex_lane();
+  const int n = dex_popc(mask);
+  if ((mask >> lane) & 1u) scratch[dex_popc(mask & ((1u << lane) - 1u))] = lane;
+  dex_syncwarp();
+  const int npair = n * (n - 1) / 2;
+#pragma unroll 1
+  for (int p0 = 0; p0 < npair; p0 += 32) {
+    const int p = p0 + lane;
+    const bool on = p < npair;
+    // p = r (r - 1) / 2 + s, 0 <= s < r
+    int r = (int)((T(1) + dx_sqrt(T(8 * (on ? p : 0) + 1))) * T(0.5));
+    if (r * (r - 1) / 2 > p) --r;
+    if ((r + 1) * r / 2 <= p) ++r;
+    const int sidx = (on ? p : 0) - r * (r - 1) / 2;
+    const int i = on ? scratch[r] : 0, j = on ? scratch[sidx] : 0;
+    const T ti0 = dex_shfl(t0, i), ti1 = dex_shfl(t1, i), ti2 = dex_shfl(t2, i);
+    const T bj0 = dex_shfl(a0, j), bj1 = dex_shfl(a1, j), bj2 = dex_shfl(a2, j);
+    if (on) H[i * DEX_MSTRIDE + j] += ti0 * bj0 + ti1 * bj1 + ti2 * bj2;
   }
   dex_syncwarp();
 }
@@ -340,7 +378,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     if (lane == 0) *(int*)(cdat + c * DEX_CDAT_STRIDE + CD_MASK) = (int)(m1 | m2);
   }
   dex_syncwarp();
-  dex_contact_dots(Jc, qv, 3 * ncon, cdot);  // contact-frame velocities
+  dex_contact_dots(Jc, qvel, 3 * ncon, cdot);  // contact-frame velocities (qvel[] is zero beyond nv)
   if (lane < ncon) {  // lane = contact: impedance, R, aref of the 4 pyramid rows
     const int c = lane;
     const T* cc = cin + c * DEX_CON_STRIDE;
@@ -379,7 +417,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   vecA[lane] = qacc;
   dex_syncwarp();
   T Ma = dex_matvec(M, vecA, nv);
-  dex_contact_dots(Jc, qacc, 3 * ncon, cdot);
+  dex_contact_dots(Jc, vecA, 3 * ncon, cdot);
   if (lane < ncon) {
     T* cdt = cdat + lane * DEX_CDAT_STRIDE;
     const T mu = cdt[CD_MU], an = cdot[3 * lane], a1 = cdot[3 * lane + 1], a2 = cdot[3 * lane + 2];
@@ -472,12 +510,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
         const T t0 = a0 * w00 + a1 * w01 + a2 * w02, t1 = a0 * w01 + a1 * w11, t2 = a0 * w02 + a2 * w22;
         const bool mine = isdof && ((mask >> lane) & 1u);
         if (mine) hd += t0 * a0 + t1 * a1 + t2 * a2;
-        while (mask) {
-          const int j = dex_ffs(mask) - 1;
-          mask &= mask - 1;
-          const T b0 = dex_shfl(a0, j), b1 = dex_shfl(a1, j), b2 = dex_shfl(a2, j);
-          if (mine && j < lane) H[lane * DEX_MSTRIDE + j] += t0 * b0 + t1 * b1 + t2 * b2;
-        }
+        dex_contact_hessian(H, mask & (nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u)), a0, a1, a2, t0, t1, t2, reinterpret_cast<int*>(cdot));
       }
       dex_syncwarp();
       int cfail = 0;
@@ -490,7 +523,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     vecB[lane] = isdof ? search : T(0);
     dex_syncwarp();
     const T Mv = dex_matvec(M, vecB, nv);
-    dex_contact_dots(Jc, isdof ? search : T(0), 3 * ncon, cdot);
+    dex_contact_dots(Jc, vecB, 3 * ncon, cdot);
     if (lane < ncon) {
       T* cdt = cdat + lane * DEX_CDAT_STRIDE;
       const T mu = cdt[CD_MU], sn = cdot[3 * lane], s1 = cdot[3 * lane + 1], s2 = cdot[3 * lane + 2];
