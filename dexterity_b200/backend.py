@@ -170,7 +170,8 @@ class PhysicsBatch:
 
     def set_solver(self, mode: int) -> None:
         """0: dense warp-per-env solver for every env; 1 (default): envs without contacts take the structured
-        8-lanes-per-env solver kernel; 2: also envs with <= 8 contacts of which <= 2 join two fingers."""
+        8-lanes-per-env solver kernel; 2: also envs with <= 8 contacts of which <= 2 join two fingers; 3: sparse L^T D L form
+        of the warp-per-env kernel for envs without finger-finger contacts."""
         _check(lib().dex_set_solver(self._ptr, int(mode)))
 
     def step(self, nsub: int = 1) -> None:

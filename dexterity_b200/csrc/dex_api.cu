@@ -12,6 +12,7 @@
 #include "dex_arrow.cuh"
 #include "dex_collide.cuh"
 #include "dex_dynamics.cuh"
+#include "dex_sparse.cuh"
 #include "dex_host_model.h"
 #include "dex_ik.cuh"
 #include "dex_task.cuh"
@@ -153,26 +154,31 @@ __global__ void __launch_bounds__(kCollideWarps * 32, DEX_K1_MINB * kWarpsPerBlo
 #define DEX_K2_WARPS 1   // single-warp CTAs: envs differ 3x in solver work, a CTA of 4 would hold its slots until the slowest is done
 #endif
 constexpr int kDynWarps = DEX_K2_WARPS;
-template <typename T>
-__global__ void __launch_bounds__(kDynWarps * 32, DEX_K2_CTAS / DEX_K2_WARPS) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
-                                                                   int integrate, int nclass) {
+#ifndef DEX_K2S_CTAS
+#define DEX_K2S_CTAS 22
+#endif
+// SP = 0: dense Cholesky form; SP = 1: sparse L^T D L form (dex_sparse.cuh).  The kernel takes K1c's classes [c0, c1).
+template <typename T, int SP>
+__global__ void __launch_bounds__(kDynWarps * 32, (SP ? DEX_K2S_CTAS : DEX_K2_CTAS) / DEX_K2_WARPS) k_dynamics(DevModel<T> m, BatchState<T> st, DynDebug<T> dbg,
+                                                                   int integrate, int c0, int c1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int slot = st.env0 + blockIdx.x * kDynWarps + warp;
   if (slot >= st.nenv) return;
   int env = slot;
-  if (st.order) {   // K1c's lists, heaviest class first; `nclass` leading classes are this kernel's (the rest: k_dynamics_arrow)
-    int s = slot - st.env0, c = 0;
+  if (st.order) {   // K1c's lists, heaviest class first
+    int s = slot - st.env0, c = c0;
     int cnt[DEX_NCLASS];   // all class counters in one go (a walk of dependent loads costs an L2 round trip per class)
 #pragma unroll
     for (int k = 0; k < DEX_NCLASS; ++k) cnt[k] = st.nwork[2 + k];
 #pragma unroll
-    for (int k = 0; k < DEX_NCLASS; ++k) if (c == k && k < nclass && s >= cnt[k]) { s -= cnt[k]; ++c; }
-    if (c >= nclass) return;
+    for (int k = 0; k < DEX_NCLASS; ++k) if (c == k && k < c1 && s >= cnt[k]) { s -= cnt[k]; ++c; }
+    if (c >= c1) return;
     env = st.order[(size_t)c * st.order_stride + st.env0 + s];
   }
-  T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * DEX_K2_SMEM_T;
-  dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
+  T* smem = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (SP ? DEX_K2S_SMEM_T : DEX_K2_SMEM_T);
+  if (SP) dex_dynamics_sp_env<T>(m, st, dbg, env, smem, integrate);
+  else dex_dynamics_env<T>(m, st, dbg, env, smem, integrate);
 }
 
 // K2A: structured solver, eight lanes per env.  Warp w takes the envs 4 w .. 4 w + 3 of the concatenated class lists
@@ -248,6 +254,7 @@ struct DeviceArrays {
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
     dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo; dev.arrow_omask = h.arrow_omask;
+    dev.sp_ok = h.sp_ok; dev.sp[0] = h.sp[0]; dev.sp[1] = h.sp[1];
     std::memcpy(dev.arrow_bdof, h.arrow_bdof, sizeof(dev.arrow_bdof)); std::memcpy(dev.arrow_odof, h.arrow_odof, sizeof(dev.arrow_odof));
     std::memcpy(dev.arrow_bmask, h.arrow_bmask, sizeof(dev.arrow_bmask)); std::memcpy(dev.arrow_rowdof, h.arrow_rowdof, sizeof(dev.arrow_rowdof));
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
@@ -306,7 +313,8 @@ struct DexBatch {
   bool attrs_set = false;
   // env chunks run as independent pipelines on library-owned streams (forked from / joined to the caller's)
   bool tree_scalar = false;  // force the thread-per-env tree kernel (tests / tuning)
-  int solver_mode = 1;       // 0 dense solver only, 1 structured solver for contact-free envs, 2 also for block-arrowhead envs with contacts
+  int solver_mode = 1;       // 0 dense solver only, 1 (default) structured solver for contact-free envs, 2 also for block-arrowhead envs with contacts,
+                             // 3 sparse form of the warp-per-env kernel (dex_sparse.cuh) for every env whose contacts keep the Hessian in the chained pattern
   bool solver_serial = false;
   // the two solver kernels work on disjoint envs: the structured one runs on a second stream, forked after K1c and joined before the next K0
   cudaStream_t s2 = nullptr;
@@ -397,7 +405,8 @@ template <typename T>
 int set_attrs(DexBatch* b) {
   if (b->attrs_set) return DEX_OK;
   DEX_CUDA(cudaFuncSetAttribute(k_collide<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kCollideWarps * DEX_K1_SMEM_T * sizeof(T))));
-  DEX_CUDA(cudaFuncSetAttribute(k_dynamics<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute((k_dynamics<T, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kDynWarps * DEX_K2_SMEM_T * sizeof(T))));
+  DEX_CUDA(cudaFuncSetAttribute((k_dynamics<T, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kDynWarps * DEX_K2S_SMEM_T * sizeof(T))));
   DEX_CUDA(cudaFuncSetAttribute((k_dynamics_arrow<T, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DEX_K2A_SMEM_T * sizeof(T))));
   DEX_CUDA(cudaFuncSetAttribute((k_dynamics_arrow<T, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)DEX_K2L_SMEM_T * sizeof(T))));
   // K0 / K1b keep per-thread state in local memory: give them the whole L1 (no shared-memory carve-out)
@@ -449,6 +458,7 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
     const int t8grid = (n + kTreeWarps * DEX_K0_ENVS - 1) / (kTreeWarps * DEX_K0_ENVS);
     const size_t smem0 = (size_t)kTreeWarps * DEX_K0_SMEM_T * sizeof(T);
     const int ngrid = narrow_grid(n);
+    st.cls_mode = (b->solver_mode == 3 && m.sp_ok) ? 2 : (m.arrow_ok ? 1 : 0);
     for (int i = 0; i < nsub; ++i) {
       {
         ProfScope ps(b, 4, cs);
@@ -465,10 +475,13 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
         // Solver kernels by K1c class (dex_compact_env): class 7 = envs without contacts -> structured solver, contact-free form;
         // classes 4-6 = block-arrowhead Hessian with contacts -> structured solver, full form (solver_mode 2) or dense;
         // classes 0-3 -> dense warp-per-env solver.  The kernels work on disjoint envs; the dense one runs on a second stream.
-        const int mode = (m.arrow_ok && st.order && collide && !dbg.M && !dbg.efc) ? b->solver_mode : 0;
+        int mode = (st.order && collide && !dbg.M && !dbg.efc) ? b->solver_mode : 0;
+        if ((mode == 1 || mode == 2) && !m.arrow_ok) mode = 0;
+        if (mode == 3 && !m.sp_ok) mode = 0;
         const int ndense = mode == 0 ? DEX_NCLASS : (mode == 1 ? DEX_NCLASS - 1 : DEX_NCLASS_DENSE);
         const int agrid = (n + DEX_AR_ENVS - 1) / DEX_AR_ENVS;
         const bool fork = mode != 0 && nchunk == 1 && !b->solver_serial;
+        const size_t smem2s = (size_t)kDynWarps * DEX_K2S_SMEM_T * sizeof(T);
         cudaStream_t sa = cs;
         if (fork) {
           if (!b->s2) {
@@ -481,9 +494,10 @@ int launch_physics(DexBatch* b, const DevModel<T>& m, BatchState<T> st, const Dy
           sa = b->s2;
         }
         if (mode == 2) { ProfScope ps(b, 7, sa); k_dynamics_arrow<T, true><<<agrid, 32, smem2a, sa>>>(m, st, dbg, integrate, DEX_NCLASS_DENSE, DEX_NCLASS - 1); b->launches++; }
-        if (mode != 0) { ProfScope ps(b, 9, sa); k_dynamics_arrow<T, false><<<agrid, 32, smem2l, sa>>>(m, st, dbg, integrate, DEX_NCLASS - 1, DEX_NCLASS); b->launches++; }
+        if (mode == 1 || mode == 2) { ProfScope ps(b, 9, sa); k_dynamics_arrow<T, false><<<agrid, 32, smem2l, sa>>>(m, st, dbg, integrate, DEX_NCLASS - 1, DEX_NCLASS); b->launches++; }
+        if (mode == 3) { ProfScope ps(b, 7, sa); k_dynamics<T, 1><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2s, sa>>>(m, st, dbg, integrate, DEX_NCLASS_DENSE, DEX_NCLASS); b->launches++; }
         if (fork) DEX_CUDA(cudaEventRecord(b->ev_k2a, b->s2));
-        { ProfScope ps(b, 2, cs); k_dynamics<T><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, ndense); b->launches++; }
+        { ProfScope ps(b, 2, cs); k_dynamics<T, 0><<<(n + kDynWarps - 1) / kDynWarps, kDynWarps * 32, smem2, cs>>>(m, st, dbg, integrate, 0, ndense); b->launches++; }
         if (fork) DEX_CUDA(cudaStreamWaitEvent(cs, b->ev_k2a, 0));
       }
     }
@@ -638,7 +652,7 @@ int dex_set_tree_kernel(DexBatch* b, int scalar) {
 }
 
 int dex_set_solver(DexBatch* b, int mode) {
-  if (!b || mode < 0 || mode > 2) return fail(DEX_E_ARG, "solver mode must be 0, 1 or 2");
+  if (!b || mode < 0 || mode > 3) return fail(DEX_E_ARG, "solver mode must be 0, 1, 2 or 3");
   b->solver_mode = mode;
   b->solver_serial = getenv("DEX_SOLVER_SERIAL") != nullptr;   // profiling aid: all solver kernels on the caller's stream
   return DEX_OK;
@@ -657,7 +671,11 @@ int dex_bind(DexBatch* b, int field, void* dev_ptr, int64_t row_stride) {
   return DEX_OK;
 }
 
+#ifdef DEX_EXP   // timing experiments (tools/k2_breakdown.py): DEX_FREEZE=1 computes the step but keeps the state
+int dex_mj_step(DexBatch* b, int nsub, void* stream) { return dispatch(b, nsub, true, true, getenv("DEX_FREEZE") ? 2 : 1, stream); }
+#else
 int dex_mj_step(DexBatch* b, int nsub, void* stream) { return dispatch(b, nsub, true, true, 1, stream); }
+#endif
 int dex_mj_forward(DexBatch* b, void* stream) { return dispatch(b, 1, true, true, 0, stream); }
 int dex_mj_collide(DexBatch* b, void* stream) { return dispatch(b, 1, true, false, 0, stream); }
 int64_t dex_launch_count(const DexBatch* b) { return b ? b->launches : 0; }

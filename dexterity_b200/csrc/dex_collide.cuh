@@ -835,7 +835,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
 // the class list (one global atomic per class and CTA).
 template <typename T>
 DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int env) {
-  if (dex_env_off(st, env)) return m.arrow_ok ? -1 : DEX_NCLASS - 1;   // warp-uniform; with the two-kernel order a skipped env is simply not listed
+  if (dex_env_off(st, env)) return st.cls_mode ? -1 : DEX_NCLASS - 1;   // warp-uniform; with the two-kernel order a skipped env is simply not listed
   const int lane = dex_lane();
   const int nslot = st.nslot[env];
   const T* stage = st.stage + (size_t)env * DEX_STAGE_ENV;
@@ -857,7 +857,12 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
     if (valid) {
       if (idx < DEX_MAXCON) { for (int k = 0; k < DEX_CON_STRIDE; ++k) cout[idx * DEX_CON_STRIDE + k] = rec[k]; }
       else overflow = true;
-      if (m.arrow_ok) {   // does the contact join two branches of the arrowhead split (finger - finger)?
+      if (st.cls_mode == 2) {   // sparse solver: the contact's dofs must lie on one root-to-leaf path of the chained elimination structure
+        const int pr = (int)rec[7];
+        const int b1 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr)), b2 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr));
+        const unsigned mx = (unsigned)dex_ldg(m.body_dofmask + b1) | (unsigned)dex_ldg(m.body_dofmask + b2);
+        cross_bad = cross_bad || ((mx & ~(unsigned)dex_ldg(m.body_augmask + b1)) && (mx & ~(unsigned)dex_ldg(m.body_augmask + b2)));
+      } else if (st.cls_mode == 1) {   // does the contact join two branches of the arrowhead split (finger - finger)?
         const int pr = (int)rec[7];
         const unsigned mx = (unsigned)dex_ldg(m.body_dofmask + dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr))) ^
                             (unsigned)dex_ldg(m.body_dofmask + dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr)));
@@ -877,7 +882,11 @@ DEX_DEV int dex_compact_env(const DevModel<T>& m, const BatchState<T>& st, int e
   // 2.4, 3.5, 4.4, 5.2, 5.9, ...), so envs with contacts go first and the kernel does not end on a few long-running
   // warps (r01n: the SMs idled 14 % of K2's duration).  Keying on the previous step's iteration count instead was
   // slower: envs with equal contact counts also share code paths and cache lines.
-  if (m.arrow_ok) {
+  if (st.cls_mode == 2) {   // classes 0-3: dense form of the solver kernel, 4-7: sparse form; most contacts first within each
+    if (dex_ballot(cross_bad)) return ncon >= 9 ? 0 : (ncon >= 4 ? 1 : (ncon >= 2 ? 2 : 3));
+    return ncon >= 4 ? 4 : (ncon >= 2 ? 5 : (ncon >= 1 ? 6 : 7));
+  }
+  if (st.cls_mode == 1) {
     // Two solver kernels: classes 0-3 = dense warp-per-env solver (dex_dynamics.cuh), classes 4-7 = structured solver with
     // eight lanes per env (dex_arrow.cuh) for envs whose Hessian is block-arrowhead plus at most two contacts that join two
     // branches (a low-rank correction), with at most one contact per lane.  Within each kernel the envs with the most contacts go first; envs with equal contact

@@ -22,6 +22,8 @@ struct HostModel {
   int nconmax, iterations, mpr_iterations, nv_euler;
   int k0_rounds, chol_split;
   int arrow_ok, arrow_nmo, arrow_bdof[5][5], arrow_odof[8], arrow_bmask[5], arrow_rowdof[24], arrow_omask;
+  int sp_ok;
+  DexSpConst sp[2];
   double timestep, gravity[3], tolerance, mpr_tolerance, meaninertia, max_margin;
 #define DEX_X_I(name) std::vector<int> name;
 #define DEX_X_R(name) std::vector<double> name;
@@ -262,6 +264,104 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
     unsigned mask = (unsigned)M.body_dofmask[M.body_parent[b]];
     for (int i = 0; i < M.body_dofnum[b]; ++i) mask |= 1u << (M.body_dofadr[b] + i);
     M.body_dofmask[b] = (int)mask;
+  }
+  // ---- elimination forests of the sparse (level-scheduled L^T D L) solver, dex_sparse.cuh.  Structure 0 = the dof
+  //      forest itself (the pattern of M: contact-free envs, implicit-damping Euler of every env).  Structure 1 =
+  //      "chained": the trees without branching (a free object's six dofs) strung into one chain that becomes the
+  //      common ancestor of every branching tree; then H = M + J^T W J keeps the no-fill pattern "a dof couples to its
+  //      ancestors only" for every contact whose dofs lie on one root-to-leaf path (object - finger, object - palm,
+  //      finger - palm; not finger - finger).  TRUNK = the dofs above a branching point (wrist; object + wrist): a chain
+  //      of up to 8 at depths 0 .. nt-1; every other dof has at most one child, so each lane pulls from at most one row
+  //      per step, and the trunk takes the rows below it in one deferred (Schur) update.  Tables: DEX_SPL_* per lane.
+  {
+    M.sp_ok = 1;
+    M.body_augmask.assign(nb, 0);
+    std::vector<int> nchild(nv, 0), branching(M.ntree, 0);
+    for (int i = 0; i < nv; ++i) if (M.dof_parent[i] >= 0) nchild[M.dof_parent[i]]++;
+    for (int i = 0; i < nv; ++i) if (nchild[i] >= 2) branching[M.dof_tree[i]] = 1;
+    std::vector<int> par[2];
+    par[0] = M.dof_parent;
+    par[1] = M.dof_parent;
+    int tail = -1;   // deepest dof of the chain so far
+    for (int i = 0; i < nv; ++i) if (!branching[M.dof_tree[i]]) { if (M.dof_parent[i] < 0) par[1][i] = tail; if (nchild[i] == 0) tail = i; }
+    for (int i = 0; i < nv; ++i) if (branching[M.dof_tree[i]] && M.dof_parent[i] < 0) par[1][i] = tail;
+    M.sp_tab.assign(2 * DEX_SPL_WORDS * 32, 0);
+    for (int s = 0; s < 2 && M.sp_ok; ++s) {
+      const std::vector<int>& P = par[s];
+      DexSpConst& C = M.sp[s];
+      std::memset(&C, 0, sizeof(C));
+      std::vector<int> depth(32, 0), step(32, 255), nch(nv, 0), trunk(nv, 0);
+      int maxd = 0;
+      for (int i = 0; i < nv; ++i) {
+        int d = 0, guard = 0;
+        for (int j = P[i]; j >= 0 && guard < 64; j = P[j], ++guard) ++d;
+        if (guard >= 64) { M.sp_ok = 0; break; }
+        depth[i] = d; maxd = std::max(maxd, d);
+        if (P[i] >= 0) nch[P[i]]++;
+      }
+      if (maxd > DEX_SP_SLOTS || maxd + 1 > 16) M.sp_ok = 0;
+      if (!M.sp_ok) break;
+      for (int i = 0; i < nv; ++i) if (nch[i] >= 2) for (int j = i; j >= 0; j = P[j]) trunk[j] = 1;
+      int nt = 0;
+      for (int i = 0; i < nv; ++i) if (trunk[i]) {
+        nt++;
+        int tc = 0;
+        for (int k = 0; k < nv; ++k) if (P[k] == i && trunk[k]) tc++;
+        if (tc > 1) M.sp_ok = 0;    // two branching points side by side: not a chain
+      }
+      if (nt > 8) M.sp_ok = 0;
+      for (int i = 0; i < nv && M.sp_ok; ++i) if (trunk[i]) { if (depth[i] >= nt) M.sp_ok = 0; else C.trunk[depth[i]] = (unsigned char)i; }
+      auto below_trunk = [&](int i) { for (int j = P[i]; j >= 0; j = P[j]) if (trunk[j]) return true; return false; };
+      int ndef = 0;
+      for (int i = 0; i < nv && M.sp_ok; ++i) if (!trunk[i] && below_trunk(i)) { if (ndef >= 24) { M.sp_ok = 0; break; } C.def[ndef++] = (unsigned char)i; }
+      if (!M.sp_ok) break;
+      C.nstep = maxd + 1; C.nslot = maxd; C.nt = nt; C.ndef = ndef;
+      C.first_trunk_step = nt > 0 ? maxd - (nt - 1) : maxd + 1;
+      for (int i = 0; i < nv; ++i) step[i] = maxd - depth[i];   // deepest dofs first
+      int* T = &M.sp_tab[(size_t)s * DEX_SPL_WORDS * 32];
+      for (int i = 0; i < 32; ++i) {
+        T[DEX_SPL_DEPTH * 32 + i] = depth[i]; T[DEX_SPL_STEP * 32 + i] = step[i];
+        unsigned char anc[16], d0[16];
+        for (int d = 0; d < 16; ++d) { anc[d] = (unsigned char)i; d0[d] = 0xff; }
+        if (i < nv) {
+          int d = depth[i];
+          for (int j = P[i]; j >= 0; j = P[j]) anc[--d] = (unsigned char)j;
+          // the row a lane pulls at each step: its only descendant eliminated then (trunk lanes: trunk descendants only)
+          for (int k = 0; k < nv; ++k) {
+            bool isanc = false;
+            for (int j = P[k]; j >= 0; j = P[j]) if (j == i) isanc = true;
+            if (!isanc || (trunk[i] && !trunk[k])) continue;
+            if (d0[step[k]] != 0xff) M.sp_ok = 0;   // cannot happen: non-trunk dofs have one child at most
+            d0[step[k]] = (unsigned char)k;
+          }
+        }
+        for (int w = 0; w < 4; ++w) {
+          unsigned a = 0, b = 0;
+          for (int q = 0; q < 4; ++q) { a |= (unsigned)anc[4 * w + q] << (8 * q); b |= (unsigned)d0[4 * w + q] << (8 * q); }
+          T[(DEX_SPL_ANC + w) * 32 + i] = (int)a; T[(DEX_SPL_DESC + w) * 32 + i] = (int)b;
+        }
+        // Schur entries (t, j), 0 <= j <= t < nt, dealt to the lanes in order t (t + 1) / 2 + j; entries 32.. are second entries of lanes 0..
+        unsigned sch = 0xffffu;
+        int q = 0;
+        for (int t = 0; t < nt; ++t) for (int j = 0; j <= t; ++j, ++q) {
+          if (q == i) sch = (sch & ~0xffu) | (unsigned)t | ((unsigned)j << 4);
+          if (q == i + 32) sch = (sch & ~0xff00u) | ((unsigned)t << 8) | ((unsigned)j << 12);
+        }
+        T[DEX_SPL_SCHUR * 32 + i] = (int)sch;
+      }
+    }
+    if (!M.sp_ok) { std::memset(M.sp, 0, sizeof(M.sp)); }
+    else {
+      // dofs a contact of body b may touch and still fit structure 1: its own chain of ancestors there
+      const std::vector<int>& P = par[1];
+      for (int b = 1; b < nb; ++b) {
+        unsigned mask = 0;
+        int leaf = -1;   // deepest dof that moves b
+        for (int a = b; a > 0 && leaf < 0; a = M.body_parent[a]) if (M.body_dofnum[a] > 0) leaf = M.body_dofadr[a] + M.body_dofnum[a] - 1;
+        for (int j = leaf; j >= 0; j = P[j]) mask |= 1u << j;
+        M.body_augmask[b] = (int)mask;
+      }
+    }
   }
   // reference body of each tree: the moving body whose origin (at qpos0) minimises the mean squared
   // distance to the tree's moving bodies -> small lever arms in FP32 (MuJoCo uses the subtree COM)

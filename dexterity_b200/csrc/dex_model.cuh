@@ -18,6 +18,24 @@
 #define DEX_CON_STRIDE 8   // words per stored contact: dist, pos(3), normal(3), pair id
 #define DEX_CUBEMAP_WORDS 192  // per mesh geom: 6 x 8 x 8 start vertices for the hill-climbing support, 2 per word
 
+// tables of the sparse solver (dex_sparse.cuh).  Per elimination structure: the warp-uniform part travels in the kernel
+// parameters (DexSpConst), the per-lane part in DevModel::sp_tab as [structure][DEX_SPL_WORDS][32 lanes].
+#define DEX_SP_SLOTS 16
+#define DEX_SPL_DEPTH 0   // slot of the lane's diagonal = number of its ancestors
+#define DEX_SPL_STEP 1    // step at which the lane is eliminated (255: lane beyond nv)
+#define DEX_SPL_ANC 2     // 4 words: ancestor lane per slot, one byte each (own lane as padding)
+#define DEX_SPL_DESC 6    // 4 words: lane whose row this lane pulls at step s, one byte each (0xff: none)
+#define DEX_SPL_SCHUR 10  // the lane's entries of the deferred trunk update: t | j << 4 | t2 << 8 | j2 << 12 (0xf: none)
+#define DEX_SPL_WORDS 11
+struct DexSpConst {
+  int nstep, nslot;          // elimination steps; off-diagonal slots in use (= maximum depth)
+  int nt;                    // trunk dofs (depths 0 .. nt-1)
+  int first_trunk_step;      // the deferred update of the trunk rows runs before this step
+  int ndef;                  // rows below the trunk
+  unsigned char def[24];     // their lanes
+  unsigned char trunk[8];    // lane of the trunk dof at depth d
+};
+
 // per-env status bits (SURVEY.md §5 failure detection: mirrors upstream PhysicsError handling)
 #define DEX_STATUS_BADQACC 1u
 #define DEX_STATUS_CON_OVERFLOW 2u
@@ -53,7 +71,7 @@ enum { DEX_GEOM_PLANE = 0, DEX_GEOM_SPHERE = 2, DEX_GEOM_CAPSULE = 3, DEX_GEOM_B
   X(I, pair_geom1) X(I, pair_geom2) X(I, pair_gg) X(I, pair_condim) X(R, pair_friction) X(R, pair_solref) \
   X(R, pair_solimp) X(R, pair_margin) X(R, pair_gap)                                       \
   X(I, site_body) X(R, site_pos)                                                           \
-  X(I, dof_pidx) X(R, dof_flrow) X(I, arrow_tab)
+  X(I, dof_pidx) X(R, dof_flrow) X(I, arrow_tab) X(I, sp_tab) X(I, body_augmask)
 
 template <typename T>
 struct DevModel {
@@ -73,6 +91,8 @@ struct DevModel {
   int arrow_bmask[5];    // dof bit mask of each branch
   int arrow_omask;       // dof bit mask of the border
   int arrow_rowdof[24];  // dofs that own friction-loss / limit rows (-1 padded), dealt three to a lane in the row view
+  int sp_ok;             // sparse solver tables valid (dex_sparse.cuh)
+  DexSpConst sp[2];      // the two elimination structures (0: dof forest, 1: chained)
   // the same tables as a device array for lane-indexed reads (arrow_tab): [8 lanes][8] = branch dofs 0-4, border dof 5, -, - then [24] rows
 #define DEX_AR_TAB_ROWS 64
 #define DEX_X_I(name) const int* name;
@@ -112,6 +132,7 @@ struct BatchState {
   int order_stride;
   int work_cap;
   T* tree;                        // [nenv][8][32] K0 outputs: cdof rows 0-5, qfrc_smooth row 6, tree reference points row 7
+  int cls_mode;                   // K1c's solver classes: 0 by contact count, 1 dense / structured (dex_arrow.cuh), 2 dense / sparse (dex_sparse.cuh)
   int skip_mode;                  // which envs a launch works on (see dex_env_off): 0 = those with skip == 0, 1 = those being placed (skip >= 2)
   double* time64;                 // optional [nenv][2]: data.time accumulated in double (MuJoCo's own arithmetic), solve-start time of the goal
 };

@@ -106,8 +106,10 @@ int dex_set_tree_kernel(DexBatch* batch, int thread_per_env);
 
 /* Chooses the constraint-solver kernels.  0 = the dense warp-per-env solver for every env; 1 (default) = envs without
  * contacts take the structured eight-lanes-per-env solver (contact-free form), the rest the dense one; 2 = in addition, envs
- * with at most 8 contacts of which at most 2 join two fingers take the structured solver's full form.  All minimise the same
- * cost to the same tolerance. */
+ * with at most 8 contacts of which at most 2 join two fingers take the structured solver's full form; 3 = envs whose contacts
+ * leave the Hessian in the mass matrix's chained no-fill pattern (no contact between two fingers) take the sparse L^T D L form
+ * of the warp-per-env kernel, the rest the dense one (measured slower than mode 1, kept as a cross-check).  All minimise the
+ * same cost to the same tolerance. */
 int dex_set_solver(DexBatch* batch, int mode);
 
 /* Number of this library's kernels launched since batch creation (bench `gpu_launches`). */

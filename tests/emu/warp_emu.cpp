@@ -18,6 +18,7 @@
 #include "../../dexterity_b200/csrc/dex_arrow.cuh"
 #include "../../dexterity_b200/csrc/dex_collide.cuh"
 #include "../../dexterity_b200/csrc/dex_dynamics.cuh"
+#include "../../dexterity_b200/csrc/dex_sparse.cuh"
 #include "../../dexterity_b200/csrc/dex_host_model.h"
 #include "../../dexterity_b200/csrc/dex_task.cuh"
 #include "../../dexterity_b200/csrc/dex_ik.cuh"
@@ -109,6 +110,7 @@ struct EmuModelT {
     dev.k0_rounds = h.k0_rounds; dev.chol_split = h.chol_split; dev.maxdepth = h.maxdepth; dev.nconmax = h.nconmax; dev.iterations = h.iterations; dev.mpr_iterations = h.mpr_iterations; dev.nv_euler = h.nv_euler;
     dev.timestep = (T)h.timestep; dev.timestep_d = h.timestep;
     dev.arrow_ok = h.arrow_ok; dev.arrow_nmo = h.arrow_nmo; dev.arrow_omask = h.arrow_omask;
+    dev.sp_ok = h.sp_ok; dev.sp[0] = h.sp[0]; dev.sp[1] = h.sp[1];
     std::memcpy(dev.arrow_bdof, h.arrow_bdof, sizeof(dev.arrow_bdof)); std::memcpy(dev.arrow_odof, h.arrow_odof, sizeof(dev.arrow_odof));
     std::memcpy(dev.arrow_bmask, h.arrow_bmask, sizeof(dev.arrow_bmask)); std::memcpy(dev.arrow_rowdof, h.arrow_rowdof, sizeof(dev.arrow_rowdof));
     for (int k = 0; k < 3; ++k) dev.gravity[k] = (T)h.gravity[k];
@@ -131,12 +133,23 @@ struct EmuModel {
 // collision stage of one env: broadphase (warp), narrowphase (one plain call per work item),
 // compaction (warp).  The work list is private to the calling worker thread.
 static std::atomic<long> g_arrow_envs{0}, g_dense_envs{0};
+// DEX_EMU_SOLVER: 0 dense only, 1 (default, as in the library) contact-free envs structured (dex_arrow.cuh), 2 also the block-arrowhead envs with contacts,
+// 3 the sparse form of the warp-per-env kernel (dex_sparse.cuh) for classes >= DEX_NCLASS_DENSE
+template <typename T>
+static int emu_solver_mode(const DevModel<T>& m) {
+  const char* ms = getenv("DEX_EMU_SOLVER");
+  int mode = getenv("DEX_EMU_DENSE") ? 0 : (ms ? atoi(ms) : 1);
+  if ((mode == 1 || mode == 2) && !m.arrow_ok) mode = 0;
+  if (mode == 3 && !m.sp_ok) mode = 0;
+  return mode;
+}
 // returns the env's solver class (dex_compact_env): 4-7 = structured solver
 template <typename T>
 static int emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T* smem) {
   std::vector<int> work(DEX_WORK_HDR + 2 * DEX_MAXSLOT, 0);
   BatchState<T> sl = st;
   sl.nwork = work.data(); sl.work = work.data() + DEX_WORK_HDR; sl.work_cap = DEX_MAXSLOT; sl.order = nullptr;
+  sl.cls_mode = emu_solver_mode(m) == 3 ? 2 : (m.arrow_ok ? 1 : 0);
   dex_emu::run_warp([&]() { dex_collide_env<T>(m, sl, env, smem); });
   for (int i = 0; i < work[0]; ++i) dex_narrow_lane<T>(m, sl, work[DEX_WORK_HDR + 2 * i], work[DEX_WORK_HDR + 1 + 2 * i]);  // K1b is thread-per-item
   int cls = -1;
@@ -149,15 +162,14 @@ static int emu_collide(const DevModel<T>& m, const BatchState<T>& st, int env, T
 template <typename T>
 static void emu_solve(const DevModel<T>& m, const BatchState<T>& st, const DynDebug<T>& dbg, int e0, int e1, const int* cls, T* smem,
                       int integrate) {
-  // DEX_EMU_SOLVER: 0 dense only, 1 contact-free envs structured, 2 (default here) also the block-arrowhead envs with contacts
   int quad[4] = {-1, -1, -1, -1}, quadl[4] = {-1, -1, -1, -1};
-  const char* ms = getenv("DEX_EMU_SOLVER");
-  const int mode = !m.arrow_ok || getenv("DEX_EMU_DENSE") || dbg.M || dbg.efc ? 0 : (ms ? atoi(ms) : 2);   // M / efc dumps: dense kernel only, as on the GPU
+  const int mode = dbg.M || dbg.efc ? 0 : emu_solver_mode(m);   // M / efc dumps: dense kernel only, as on the GPU
   bool any = false, anyl = false;
   for (int env = e0; env < e1; ++env) {
     const int c = cls[env - e0];
-    if (mode >= 1 && c == DEX_NCLASS - 1) { quadl[env - e0] = env; anyl = true; g_arrow_envs++; }
-    else if (mode >= 2 && c >= DEX_NCLASS_DENSE) { quad[env - e0] = env; any = true; g_arrow_envs++; }
+    if (mode == 3 && c >= DEX_NCLASS_DENSE) { dex_emu::run_warp([&]() { dex_dynamics_sp_env<T>(m, st, dbg, env, smem, integrate); }); g_arrow_envs++; }
+    else if (mode >= 1 && mode <= 2 && c == DEX_NCLASS - 1) { quadl[env - e0] = env; anyl = true; g_arrow_envs++; }
+    else if (mode == 2 && c >= DEX_NCLASS_DENSE) { quad[env - e0] = env; any = true; g_arrow_envs++; }
     else { dex_emu::run_warp([&]() { dex_dynamics_env<T>(m, st, dbg, env, smem, integrate); }); g_dense_envs++; }
   }
   if (any) dex_emu::run_warp([&]() { dex_arrow_warp<T, true>(m, st, dbg, quad[dex_lane() >> 3], smem, integrate); });
@@ -176,7 +188,7 @@ template <typename T>
 static void emu_run(const DevModel<T>& m, BatchState<T> st, DynDebug<T> dbg, int nsub, int integrate, int do_collide,
                     int do_dynamics, int nthreads) {
   auto work = [&](int lo, int hi) {
-    std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), std::max<int>(DEX_K0_SMEM_T, DEX_K2A_SMEM_T)) + 64);
+    std::vector<T> smem(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), std::max<int>(DEX_K0_SMEM_T, std::max<int>(DEX_K2A_SMEM_T, DEX_K2S_SMEM_T))) + 64);
     BatchState<T> sb = st;
     sb.nenv = hi;   // the 4-env tree warps must not spill into another worker's range
     for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {
@@ -290,7 +302,7 @@ int emu_env_step(void* mp, int dtype, int nenv, void** f, const int64_t* stride,
     st.time64 = (double*)f[DEX_FIELD_TIME64];
     DynDebug<T> dbg = {nullptr, nullptr, nullptr, nullptr, nullptr};
     auto work = [&](int lo, int hi) {
-      std::vector<T> smem(std::max<int>(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T), std::max<int>(DEX_K0_SMEM_T, DEX_K2A_SMEM_T)) + 64);
+      std::vector<T> smem(std::max<int>(std::max<int>(std::max<int>(DEX_K1_SMEM_T, DEX_K2_SMEM_T), DEX_K3_SMEM_T), std::max<int>(DEX_K0_SMEM_T, std::max<int>(DEX_K2A_SMEM_T, DEX_K2S_SMEM_T))) + 64);
       BatchState<T> sb = st;
       sb.nenv = hi;
       for (int e0 = lo; e0 < hi; e0 += DEX_K0_ENVS) {

@@ -86,7 +86,7 @@ def test_structured_solver_forms_match_dense_kernel_and_oracle(reorient_model, e
     cnt = (ctypes.c_long * 2)()
     emu_model.lib.emu_solver_counts.argtypes = [ctypes.POINTER(ctypes.c_long), ctypes.c_int]
     outs = {}
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         monkeypatch.setenv("DEX_EMU_SOLVER", str(mode))
         emu_model.lib.emu_solver_counts(cnt, 1)
         outs[mode] = emu_model.run(st["qpos"], st["qvel"], st["ctrl"], st["warm"], nsub=1, dtype=np.float64)
@@ -95,9 +95,10 @@ def test_structured_solver_forms_match_dense_kernel_and_oracle(reorient_model, e
         if mode == 0: assert cnt[0] == 0
         if mode == 1: assert cnt[0] == (ref["ncon"] == 0).sum()
         if mode == 2: assert cnt[0] >= 0.9 * n and cnt[0] > (~cross).sum() - 8, "cross-contact envs must take the structured solver too"
+        if mode == 3: assert cnt[0] == (~cross).sum(), "the sparse form takes exactly the envs without a finger-finger contact"
         assert (outs[mode]["status"] == 0).all() and (outs[mode]["ncon"] == ref["ncon"]).all()
     scale = np.maximum(1, np.abs(outs[0]["qvel"]).max(axis=1))
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         d = np.abs(outs[mode]["qvel"] - outs[0]["qvel"]).max(axis=1) / scale
         assert d.max() < 1e-10, (mode, d.max())
         assert (outs[mode]["niter"] == outs[0]["niter"]).mean() > 0.98

@@ -192,8 +192,8 @@ def test_kernel_forms_and_env_chunks_agree(setup):
 
 
 def test_solver_kernels_agree(reorient_model):
-    """K2 is three kernels (dexterity_b200.h, dex_set_solver): the dense warp-per-env solver, and the structured
-    eight-lanes-per-env solver in its full and its contact-free form.  Whichever kernel an env is routed to, it minimises the
+    """K2 is four kernels (dexterity_b200.h, dex_set_solver): the dense warp-per-env solver, the structured
+    eight-lanes-per-env solver in its full and its contact-free form, and the sparse L^T D L form of the warp-per-env solver.  Whichever kernel an env is routed to, it minimises the
     same cost to the same tolerance: on 4096 rollout states the modes agree with each other to FP32 rounding (FP64: to
     1e-10) and each is within the north-star tolerance of the oracle; mode 2 must route most envs to the structured kernel."""
     from dexterity_b200 import backend
@@ -205,18 +205,18 @@ def test_solver_kernels_agree(reorient_model):
     stable = statelib.mpr_stable_mask(compiled, states)
     for dtype, tol_modes in ((torch.float64, 1e-10), (torch.float32, 5e-5)):
         outs = {}
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             b = backend.PhysicsBatch(model, n, dtype)
             b.set_solver(mode)
             statelib.upload(b, states)
             launches0 = b.launch_count
             b.step(1)
             torch.cuda.synchronize()
-            assert b.launch_count - launches0 == 5 + mode     # tree, broadphase, narrowphase, compaction, dense solver (+ structured forms)
+            assert b.launch_count - launches0 == 5 + min(mode, 4 - mode)     # tree, broadphase, narrowphase, compaction, dense solver (+ structured / sparse forms)
             assert (b.status.cpu().numpy() & 1 == 0).all()
             outs[mode] = (b.qpos.cpu().numpy().astype(np.float64), b.qvel.cpu().numpy().astype(np.float64), b.niter.cpu().numpy(),
                           b.ncon.cpu().numpy())
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             assert (outs[mode][3] == outs[0][3]).all()
             dv = relerr(outs[mode][1], outs[0][1])
             frac = (dv <= tol_modes).mean()

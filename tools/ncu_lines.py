@@ -8,7 +8,7 @@ tot = collections.Counter(); totsamp = collections.Counter()
 for r in rows:
     if not r: continue
     if r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
-    if r[0] == "Function Name": kern = r[1].split("(")[0].split("::")[-1]; continue
+    if r[0] == "Function Name": kern = r[1].split("(")[0].split("::")[-1] + (r[1].split("(")[0].split(",")[-1] if "," in r[1].split("(")[0] else ""); continue
     if r[0] == "Line No": hdr = r; i_inst = hdr.index("Instructions Executed"); i_samp = hdr.index("# Samples"); continue
     if hdr is None or len(r) < len(hdr): continue
     try:
