@@ -78,6 +78,14 @@ DEX_DEV_NOINLINE V3<T> dex_support_local(const T* vert, int n, int gtype, const 
     }
     dex_warp_argmax(best, bi);
     dex_ldg_xyz(vert + 4 * bi, out.x, out.y, out.z);
+  } else if (gtype == DEX_GEOM_CAPSULE) {  // sphere of the radius plus the half length along the geom's z axis
+    T G[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
+    for (int i = 0; i < 9; ++i) G[i] = dex_ldg(mat + i);
+    rotT_vec(l2, G, ld);
+    const T r = dex_ldg(size), hl = dex_ldg(size + 1);
+    cn[0] = l2[0] * r; cn[1] = l2[1] * r; cn[2] = l2[2] * r + (l2[2] > 0 ? hl : -hl);
+    rot_vec(loc, G, cn);
+    out.x = loc[0] + dex_ldg(pack); out.y = loc[1] + dex_ldg(pack + 1); out.z = loc[2] + dex_ldg(pack + 2);
   } else {  // box
     T G[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
     for (int i = 0; i < 9; ++i) G[i] = dex_ldg(mat + i);
@@ -255,16 +263,21 @@ DEX_DEV void dex_support_lane(const DevModel<T>& m, LaneGeom<T>& G, T lx, T ly, 
       G.last = bi;
     }
     dex_ldg_xyz(G.vert + 4 * bi, out[0], out[1], out[2]);
-  } else {  // box
+  } else {  // box, capsule (mjccd_support: sphere of the radius plus the half length along the geom's z axis)
     const T* mat = m.geom_mat + 9 * G.g;
     const T* size = m.geom_size + 3 * G.g;
     const T* pack = m.geom_pack + DEX_GPACK * G.g;
     T Gm[9], ld[3] = {lx, ly, lz}, l2[3], cn[3], loc[3];
     for (int i = 0; i < 9; ++i) Gm[i] = dex_ldg(mat + i);
     rotT_vec(l2, Gm, ld);
+    if (G.type == DEX_GEOM_CAPSULE) {
+      const T r = dex_ldg(size), hl = dex_ldg(size + 1);
+      cn[0] = l2[0] * r; cn[1] = l2[1] * r; cn[2] = l2[2] * r + (l2[2] > 0 ? hl : -hl);
+    } else {
     cn[0] = l2[0] > 0 ? dex_ldg(size) : -dex_ldg(size);
     cn[1] = l2[1] > 0 ? dex_ldg(size + 1) : -dex_ldg(size + 1);
     cn[2] = l2[2] > 0 ? dex_ldg(size + 2) : -dex_ldg(size + 2);
+    }
     rot_vec(loc, Gm, cn);
     out[0] = loc[0] + dex_ldg(pack); out[1] = loc[1] + dex_ldg(pack + 1); out[2] = loc[2] + dex_ldg(pack + 2);
   }
@@ -516,6 +529,70 @@ DEX_DEV bool dex_obb_overlap(const Xf<T>& rel, const T* pk1, const T* pk2, T mar
   return true;
 }
 
+// mjraw_SphereSphere: contact between two spheres (centres in the world frame); returns whether it exists
+template <typename T>
+DEX_DEV bool dex_sphere_sphere(const T* p1, T r1, const T* p2, T r2, T margin, int pair, T* out) {
+  T dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  const T cdist = dx_sqrt(dot3(dif, dif));
+  const T dist = cdist - r1 - r2;
+  if (dist > margin) return false;
+  T n[3] = {1, 0, 0};
+  if (cdist >= Real<T>::minval()) { n[0] = dif[0] / cdist; n[1] = dif[1] / cdist; n[2] = dif[2] / cdist; }
+  const T a = r1 + T(0.5) * dist;
+  T pos[3] = {p1[0] + n[0] * a, p1[1] + n[1] * a, p1[2] + n[2] * a};
+  dex_store_contact(out, dist, pos, n, pair);
+  return true;
+}
+// mjc_CapsuleCapsule (engine_collision_primitive.c): closest points of the two axis segments, then sphere-sphere there; for
+// parallel axes the four end-point configurations, two contacts at most.  Warp-uniform arithmetic, lane 0 writes the two
+// staging slots at `out` (pair < 0 = no contact).
+template <typename T>
+DEX_DEV void dex_capsule_capsule(const DevModel<T>& m, const T* xpos, const T* xmat, int g1, int g2, T margin, int pair, T* out) {
+  const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
+  T pos1[3], pos2[3], ax1[3], ax2[3];
+  {
+    const T* G1 = m.geom_mat + 9 * g1; const T* G2 = m.geom_mat + 9 * g2;
+    T l1[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 2)};
+    T l2[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g2), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 2)};
+    T z1[3] = {dex_ldg(G1 + 2), dex_ldg(G1 + 5), dex_ldg(G1 + 8)}, z2[3] = {dex_ldg(G2 + 2), dex_ldg(G2 + 5), dex_ldg(G2 + 8)};
+    rot_vec(pos1, xmat + 9 * b1, l1); rot_vec(pos2, xmat + 9 * b2, l2);
+    for (int k = 0; k < 3; ++k) { pos1[k] += xpos[3 * b1 + k]; pos2[k] += xpos[3 * b2 + k]; }
+    rot_vec(ax1, xmat + 9 * b1, z1); rot_vec(ax2, xmat + 9 * b2, z2);
+  }
+  const T r1 = dex_ldg(m.geom_size + 3 * g1), h1 = dex_ldg(m.geom_size + 3 * g1 + 1);
+  const T r2 = dex_ldg(m.geom_size + 3 * g2), h2 = dex_ldg(m.geom_size + 3 * g2 + 1);
+  const T dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  const T ma = dot3(ax1, ax1), mb = -dot3(ax1, ax2), mc = dot3(ax2, ax2);
+  const T u = -dot3(ax1, dif), v = dot3(ax2, dif);
+  const T det = ma * mc - mb * mb;
+  T rec[2][DEX_CON_STRIDE];
+  int n = 0;
+  auto at = [&](T x1, T x2) {
+    T v1[3] = {pos1[0] + ax1[0] * x1, pos1[1] + ax1[1] * x1, pos1[2] + ax1[2] * x1};
+    T v2[3] = {pos2[0] + ax2[0] * x2, pos2[1] + ax2[1] * x2, pos2[2] + ax2[2] * x2};
+    if (n < 2 && dex_sphere_sphere(v1, r1, v2, r2, margin, pair, rec[n])) ++n;
+  };
+  if (dx_abs(det) >= Real<T>::minval()) {   // general configuration
+    T x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > h1) { x1 = h1; x2 = (v - mb * h1) / mc; }
+    else if (x1 < -h1) { x1 = -h1; x2 = (v + mb * h1) / mc; }
+    if (x2 > h2) { x2 = h2; x1 = dx_clamp((u - mb * h2) / ma, -h1, h1); }
+    else if (x2 < -h2) { x2 = -h2; x1 = dx_clamp((u + mb * h2) / ma, -h1, h1); }
+    at(x1, x2);
+  } else {   // parallel axes: each end point of either segment against the other segment
+    at(h1, dx_clamp((v - mb * h1) / mc, -h2, h2));
+    at(-h1, dx_clamp((v + mb * h1) / mc, -h2, h2));
+    if (n < 2) at(dx_clamp((u - mb * h2) / ma, -h1, h1), h2);
+    if (n < 2) at(dx_clamp((u + mb * h2) / ma, -h1, h1), -h2);
+  }
+  if (dex_lane() == 0) {
+    for (int i = 0; i < 2; ++i) {
+      if (i < n) { for (int k = 0; k < DEX_CON_STRIDE; ++k) out[i * DEX_CON_STRIDE + k] = rec[i][k]; }
+      else out[i * DEX_CON_STRIDE + 7] = T(-1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1a body.  smem: [xpos | xmat | geom spheres | body spheres | cand(int) | surviving body pairs(int)]
 // ------------------------------------------------------------------------------------------
@@ -748,6 +825,12 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     const int p = cand[ci];
     const int g1 = dex_ldg(m.pair_geom1 + p), g2 = dex_ldg(m.pair_geom2 + p);
     const int t1 = dex_ldg(m.geom_type + g1), t2 = dex_ldg(m.geom_type + g2);
+    if (t1 == DEX_GEOM_CAPSULE && t2 == DEX_GEOM_CAPSULE) {   // mjc_CapsuleCapsule: closed form, up to two contacts (parallel axes)
+      if (nslot + 2 > DEX_MAXSLOT) { status |= DEX_STATUS_CAND_OVERFLOW; continue; }
+      dex_capsule_capsule<T>(m, xpos, xmat, g1, g2, dex_ldg(m.pair_margin + p), p, stage + nslot * DEX_CON_STRIDE);
+      nslot += 2;
+      continue;
+    }
     if (t1 != DEX_GEOM_PLANE) {
       if (nslot < DEX_MAXSLOT) {
         dex_syncwarp();

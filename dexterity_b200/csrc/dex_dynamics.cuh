@@ -313,19 +313,13 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
 
   // ------------------------------------------------------------------ constraint rows
   // friction loss (lane = dof)
-  T f_loss = 0, f_R = 1, f_D = 0, f_aref = 0;
+  // (state independent up to aref = -B qvel: R f, D = 1 / R and B come precomputed from the host, dof_flrow)
+  T f_loss = 0, f_lim = Real<T>::big(), f_D = 0, f_aref = 0;
   if (isdof) {
     f_loss = dex_ldg(m.dof_frictionloss + lane);
-    if (f_loss > 0) {
-      T si[5], sr[2], imp, K, B;
-      for (int k = 0; k < 5; ++k) si[k] = dex_ldg(m.dof_solimp + 5 * lane + k);
-      sr[0] = dex_ldg(m.dof_solref + 2 * lane); sr[1] = dex_ldg(m.dof_solref + 2 * lane + 1);
-      dex_impedance(si, T(0), T(0), &imp);
-      dex_kb(sr, si, h, &K, &B);
-      f_R = dx_max(Real<T>::minval(), (1 - imp) / imp * dex_ldg(m.dof_invweight0 + lane));
-      f_D = 1 / f_R;
-      f_aref = -B * qv;
-    }
+    T fr[4];
+    dex_ldg4(m.dof_flrow + 4 * lane, fr);
+    if (f_loss > 0) { f_lim = fr[0]; f_D = fr[1]; f_aref = -fr[2] * qv; }
   }
   // joint limit (lane = dof of a limited hinge/slide joint; at most one side active)
   T l_sign = 0, l_D = 0, l_aref = 0;
@@ -384,7 +378,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     const T* cc = cin + c * DEX_CON_STRIDE;
     const int pr = (int)cc[7];
     const int b1 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom1 + pr)), b2 = dex_ldg(m.geom_body + dex_ldg(m.pair_geom2 + pr));
-    const T mu = dex_ldg(m.pair_friction + 5 * pr);
+    const T mu_pair = dex_ldg(m.pair_friction + 5 * pr);
     const T cmargin = dex_ldg(m.pair_margin + pr) - dex_ldg(m.pair_gap + pr);
     T si[5], sr[2], imp, K, B;
     for (int k = 0; k < 5; ++k) si[k] = dex_ldg(m.pair_solimp + 5 * pr + k);
@@ -392,8 +386,12 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     dex_impedance(si, cc[0], cmargin, &imp);
     dex_kb(sr, si, h, &K, &B);
     const T tran = dex_ldg(m.body_invweight0 + 2 * b1) + dex_ldg(m.body_invweight0 + 2 * b2);
+    // condim 1: one frictionless row, R from diagApprox = tran, carried as mu = 0 (the per-contact loops below then take one
+    // row instead of the four pyramid edges); condim 3: pyramid edges n +- mu t1, n +- mu t2 sharing Rpy = 2 mu^2 R0
+    const bool frictionless = dex_ldg(m.pair_condim + pr) == 1;
+    const T mu = frictionless ? T(0) : mu_pair;
     const T R0 = dx_max(Real<T>::minval(), (1 - imp) / imp * (tran + mu * mu * tran));
-    const T Rpy = 2 * mu * mu * R0;
+    const T Rpy = frictionless ? R0 : 2 * mu * mu * R0;
     T* cdt = cdat + c * DEX_CDAT_STRIDE;
     cdt[CD_MU] = mu;
     cdt[CD_D] = 1 / Rpy;
@@ -438,9 +436,9 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     T mycost = T(0.5) * qacc * Ma - qacc * fs, fdof = 0, hdiag = 0;
     int asig = 0;
     {
-      const T x = qacc - f_aref, lim = f_R * f_loss;
+      const T x = qacc - f_aref, lim = f_lim;
       const bool on = f_loss > 0, lo = x <= -lim, hi = x >= lim;
-      const T c = lo ? f_loss * (T(-0.5) * f_R * f_loss - x) : (hi ? f_loss * (T(-0.5) * f_R * f_loss + x) : T(0.5) * f_D * x * x);
+      const T c = lo ? f_loss * (T(-0.5) * f_lim - x) : (hi ? f_loss * (T(-0.5) * f_lim + x) : T(0.5) * f_D * x * x);
       const T f = lo ? f_loss : (hi ? -f_loss : -(f_D * x));
       mycost += on ? c : T(0); fdof += on ? f : T(0); hdiag += (on && !lo && !hi) ? f_D : T(0);
     }
@@ -453,9 +451,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       T* cdt = cdat + lane * DEX_CDAT_STRIDE;
       const T D = cdt[CD_D], mu = cdt[CD_MU];
       T f[4], w[4];
+      const int nrow = mu == 0 ? 1 : 4;
       for (int r = 0; r < 4; ++r) {
         const T x = cdt[CD_JAR + r];
-        const bool on = x < 0;   // pyramid edge active
+        const bool on = x < 0 && r < nrow;   // pyramid edge active
         f[r] = on ? -D * x : T(0); w[r] = on ? D : T(0); mycost += on ? T(0.5) * D * x * x : T(0); asig |= on ? 1 << r : 0;
       }
       cdt[CD_F + 0] = f[0] + f[1] + f[2] + f[3];
@@ -539,7 +538,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     for (int ls = 1; ls < 24 && g0 < 0; ++ls) {
       T g = q1 + alpha * q2, hh = q2;
       {  // friction loss and limit rows, branch-free (same regimes as in the force update above)
-        const T x = qacc + alpha * search - f_aref, lim = f_R * f_loss;
+        const T x = qacc + alpha * search - f_aref, lim = f_lim;
         const bool on = f_loss > 0, lo = x <= -lim, hi = x >= lim;
         const T dg = lo ? -(f_loss * search) : (hi ? f_loss * search : f_D * x * search);
         g += on ? dg : T(0); hh += (on && !lo && !hi) ? f_D * search * search : T(0);
@@ -550,9 +549,10 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       if (lane < ncon) {
         const T* cdt = cdat + lane * DEX_CDAT_STRIDE;
         const T D = cdt[CD_D];
+        const int nrow = cdt[CD_MU] == 0 ? 1 : 4;
         for (int r = 0; r < 4; ++r) {
           const T jv = cdt[CD_JV + r], x = cdt[CD_JAR + r] + alpha * jv;
-          const bool on = x < 0;
+          const bool on = x < 0 && r < nrow;
           g += on ? D * x * jv : T(0); hh += on ? D * jv * jv : T(0);
         }
       }

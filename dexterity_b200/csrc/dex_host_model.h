@@ -515,6 +515,14 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
           for (int k = 0; k < 3; ++k) p[k] = M.geom_pos[3 * g + k] + G[3 * k] * l[0] + G[3 * k + 1] * l[1] + G[3 * k + 2] * l[2];
           grow(p);
         }
+      } else if (M.geom_type[g] == DEX_GEOM_CAPSULE || M.geom_type[g] == DEX_GEOM_SPHERE) {
+        const double* G = &M.geom_mat[9 * g];
+        const double r = M.geom_size[3 * g], hl = M.geom_type[g] == DEX_GEOM_CAPSULE ? M.geom_size[3 * g + 1] : 0.0;
+        for (int sgn = -1; sgn <= 1; sgn += 2) for (int c = 0; c < 8; ++c) {   // boxes around the two end spheres
+          double p[3];
+          for (int k = 0; k < 3; ++k) p[k] = M.geom_pos[3 * g + k] + sgn * hl * G[3 * k + 2] + ((c >> k) & 1 ? r : -r);
+          grow(p);
+        }
       } else { for (int k = 0; k < 3; ++k) { lo[k] = -1e30; hi[k] = 1e30; } }
       for (int k = 0; k < 3; ++k) { M.geom_aabb[6 * g + k] = 0.5 * (lo[k] + hi[k]); M.geom_aabb[6 * g + 3 + k] = 0.5 * (hi[k] - lo[k]); }
     }
@@ -571,10 +579,13 @@ inline std::string build(const void* blob, uint64_t nbytes, HostModel& M) {
   {
     double maxmargin = 0;
     for (int p = 0; p < M.npair; ++p) {
-      if (M.pair_condim[p] != 3) return "only condim-3 contact pairs are supported yet";
+      if (M.pair_condim[p] != 3 && M.pair_condim[p] != 1) return "only condim-1 and condim-3 contact pairs are supported yet";
+      if (M.pair_condim[p] != 3) { M.arrow_ok = 0; M.sp_ok = 0; }   // the structured / sparse solver forms know pyramidal contacts only
       int t1 = M.geom_type[M.pair_geom1[p]], t2 = M.geom_type[M.pair_geom2[p]];
-      bool okp = (t1 == DEX_GEOM_PLANE && (t2 == DEX_GEOM_BOX || t2 == DEX_GEOM_MESH)) ||
-                 ((t1 == DEX_GEOM_BOX || t1 == DEX_GEOM_MESH) && t2 == DEX_GEOM_MESH);
+      // narrowphases: plane-box, plane-mesh, capsule-capsule (closed forms); any two of capsule / box / mesh through MPR
+      // (geoms of a pair are ordered by type, mj_collideGeoms)
+      auto convex = [](int t) { return t == DEX_GEOM_CAPSULE || t == DEX_GEOM_BOX || t == DEX_GEOM_MESH; };
+      bool okp = (t1 == DEX_GEOM_PLANE && (t2 == DEX_GEOM_BOX || t2 == DEX_GEOM_MESH)) || (convex(t1) && convex(t2) && t1 <= t2 && !(t1 == DEX_GEOM_BOX && t2 == DEX_GEOM_BOX));
       if (!okp) return "unsupported geom pair type";
       maxmargin = std::max(maxmargin, M.pair_margin[p]);
       int a = M.geom_body[M.pair_geom1[p]], b = M.geom_body[M.pair_geom2[p]];

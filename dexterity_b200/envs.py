@@ -104,14 +104,18 @@ class BatchedGoalEnvironment:
     def __init__(self, task_name: str, num_envs: int, seed: Optional[int] = None, device: int = 0,
                  dtype: torch.dtype = torch.float32, time_limit: Optional[float] = None,
                  fall_termination: bool = True, dense_reward: bool = True, prop_spawn_bbox=None,
-                 place_max_attempts: Optional[int] = None) -> None:
-        """`prop_spawn_bbox` = (lower, upper) overrides the reference's spawn box (reorient.py:72-78).
+                 place_max_attempts: Optional[int] = None, hand: str = "shadow_hand_e") -> None:
+        """`hand`: "shadow_hand_e" or (reach only) "adroit_hand", the hand of the reference's registered reach task.
+        `prop_spawn_bbox` = (lower, upper) overrides the reference's spawn box (reorient.py:72-78).
         `place_max_attempts`: draws of the collision-checked prop placement (PropPlacer); None = decide from a static
         clearance proof of the spawn box (dexterity_b200/placement.py): 0 when no draw can collide, else 20."""
         if task_name not in ("reorient", "reach"):
             raise ValueError(f"Unknown task: {task_name}")
-        self.task_name = task_name
-        self.compiled = scenes.load_compiled("reorient_shadow" if task_name == "reorient" else "reach_shadow")
+        if hand not in scenes.HANDS or (task_name == "reorient" and hand != "shadow_hand_e"):
+            raise ValueError(f"Unknown hand for {task_name}: {hand}")
+        self.task_name, self.hand_name = task_name, hand
+        self.compiled = scenes.load_compiled({("reorient", "shadow_hand_e"): "reorient_shadow", ("reach", "shadow_hand_e"): "reach_shadow",
+                                              ("reach", "adroit_hand"): "reach_adroit"}[(task_name, hand)])
         c = self.compiled
         self.model = backend.PhysicsModel(c, device)
         self.physics = backend.PhysicsBatch(self.model, num_envs, dtype)
@@ -143,8 +147,8 @@ class BatchedGoalEnvironment:
         backend._check(backend.lib().dex_bind(self.physics.ptr, 26, ctypes.c_void_p(self._skip.data_ptr()), 1))
 
         # task description
-        hand_prefix = "shadow_hand_e"
-        sites = [c.site_names.index(f"{hand_prefix}/{t}_site") for t in scenes.SHADOW_FINGERTIPS]
+        hand_prefix = hand
+        sites = [c.site_names.index(f"{hand_prefix}/{t}") for t in scenes.HANDS[hand][2]]
         nhand = sum(1 for j in c.joint_names if j.startswith(hand_prefix + "/"))
         p = TaskParams()
         p.task = 0 if task_name == "reorient" else 1
@@ -279,10 +283,10 @@ class ReachEnvironment(BatchedGoalEnvironment):
     _INIT_JOINT_RANGE_FRACTION = 0.5     # reach.py:45
 
     def __init__(self, num_envs: int, seed=None, device: int = 0, dtype: torch.dtype = torch.float32,
-                 time_limit=None, dense_reward: bool = True) -> None:
-        super().__init__("reach", num_envs, seed, device, dtype, time_limit, dense_reward=dense_reward)
+                 time_limit=None, dense_reward: bool = True, hand: str = "adroit_hand") -> None:
+        super().__init__("reach", num_envs, seed, device, dtype, time_limit, dense_reward=dense_reward, hand=hand)
         from dexterity_b200 import goals, hands
-        self.hand = hands.DexterousHand(self.compiled)
+        self.hand = hands.DexterousHand(self.compiled, prefix=scenes.HANDS[hand][1], fingertip_sites=scenes.HANDS[hand][2])
         self.goal_generator = goals.FingertipCartesianPosition(self.hand, self.model)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(self.seed)
@@ -294,7 +298,7 @@ class ReachEnvironment(BatchedGoalEnvironment):
         """Fingertip site world positions [n, 15] at the physics' current qpos, from the observation
         refresh kernel when `physics` is this env's own batch, else via a scratch forward pass."""
         if physics is None or physics is self.physics:
-            return self._obs[:, self.obs_layout["shadow_hand_e/fingertip_positions"]]
+            return self._obs[:, self.obs_layout[f"{self.hand_name}/fingertip_positions"]]
         return _fk_sites(self.compiled, self.hand, physics)
 
     def _phase(self, phases: int, force_reset: int = 0) -> None:
@@ -395,8 +399,11 @@ def _fk_sites(compiled, hand, physics) -> torch.Tensor:
 
 def load(domain_name: str, task_name: str = "state_dense", seed: Optional[int] = None,
          strip_singleton_obs_buffer_dim: bool = True, time_limit: Optional[float] = None,
-         num_envs: int = 1, device: int = 0, dtype: torch.dtype = torch.float32) -> BatchedGoalEnvironment:
-    """Batched counterpart of reference `manipulation.load` (same leading arguments)."""
+         num_envs: int = 1, device: int = 0, dtype: torch.dtype = torch.float32,
+         hand: Optional[str] = None) -> BatchedGoalEnvironment:
+    """Batched counterpart of reference `manipulation.load` (same leading arguments).  `hand` defaults to the hand of the
+    reference's registered task: the Shadow hand for reorient (reorient.py:324-364), the Adroit hand for reach
+    (reach.py:223-249); `hand="shadow_hand_e"` gives the Shadow-hand reach of BASELINE.json configs[0..1]."""
     del strip_singleton_obs_buffer_dim
     tasks = {"reorient": ("state_dense",), "reach": ("state_dense", "state_sparse")}
     if domain_name not in tasks:
@@ -404,5 +411,6 @@ def load(domain_name: str, task_name: str = "state_dense", seed: Optional[int] =
     if task_name not in tasks[domain_name]:
         raise ValueError(f"Unknown task: {task_name}")
     if domain_name == "reach":
-        return ReachEnvironment(num_envs, seed, device, dtype, time_limit, dense_reward=(task_name == "state_dense"))
-    return BatchedGoalEnvironment(domain_name, num_envs, seed, device, dtype, time_limit)
+        return ReachEnvironment(num_envs, seed, device, dtype, time_limit, dense_reward=(task_name == "state_dense"),
+                                hand=hand or "adroit_hand")
+    return BatchedGoalEnvironment(domain_name, num_envs, seed, device, dtype, time_limit, hand=hand or "shadow_hand_e")

@@ -109,6 +109,22 @@ def reach_shadow_scene() -> compile_lib.CompiledModel:
     return compile_lib.compile_model(model, **kw)
 
 
+def reach_adroit_assembly():
+    """The REGISTERED reach task's scene (reference manipulation/tasks/reach.py:223-269 with `AdroitHand`,
+    models/hands/adroit_hand.py:12-29): Standard arena with the ground's collisions disabled, the Adroit hand attached at
+    its palm-upright pose.  The hand's collision geoms have conaffinity 0 (adroit_hand.xml:29-31), so the only contacts are
+    its 18 distinct explicit `<contact><pair condim="1">` elements (:231-251): 17 capsule-capsule, 1 capsule-box."""
+    scene = _standard_arena(ground_collides=False)
+    hand = mjcf.load(_paths()["adroit"], name="adroit_hand", base_defaults=scene.root_defaults)
+    scene.attach(hand, pos=SHADOW_PALM_UPRIGHT_POS, quat=SHADOW_PALM_UPRIGHT_QUAT)   # adroit_hand.py:12-13: the same pose
+    return scene.model, dict(timestep=REACH_PHYSICS_TIMESTEP, nconmax=48, xfrc_gravcomp_prefix="adroit_hand/")
+
+
+def reach_adroit_scene() -> compile_lib.CompiledModel:
+    model, kw = reach_adroit_assembly()
+    return compile_lib.compile_model(model, **kw)
+
+
 def shadow_hand_only() -> compile_lib.CompiledModel:
     """The hand's own root model (no arena, no attachment offset): IKSolver's physics."""
     scene = mjcf.Scene(mjcf.Model("ik", mjcf.Body("world", np.zeros(3), np.array([1.0, 0, 0, 0]), None),
@@ -153,12 +169,13 @@ def adroit_hand_only() -> compile_lib.CompiledModel:
 _BUILDERS = {
     "reorient_shadow": reorient_scene,
     "reach_shadow": reach_shadow_scene,
+    "reach_adroit": reach_adroit_scene,
     "shadow_hand_only": shadow_hand_only,
     "adroit_hand_only": adroit_hand_only,
 }
 
 # scenes whose assembled MJCF can be exported (dexterity_b200/model/export.py, tools/export_task.py)
-ASSEMBLIES = {"reorient_shadow": reorient_assembly, "reach_shadow": reach_shadow_assembly}
+ASSEMBLIES = {"reorient_shadow": reorient_assembly, "reach_shadow": reach_shadow_assembly, "reach_adroit": reach_adroit_assembly}
 
 # hand name -> (hand-only compiled model, name prefix, fingertip site names)
 HANDS = {

@@ -797,6 +797,52 @@ int convex_convex(const Data& d, int g1, int g2, R margin, Contact* con) {  // m
   return 1;
 }
 
+// mjraw_SphereSphere [upstream engine_collision_primitive.c]
+int sphere_sphere(const R* p1, R r1, const R* p2, R r2, R margin, Contact* con) {
+  R dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  R cdist = norm3(dif);
+  if (cdist - r1 - r2 > margin) return 0;
+  con->dist = cdist - r1 - r2;
+  R n[3] = {1, 0, 0};
+  if (cdist >= MINVAL) for (int k = 0; k < 3; k++) n[k] = dif[k] / cdist;
+  for (int k = 0; k < 3; k++) { con->frame[k] = n[k]; con->frame[3 + k] = 0; con->pos[k] = p1[k] + n[k] * (r1 + 0.5 * con->dist); }
+  return 1;
+}
+// mjc_CapsuleCapsule [upstream engine_collision_primitive.c]: closest points of the two axis segments (2 x 2 system in the
+// segment parameters, clamped), then sphere-sphere; parallel axes: the end points of each segment against the other, two
+// contacts at most.  Used by the Adroit hand's explicit <contact><pair>s (adroit_hand.xml:231-251).
+int capsule_capsule(const Data& d, int g1, int g2, R margin, Contact* con) {
+  const Model& m = *d.m;
+  const R *pos1 = &d.geom_xpos[3 * g1], *pos2 = &d.geom_xpos[3 * g2], *mat1 = &d.geom_xmat[9 * g1], *mat2 = &d.geom_xmat[9 * g2];
+  const R *size1 = m.F(DEXF_GEOM_SIZE) + 3 * g1, *size2 = m.F(DEXF_GEOM_SIZE) + 3 * g2;
+  R ax1[3] = {mat1[2], mat1[5], mat1[8]}, ax2[3] = {mat2[2], mat2[5], mat2[8]};
+  R dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  R ma = dot3(ax1, ax1), mb = -dot3(ax1, ax2), mc = dot3(ax2, ax2);
+  R u = -dot3(ax1, dif), v = dot3(ax2, dif);
+  R det = ma * mc - mb * mb;
+  auto clip = [](R x, R lo, R hi) { return std::min(std::max(x, lo), hi); };
+  int n = 0;
+  auto at = [&](R x1, R x2) {
+    R v1[3], v2[3];
+    for (int k = 0; k < 3; k++) { v1[k] = pos1[k] + ax1[k] * x1; v2[k] = pos2[k] + ax2[k] * x2; }
+    if (n < 2) n += sphere_sphere(v1, size1[0], v2, size2[0], margin, con + n);
+  };
+  if (std::fabs(det) >= MINVAL) {
+    R x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > size1[1]) { x1 = size1[1]; x2 = (v - mb * size1[1]) / mc; }
+    else if (x1 < -size1[1]) { x1 = -size1[1]; x2 = (v + mb * size1[1]) / mc; }
+    if (x2 > size2[1]) { x2 = size2[1]; x1 = clip((u - mb * size2[1]) / ma, -size1[1], size1[1]); }
+    else if (x2 < -size2[1]) { x2 = -size2[1]; x1 = clip((u + mb * size2[1]) / ma, -size1[1], size1[1]); }
+    at(x1, x2);
+  } else {
+    at(size1[1], clip((v - mb * size1[1]) / mc, -size2[1], size2[1]));
+    at(-size1[1], clip((v + mb * size1[1]) / mc, -size2[1], size2[1]));
+    if (n < 2) at(clip((u - mb * size2[1]) / ma, -size1[1], size1[1]), size2[1]);
+    if (n < 2) at(clip((u + mb * size2[1]) / ma, -size1[1], size1[1]), -size2[1]);
+  }
+  return n;
+}
+
 void make_frame(R* f) {  // mju_makeFrame
   normalize3(f);
   if (norm3(f + 3) < 0.5) {
@@ -835,7 +881,11 @@ void collision(Data& d) {
     int n = 0;
     if (gtype[g1] == 0 && gtype[g2] == 6) n = plane_box(d, g1, g2, margin, con);
     else if (gtype[g1] == 0 && gtype[g2] == 7) n = plane_convex(d, g1, g2, margin, con);
-    else if ((gtype[g1] == 6 || gtype[g1] == 7) && gtype[g2] == 7) n = convex_convex(d, g1, g2, margin, con);
+    else if (gtype[g1] == 3 && gtype[g2] == 3) n = capsule_capsule(d, g1, g2, margin, con);
+    // capsule-box goes through MPR here AND in the kernels: upstream has a closed form (mjc_CapsuleBox, up to two contacts) that
+    // this restatement does not reproduce; one of the Adroit hand's 19 pairs (C_palm0 - C_thdistal) is of this type
+    else if ((gtype[g1] == 3 || gtype[g1] == 6 || gtype[g1] == 7) && (gtype[g2] == 6 || gtype[g2] == 7) && !(gtype[g1] == 6 && gtype[g2] == 6))
+      n = convex_convex(d, g1, g2, margin, con);
     else continue;  // pair type not used by the compiled scenes
     for (int i = 0; i < n; i++) {
       Contact& c = con[i];

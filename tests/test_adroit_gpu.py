@@ -45,3 +45,54 @@ def test_adroit_dynamics_match_oracle_gpu():
             x = getattr(b, name).cpu().numpy().astype(np.float64)[:, :r.shape[1]]
             rel = np.abs(x - r).max(axis=1) / np.maximum(1.0, np.abs(r).max(axis=1))
             assert rel.max() <= tol, (dtype, name, rel.max())
+
+
+def test_reach_adroit_contacts_match_oracle_gpu():
+    """The registered reach scene on the GPU: capsule-capsule (closed form) and capsule-box (MPR) contacts of the hand's explicit
+    condim-1 pairs, one frictionless row per contact: contact counts equal, single-step state within the north-star tolerance."""
+    from dexterity_b200 import backend
+    from dexterity_b200.model import scenes
+    from tests.test_adroit_cpu import reach_adroit_states
+    c = scenes.load_compiled("reach_adroit")
+    model = backend.PhysicsModel(c, 0)
+    for thumb, seed in ((False, 5), (True, 6)):
+        st = reach_adroit_states(c, seed, 1024, thumb_on_palm=thumb)
+        ref = statelib.oracle_step(c, st, nsub=1)
+        assert (ref["ncon"] > 0).mean() > 0.5
+        for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 1e-4)):
+            b = backend.PhysicsBatch(model, 1024, dtype)
+            statelib.upload(b, st)
+            b.step(1)
+            torch.cuda.synchronize()
+            assert (b.status.cpu().numpy() == 0).all()
+            same = b.ncon.cpu().numpy() == ref["ncon"]
+            assert same.mean() >= (1.0 if dtype == torch.float64 else 0.995), same.mean()
+            v = b.qvel.cpu().numpy().astype(np.float64)
+            rel = np.abs(v - ref["qvel"]).max(axis=1) / np.maximum(1.0, np.abs(ref["qvel"]).max(axis=1))
+            print(f"reach_adroit thumb={thumb} {dtype}: median {np.median(rel):.2e} max {rel.max():.2e} share <= tol {(rel <= tol).mean():.4f}")
+            assert (rel[same] <= tol).mean() >= (1.0 if dtype == torch.float64 else 0.99), (dtype, rel.max())
+
+
+def test_registered_reach_is_the_adroit_hand():
+    """`load("reach", ...)` without a hand builds the reference's registered task (reach.py:223-269: AdroitHand): 24 actuators,
+    117 observation floats, and the behaviour reach_test.py:12-35 checks: sparse reward -1 away from the goal, 0 once the
+    position-controlled hand (ctrl = goal qpos, adroit_hand.py:104-111) has reached it."""
+    from dexterity_b200 import envs
+    env = envs.load("reach", "state_sparse", seed=12345, num_envs=64)
+    assert env.hand_name == "adroit_hand" and env.action_spec().shape == (24,)
+    assert not env.hand.underactuated
+    ts = env.reset()
+    torch.cuda.synchronize()
+    assert (ts.step_type == 0).all()
+    assert sum(s.shape[0] for s in env.observation_spec().values()) == 117
+    g = env.goal[:, :15]
+    assert torch.isfinite(g).all() and (g.reshape(-1, 5, 3).norm(dim=-1) < 0.6).all()
+    ts = env.step(torch.zeros(64, 24, device=env.device))
+    far = env.goal_distance.min(dim=1).values > 0.01          # every fingertip further than the success threshold
+    assert far.any() and (ts.reward[far] == -1.0).all()
+    reached = torch.zeros(64, dtype=torch.bool, device=env.device)
+    for _ in range(150):
+        ts = env.step(env.hand.joint_positions_to_control(env.goal_qpos))
+        reached |= (env.successes > 0) & (ts.reward == 0.0)
+    assert (env.physics.status == 0).all()
+    assert reached.float().mean() > 0.7, reached.float().mean()

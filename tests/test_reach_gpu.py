@@ -46,7 +46,7 @@ def test_reach_dense_reward_matches_tanh_squared():
     goal distances the step reports; tanh^2 at the margin is the reference's loss_at_margin = 0.95."""
     from dexterity_b200 import envs
     from oracle import task_oracle
-    env = envs.load("reach", "state_dense", seed=321, num_envs=256)
+    env = envs.load("reach", "state_dense", seed=321, num_envs=256, hand="shadow_hand_e")
     env.reset()
     ts = env.step(torch.zeros(256, 20, device=env.device))
     torch.cuda.synchronize()
@@ -63,7 +63,7 @@ def test_reach_dense_reward_matches_tanh_squared():
 
 def test_reach_behaviour_like_reference():
     from dexterity_b200 import envs
-    env = envs.load("reach", "state_sparse", seed=12345, num_envs=64)
+    env = envs.load("reach", "state_sparse", seed=12345, num_envs=64, hand="shadow_hand_e")
     ts = env.reset()
     torch.cuda.synchronize()
     assert (ts.step_type == 0).all()

@@ -5,7 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dexterity_b200.model import scenes
 
-for name in ("reorient_shadow", "reach_shadow", "shadow_hand_only", "adroit_hand_only"):
+for name in ("reorient_shadow", "reach_shadow", "reach_adroit", "shadow_hand_only", "adroit_hand_only"):
     m = scenes.load_compiled(name, rebuild=True)
     print(name, dict(nbody=m.nbody, nq=m.nq, nv=m.nv, nu=m.nu, ngeom=m.ngeom, npair=m.npair, nsite=m.nsite),
           os.path.getsize(os.path.join(scenes.ASSET_DIR, name + ".npz")), "bytes")

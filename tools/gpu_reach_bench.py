@@ -21,7 +21,7 @@ while time.perf_counter() - t0 < 5.0:
 print("config 0: reach, 1 env, 1 host core, FP64 restatement (not MuJoCo): %.0f env-steps/s (1 mj_step each)" % (n / (time.perf_counter() - t0)))
 
 N = 4096
-env = envs.load("reach", "state_dense", seed=12345, num_envs=N)
+env = envs.load("reach", "state_dense", seed=12345, num_envs=N, hand=os.environ.get("HAND", "shadow_hand_e"))
 spec = env.action_spec()
 lo_t = torch.as_tensor(spec.minimum, device=env.device); hi_t = torch.as_tensor(spec.maximum, device=env.device)
 env.reset()
