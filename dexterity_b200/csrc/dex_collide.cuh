@@ -669,7 +669,9 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
       bool pass = false;
       if (bp < m.nbodypair) {
         const int b1 = b1s[q], b2 = b2s[q];
-        const T r1 = bsph[4 * b1 + 3], r2 = bsph[4 * b2 + 3];
+        T s1[4], s2[4];
+        dex_ld4(bsph + 4 * b1, s1); dex_ld4(bsph + 4 * b2, s2);
+        const T r1 = s1[3], r2 = s2[3];
         if (r1 < 0) {  // body 1 owns a plane (planes sort first in a pair): half-space test of body 2's sphere
           const int gp = dex_ldg(m.pair_geom1 + dex_ldg(m.bp_pairadr + bp));
           const T* G = m.geom_mat + 9 * gp;
@@ -678,7 +680,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
           T d[3] = {bsph[4 * b2] - gsph[4 * gp], bsph[4 * b2 + 1] - gsph[4 * gp + 1], bsph[4 * b2 + 2] - gsph[4 * gp + 2]};
           pass = dot3(d, n) <= r2 + slack;
         } else {
-          T d[3] = {bsph[4 * b2] - bsph[4 * b1], bsph[4 * b2 + 1] - bsph[4 * b1 + 1], bsph[4 * b2 + 2] - bsph[4 * b1 + 2]};
+          T d[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
           const T bound = r1 + r2 + slack;
           pass = dot3(d, d) <= bound * bound;
         }
@@ -748,15 +750,17 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
         ok[q] = false;
         if (p0 + 32 * q + lane < num) {
           const int g1 = gg[q] & 0xffff, g2 = gg[q] >> 16;
-          T d[3] = {gsph[4 * g2] - gsph[4 * g1], gsph[4 * g2 + 1] - gsph[4 * g1 + 1], gsph[4 * g2 + 2] - gsph[4 * g1 + 2]};
-          const T r2 = gsph[4 * g2 + 3];
+          T s1[4], s2[4];   // one 16-byte shared-memory load per sphere
+          dex_ld4(gsph + 4 * g1, s1); dex_ld4(gsph + 4 * g2, s2);
+          T d[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
+          const T r2 = s2[3];
           if (plane && dex_ldg(m.geom_type + g1) == DEX_GEOM_PLANE) {
             const T* G = m.geom_mat + 9 * g1;
             T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
             rot_vec(n, xmat + 9 * b1, nl);
             ok[q] = dot3(d, n) <= mg[q] + r2 + slack;
           } else {
-            const T bound = mg[q] + gsph[4 * g1 + 3] + r2 + slack;
+            const T bound = mg[q] + s1[3] + r2 + slack;
             ok[q] = dot3(d, d) <= bound * bound;
           }
         }
