@@ -546,21 +546,24 @@ DEX_DEV bool dex_sphere_sphere(const T* p1, T r1, const T* p2, T r2, T margin, i
 // mjc_CapsuleCapsule (engine_collision_primitive.c): closest points of the two axis segments, then sphere-sphere there; for
 // parallel axes the four end-point configurations, two contacts at most.  Warp-uniform arithmetic, lane 0 writes the two
 // staging slots at `out` (pair < 0 = no contact).
+// Not inlined (it is off the reorient scenes' path and K1a is sensitive to its code size); the model tables come as plain
+// pointers so that the callee never takes the address of the kernel's constant-bank model.
 template <typename T>
-DEX_DEV void dex_capsule_capsule(const DevModel<T>& m, const T* xpos, const T* xmat, int g1, int g2, T margin, int pair, T* out) {
-  const int b1 = dex_ldg(m.geom_body + g1), b2 = dex_ldg(m.geom_body + g2);
+DEX_DEV_NOINLINE void dex_capsule_capsule(const int* geom_body, const T* geom_mat, const T* geom_pack, const T* geom_size, const T* xpos,
+                                          const T* xmat, int g1, int g2, T margin, int pair, T* out) {
+  const int b1 = dex_ldg(geom_body + g1), b2 = dex_ldg(geom_body + g2);
   T pos1[3], pos2[3], ax1[3], ax2[3];
   {
-    const T* G1 = m.geom_mat + 9 * g1; const T* G2 = m.geom_mat + 9 * g2;
-    T l1[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g1 + 2)};
-    T l2[3] = {dex_ldg(m.geom_pack + DEX_GPACK * g2), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 1), dex_ldg(m.geom_pack + DEX_GPACK * g2 + 2)};
+    const T* G1 = geom_mat + 9 * g1; const T* G2 = geom_mat + 9 * g2;
+    T l1[3] = {dex_ldg(geom_pack + DEX_GPACK * g1), dex_ldg(geom_pack + DEX_GPACK * g1 + 1), dex_ldg(geom_pack + DEX_GPACK * g1 + 2)};
+    T l2[3] = {dex_ldg(geom_pack + DEX_GPACK * g2), dex_ldg(geom_pack + DEX_GPACK * g2 + 1), dex_ldg(geom_pack + DEX_GPACK * g2 + 2)};
     T z1[3] = {dex_ldg(G1 + 2), dex_ldg(G1 + 5), dex_ldg(G1 + 8)}, z2[3] = {dex_ldg(G2 + 2), dex_ldg(G2 + 5), dex_ldg(G2 + 8)};
     rot_vec(pos1, xmat + 9 * b1, l1); rot_vec(pos2, xmat + 9 * b2, l2);
     for (int k = 0; k < 3; ++k) { pos1[k] += xpos[3 * b1 + k]; pos2[k] += xpos[3 * b2 + k]; }
     rot_vec(ax1, xmat + 9 * b1, z1); rot_vec(ax2, xmat + 9 * b2, z2);
   }
-  const T r1 = dex_ldg(m.geom_size + 3 * g1), h1 = dex_ldg(m.geom_size + 3 * g1 + 1);
-  const T r2 = dex_ldg(m.geom_size + 3 * g2), h2 = dex_ldg(m.geom_size + 3 * g2 + 1);
+  const T r1 = dex_ldg(geom_size + 3 * g1), h1 = dex_ldg(geom_size + 3 * g1 + 1);
+  const T r2 = dex_ldg(geom_size + 3 * g2), h2 = dex_ldg(geom_size + 3 * g2 + 1);
   const T dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
   const T ma = dot3(ax1, ax1), mb = -dot3(ax1, ax2), mc = dot3(ax2, ax2);
   const T u = -dot3(ax1, dif), v = dot3(ax2, dif);
@@ -669,9 +672,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
       bool pass = false;
       if (bp < m.nbodypair) {
         const int b1 = b1s[q], b2 = b2s[q];
-        T s1[4], s2[4];
-        dex_ld4(bsph + 4 * b1, s1); dex_ld4(bsph + 4 * b2, s2);
-        const T r1 = s1[3], r2 = s2[3];
+        const T r1 = bsph[4 * b1 + 3], r2 = bsph[4 * b2 + 3];
         if (r1 < 0) {  // body 1 owns a plane (planes sort first in a pair): half-space test of body 2's sphere
           const int gp = dex_ldg(m.pair_geom1 + dex_ldg(m.bp_pairadr + bp));
           const T* G = m.geom_mat + 9 * gp;
@@ -680,7 +681,7 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
           T d[3] = {bsph[4 * b2] - gsph[4 * gp], bsph[4 * b2 + 1] - gsph[4 * gp + 1], bsph[4 * b2 + 2] - gsph[4 * gp + 2]};
           pass = dot3(d, n) <= r2 + slack;
         } else {
-          T d[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
+          T d[3] = {bsph[4 * b2] - bsph[4 * b1], bsph[4 * b2 + 1] - bsph[4 * b1 + 1], bsph[4 * b2 + 2] - bsph[4 * b1 + 2]};
           const T bound = r1 + r2 + slack;
           pass = dot3(d, d) <= bound * bound;
         }
@@ -750,17 +751,15 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
         ok[q] = false;
         if (p0 + 32 * q + lane < num) {
           const int g1 = gg[q] & 0xffff, g2 = gg[q] >> 16;
-          T s1[4], s2[4];   // one 16-byte shared-memory load per sphere
-          dex_ld4(gsph + 4 * g1, s1); dex_ld4(gsph + 4 * g2, s2);
-          T d[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
-          const T r2 = s2[3];
+          T d[3] = {gsph[4 * g2] - gsph[4 * g1], gsph[4 * g2 + 1] - gsph[4 * g1 + 1], gsph[4 * g2 + 2] - gsph[4 * g1 + 2]};
+          const T r2 = gsph[4 * g2 + 3];
           if (plane && dex_ldg(m.geom_type + g1) == DEX_GEOM_PLANE) {
             const T* G = m.geom_mat + 9 * g1;
             T nl[3] = {dex_ldg(G + 2), dex_ldg(G + 5), dex_ldg(G + 8)}, n[3];
             rot_vec(n, xmat + 9 * b1, nl);
             ok[q] = dot3(d, n) <= mg[q] + r2 + slack;
           } else {
-            const T bound = mg[q] + s1[3] + r2 + slack;
+            const T bound = mg[q] + gsph[4 * g1 + 3] + r2 + slack;
             ok[q] = dot3(d, d) <= bound * bound;
           }
         }
@@ -831,7 +830,8 @@ DEX_DEV void dex_collide_env(const DevModel<T>& m, const BatchState<T>& st, int 
     const int t1 = dex_ldg(m.geom_type + g1), t2 = dex_ldg(m.geom_type + g2);
     if (t1 == DEX_GEOM_CAPSULE && t2 == DEX_GEOM_CAPSULE) {   // mjc_CapsuleCapsule: closed form, up to two contacts (parallel axes)
       if (nslot + 2 > DEX_MAXSLOT) { status |= DEX_STATUS_CAND_OVERFLOW; continue; }
-      dex_capsule_capsule<T>(m, xpos, xmat, g1, g2, dex_ldg(m.pair_margin + p), p, stage + nslot * DEX_CON_STRIDE);
+      dex_capsule_capsule<T>(m.geom_body, m.geom_mat, m.geom_pack, m.geom_size, xpos, xmat, g1, g2, dex_ldg(m.pair_margin + p), p,
+                             stage + nslot * DEX_CON_STRIDE);
       nslot += 2;
       continue;
     }

@@ -535,23 +535,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     // curvature search . H search = -search . grad (H search = -grad), so the step lands on alpha = 1 exactly.
     const T g0 = dex_warp_sum(isdof ? search * grad : T(0));
     T alpha = g0 < 0 ? T(1) : T(0), lo = 0, hi = -1;   // not a descent direction: alpha stays 0
-    // If no row changes its regime between alpha = 0 and alpha = 1 (rows are linear in alpha, regimes are intervals), the cost is
-    // exactly quadratic on the whole step and alpha = 1 IS the line minimum: no row pass at all (each pass costs two dependent
-    // warp reductions).  This is the usual case of the last Newton iterations, once the active set has settled.
-    bool same;
-    {
-      const T x0 = qacc - f_aref, x1 = x0 + search;
-      const int r0 = x0 <= -f_lim ? -1 : (x0 >= f_lim ? 1 : 0), r1 = x1 <= -f_lim ? -1 : (x1 >= f_lim ? 1 : 0);
-      const T xl0 = l_sign * qacc - l_aref, xl1 = xl0 + l_sign * search;
-      same = (!(f_loss > 0) || r0 == r1) && (l_sign == 0 || (xl0 < 0) == (xl1 < 0));
-    }
-    if (lane < ncon) {
-      const T* cdt = cdat + lane * DEX_CDAT_STRIDE;
-      const int nrow = cdt[CD_MU] == 0 ? 1 : 4;
-      for (int r = 0; r < nrow; ++r) same = same && ((cdt[CD_JAR + r] < 0) == (cdt[CD_JAR + r] + cdt[CD_JV + r] < 0));
-    }
-    const bool quadratic = dex_ballot(!same) == 0;
-    for (int ls = 1; ls < 24 && g0 < 0 && !quadratic; ++ls) {
+    for (int ls = 1; ls < 24 && g0 < 0; ++ls) {
       T g = q1 + alpha * q2, hh = q2;
       {  // friction loss and limit rows, branch-free (same regimes as in the force update above)
         const T x = qacc + alpha * search - f_aref, lim = f_lim;
