@@ -94,9 +94,15 @@ constexpr int kNarrowBlock = DEX_NARROW_BLOCK;
 #ifndef DEX_NARROW_MINB
 #define DEX_NARROW_MINB 8
 #endif
+#ifdef DEX_NARROW_PROF   // tuning aid (variants only): cycles and active lanes per trip index of a warp's loop
+__device__ unsigned long long g_trip_cycles[128], g_trip_warps[128], g_trip_lanes[128];
+#endif
 template <typename T>
 __global__ void __launch_bounds__(kNarrowBlock, DEX_NARROW_MINB) k_narrow(DevModel<T> m, BatchState<T> st) {
   int n = st.nwork[0];
+#ifdef DEX_NARROW_PROF
+  int trip = 0;
+#endif
   if (n > st.work_cap) n = st.work_cap;
   const int lane = threadIdx.x & 31;
   MprLane<T> L;
@@ -115,7 +121,19 @@ __global__ void __launch_bounds__(kNarrowBlock, DEX_NARROW_MINB) k_narrow(DevMod
       L.begin(m, st, st.work[2 * (size_t)i], st.work[2 * (size_t)i + 1]);
       have = true;
     }
+#ifdef DEX_NARROW_PROF
+    const long long t0 = clock64();
+    const unsigned am0 = __activemask();
+#endif
     L.step(m);
+#ifdef DEX_NARROW_PROF
+    {
+      const long long t1 = clock64();
+      const int tt = trip < 127 ? trip : 127;
+      if (lane == __ffs(am0) - 1) { atomicAdd(&g_trip_cycles[tt], (unsigned long long)(t1 - t0)); atomicAdd(&g_trip_warps[tt], 1ull); atomicAdd(&g_trip_lanes[tt], (unsigned long long)__popc(am0)); }
+      ++trip;
+    }
+#endif
   }
 }
 
@@ -747,6 +765,16 @@ int dex_get_kernel_times(DexBatch* b, double* ms, int64_t* count, int reset) {
   }
   return DEX_OK;
 }
+#ifdef DEX_NARROW_PROF
+int dex_debug_trips(unsigned long long* out, int reset) {   // out[3][128]: cycles, warps, lanes per trip index
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_trip_cycles, sizeof(g_trip_cycles));
+  cudaMemcpyFromSymbol(out + 128, g_trip_warps, sizeof(g_trip_warps));
+  cudaMemcpyFromSymbol(out + 256, g_trip_lanes, sizeof(g_trip_lanes));
+  if (reset) { unsigned long long z[128] = {0}; cudaMemcpyToSymbol(g_trip_cycles, z, sizeof(z)); cudaMemcpyToSymbol(g_trip_warps, z, sizeof(z)); cudaMemcpyToSymbol(g_trip_lanes, z, sizeof(z)); }
+  return 0;
+}
+#endif
 int dex_env_reset(DexBatch* b, void* stream) { return dispatch_env(b, 1, 1, stream); }
 int dex_env_step(DexBatch* b, int nsub, void* stream) { return dispatch_env(b, nsub, 0, stream); }
 int dex_env_phase(DexBatch* b, int phases, int nsub, int force_reset, void* stream) { return dispatch_env(b, nsub, force_reset, stream, phases); }

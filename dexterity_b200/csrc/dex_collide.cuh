@@ -189,7 +189,9 @@ template <typename T> DEX_DEV void expand_portal(SupPt<T>* s, const SupPt<T>& v4
 // On a convex hull every local maximum is global, so both give the first-maximum vertex except on
 // exact ties (a face perpendicular to the direction), the degenerate states DESIGN.md describes.
 // ------------------------------------------------------------------------------------------
-#define DEX_SCAN_MAX 24
+#ifndef DEX_SCAN_MAX
+#define DEX_SCAN_MAX 4    // 0 / 4 / 8 / 16-32 / 48: narrowphase 0.109 / 0.109 / 0.110 / 0.115 / 0.120 ms per launch (climbing wins even on small hulls)
+#endif
 template <typename T>
 struct LaneGeom {
   const T* vert;   // body-frame hull vertices of the geom instance (4 reals per vertex)

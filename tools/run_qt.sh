@@ -1,4 +1,5 @@
-python -m pytest tests/test_physics_gpu.py tests/test_env_gpu.py -m gpu -x -q 2>&1 | tail -3
-python tools/quick_time.py
-DEX_NARROW_ONE_PASS=1 python tools/quick_time.py
-for v in nt3 nt8 nb4 nb1; do python tools/quick_time.py variants/libdex_$v.so; done
+for v in sm0 sm4; do python tools/quick_time.py variants/libdex_$v.so; done
+DEX_CHUNKS=2 python tools/quick_time.py
+DEX_CHUNKS=2 DEX_SOLVER_MODE=0 python tools/quick_time.py
+DEX_CHUNKS=3 DEX_SOLVER_MODE=0 python tools/quick_time.py
+DEX_CHUNKS=4 DEX_SOLVER_MODE=0 python tools/quick_time.py
