@@ -1,5 +1,3 @@
-for v in sm0 sm4; do python tools/quick_time.py variants/libdex_$v.so; done
-DEX_CHUNKS=2 python tools/quick_time.py
-DEX_CHUNKS=2 DEX_SOLVER_MODE=0 python tools/quick_time.py
-DEX_CHUNKS=3 DEX_SOLVER_MODE=0 python tools/quick_time.py
-DEX_CHUNKS=4 DEX_SOLVER_MODE=0 python tools/quick_time.py
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/quick_time.py
+DEX_WORK_FLAT=1 python tools/quick_time.py
