@@ -260,6 +260,40 @@ class BatchedGoalEnvironment:
     def successes(self) -> torch.Tensor:
         return self._task_i[:, 0]
 
+    # ------------------------------------------------------------------ hand observables outside HAND_OBSERVABLES
+    # The reference defines them (models/hands/dexterous_hand.py:244-350) but no registered task enables them
+    # (shared/observations.py:96-103); they are served from the device state on request instead of being packed into the
+    # observation vector.  joint_torques (torque sensors, mj_rnePostConstraint) and fingertip_angular_velocities are not built.
+    def _hand_qpos_adr(self) -> torch.Tensor:
+        c = self.compiled
+        ids = [i for i, n in enumerate(c.joint_names) if n.startswith(self.hand_name + "/")]
+        return torch.as_tensor(np.asarray(c.JNT_QPOSADR)[ids].astype(np.int64), device=self.device)
+
+    def joint_positions(self) -> torch.Tensor:
+        """[num_envs, hand joints]: dexterous_hand.py:249-251 (MJCFFeature "qpos" of the hand's joints)."""
+        return self.physics.qpos[:, self._hand_qpos_adr()]
+
+    def _site_frames(self):
+        """World positions [n, sites, 3] and rotation matrices [n, sites, 3, 3] of the fingertip sites and the pose of the hand's
+        root body, by forward kinematics of the current qpos (torch; the hand is a tree of hinges on a fixed base)."""
+        from dexterity_b200 import hands
+        c = self.compiled
+        hand = getattr(self, "hand", None) or hands.DexterousHand(c, prefix=scenes.HANDS[self.hand_name][1],
+                                                                   fingertip_sites=scenes.HANDS[self.hand_name][2])
+        root = c.body_names.index(f"{self.hand_name}/forearm")      # root_body (shadow_hand_e.py / adroit_hand.py: find("body", "forearm"))
+        return _fk_sites(c, hand, self.physics, frames=True, extra_body=root)
+
+    def fingertip_orientations(self) -> torch.Tensor:
+        """[num_envs, 4 * sites] world-frame quaternions of the fingertip sites (dexterous_hand.py:286-295)."""
+        _, R, _, _ = self._site_frames()
+        return _mat_to_quat(R).reshape(self.num_envs, -1)
+
+    def fingertip_positions_ego(self) -> torch.Tensor:
+        """[num_envs, 3 * sites] fingertip positions relative to the hand's root body, in that body's frame: the `framepos`
+        sensors with reftype = body, refname = root_body of dexterous_hand.py:325-348."""
+        p, _, rpos, rmat = self._site_frames()
+        return torch.einsum("nji,nsj->nsi", rmat, p - rpos[:, None, :]).reshape(self.num_envs, -1)
+
     def request_reset(self, mask: torch.Tensor) -> None:
         """Marks envs to be re-initialised at the next `step` (their action is ignored)."""
         self._reset_mask.copy_(mask.to(torch.uint8))
@@ -355,8 +389,23 @@ class ReachEnvironment(BatchedGoalEnvironment):
         return self._timestep()
 
 
-def _fk_sites(compiled, hand, physics) -> torch.Tensor:
-    """Torch forward kinematics of the fingertip sites for a scratch batch (hinge chains only)."""
+def _mat_to_quat(R: torch.Tensor) -> torch.Tensor:
+    """[..., 3, 3] rotation matrices -> [..., 4] unit quaternions (w, x, y, z), w >= 0."""
+    m00, m11, m22 = R[..., 0, 0], R[..., 1, 1], R[..., 2, 2]
+    w = (1 + m00 + m11 + m22).clamp_min(0).sqrt() / 2
+    x = (1 + m00 - m11 - m22).clamp_min(0).sqrt() / 2
+    y = (1 - m00 + m11 - m22).clamp_min(0).sqrt() / 2
+    z = (1 - m00 - m11 + m22).clamp_min(0).sqrt() / 2
+    x = torch.copysign(x, R[..., 2, 1] - R[..., 1, 2])
+    y = torch.copysign(y, R[..., 0, 2] - R[..., 2, 0])
+    z = torch.copysign(z, R[..., 1, 0] - R[..., 0, 1])
+    q = torch.stack([w, x, y, z], -1)
+    return q / q.norm(dim=-1, keepdim=True)
+
+
+def _fk_sites(compiled, hand, physics, frames: bool = False, extra_body: Optional[int] = None):
+    """Torch forward kinematics of the fingertip sites for a scratch batch (hinge chains only): positions [n, 3 * sites], or
+    with `frames` (positions [n, sites, 3], rotations [n, sites, 3, 3], position and rotation of body `extra_body`)."""
     c = compiled
     n = physics.num_envs
     dev, dt = physics.device, physics.dtype
@@ -370,6 +419,9 @@ def _fk_sites(compiled, hand, physics) -> torch.Tensor:
         b = int(c.SITE_BODY[s])
         while b > 0:
             needed.add(b); b = int(c.BODY_PARENT[b])
+    b = extra_body if extra_body is not None else 0
+    while b > 0:
+        needed.add(b); b = int(c.BODY_PARENT[b])
     from dexterity_b200.model import mjcf
     for b in range(1, c.nbody):
         if b not in needed:
@@ -390,10 +442,14 @@ def _fk_sites(compiled, hand, physics) -> torch.Tensor:
             R = R @ Rj
             x = anchor - R @ jp
         pos[b], rot[b] = x, R
-    out = []
+    out, mats = [], []
     for s in hand.fingertip_site_ids:
         b = int(c.SITE_BODY[s])
         out.append(pos[b] + rot[b] @ torch.as_tensor(c.SITE_POS[s], dtype=dt, device=dev))
+        if frames:
+            mats.append(rot[b] @ torch.as_tensor(mjcf.quat_to_mat(np.asarray(c.SITE_QUAT[s])), dtype=dt, device=dev))
+    if frames:
+        return torch.stack(out, 1), torch.stack(mats, 1), pos[extra_body], rot[extra_body]
     return torch.cat(out, dim=1)
 
 

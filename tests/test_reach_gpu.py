@@ -81,3 +81,39 @@ def test_reach_behaviour_like_reference():
         ts = env.step(ctrl)
         reached |= (env.successes > 0) & (ts.reward == 0.0)
     assert reached.float().mean() > 0.7, reached.float().mean()
+
+
+@pytest.mark.parametrize("hand", ["shadow_hand_e", "adroit_hand"])
+def test_hand_observables_outside_the_default_set(hand):
+    """joint_positions, fingertip_orientations and fingertip_positions_ego (reference dexterous_hand.py:249-251,286-295,
+    325-348; defined but enabled by no registered task) against the oracle's kinematics at the env's own state."""
+    from dexterity_b200 import envs
+    from oracle import oracle as orc
+    env = envs.load("reach", "state_dense", seed=5, num_envs=8, hand=hand)
+    env.reset()
+    for _ in range(3):
+        lo = torch.as_tensor(env.action_spec().minimum, device=env.device); hi = torch.as_tensor(env.action_spec().maximum, device=env.device)
+        env.step(lo + (hi - lo) * torch.rand(8, lo.numel(), device=env.device))
+    c = env.compiled
+    jp = env.joint_positions().cpu().numpy()
+    quat = env.fingertip_orientations().cpu().numpy().reshape(8, 5, 4)
+    ego = env.fingertip_positions_ego().cpu().numpy().reshape(8, 5, 3)
+    tips = env.fingertip_positions().cpu().numpy().reshape(8, 5, 3)
+    qpos = env.physics.qpos.cpu().numpy().astype(np.float64)
+    assert jp.shape == (8, 24) and np.allclose(jp, qpos[:, :24])
+    d = orc.OracleData(orc.OracleModel(c))
+    root = c.body_names.index(hand + "/forearm")
+    for e in range(8):
+        d.set_state(qpos[e], np.zeros(c.nv), np.zeros(c.nu), np.zeros(c.nv)); d.kinematics()
+        xpos, xmat = d.get("xpos").reshape(-1, 3), d.get("xmat").reshape(-1, 3, 3)
+        for k, s in enumerate(env.hand.fingertip_site_ids):
+            b = int(c.SITE_BODY[s])
+            p = xpos[b] + xmat[b] @ np.asarray(c.SITE_POS[s])
+            assert np.abs(p - tips[e, k]).max() < 1e-5
+            assert np.abs(xmat[root].T @ (p - xpos[root]) - ego[e, k]).max() < 1e-5
+            w, x, y, z = quat[e, k]
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                          [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                          [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+            from dexterity_b200.model import mjcf
+            assert np.abs(R - xmat[b] @ mjcf.quat_to_mat(np.asarray(c.SITE_QUAT[s]))).max() < 5e-4   # FP32 quaternion of a half-turn

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python tools/quick_time.py
-DEX_WORK_FLAT=1 python tools/quick_time.py
+for v in mb10 mb12 nb128 nb32; do python tools/quick_time.py variants/libdex_$v.so; done
