@@ -1,2 +1,4 @@
-python tools/quick_time.py
-for v in mb10 mb12 nb128 nb32; do python tools/quick_time.py variants/libdex_$v.so; done
+DEX_SOLVER_MODE=1 python tools/quick_time.py
+DEX_SOLVER_MODE=4 python tools/quick_time.py
+DEX_SOLVER_MODE=4 python tools/quick_time.py
+DEX_SOLVER_MODE=1 python tools/quick_time.py
