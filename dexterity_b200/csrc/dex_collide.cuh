@@ -26,6 +26,9 @@
 #define DEX_MAXGEOM 256    // world bounding spheres of all geoms are staged in shared memory
 #define DEX_MAXBPL 128     // body pairs that survive the body-level culls
 #define DEX_K1_SMEM_T (DEX_MAXBODY * 16 + DEX_MAXGEOM * 4 + DEX_MAXCAND1 + DEX_MAXBPL + 8 * 4)
+// 20 single-warp CTAs per SM (the register limit) must fit the 196 KB shared-memory configuration, 1 KB of system use per CTA
+// included: 64 words more per CTA select the 228 KB configuration, and the L1 lost to it costs K1a 15 % (0.156 -> 0.179 ms, r2zm)
+static_assert((DEX_K1_SMEM_T * 4 + 1024) * 20 <= 196 * 1024, "K1a's shared memory crosses into the 228 KB configuration");
 #define DEX_NCLASS 8       // solver-cost classes of K2's processing order
 #define DEX_NCLASS_DENSE 4 // with the structured solver on (DevModel::arrow_ok): classes 0-3 dense kernel, 4-7 structured kernel
 #define DEX_AR_MAXCON_K1 8 // = DEX_AR_MAXCON (dex_arrow.cuh)

@@ -1,4 +1,1 @@
-DEX_SOLVER_MODE=1 python tools/quick_time.py
-DEX_SOLVER_MODE=4 python tools/quick_time.py
-DEX_SOLVER_MODE=4 python tools/quick_time.py
-DEX_SOLVER_MODE=1 python tools/quick_time.py
+for v in cl12 cl16 cl24; do python tools/quick_time.py variants/libdex_$v.so; done
