@@ -132,3 +132,71 @@ def test_reach_adroit_kernel_bodies_match_oracle(reach_adroit_model):
         out32 = m.run(st["qpos"], st["qvel"], st["ctrl"], st["warm"], nsub=1, dtype=np.float32)
         rel32 = np.abs(out32["qvel"][:, :c.nv] - ref["qvel"]).max(axis=1) / np.maximum(1, np.abs(ref["qvel"]).max(axis=1))
         assert (out32["ncon"] == ref["ncon"]).mean() >= 0.99 and (rel32 <= 1e-4).mean() >= 0.98     # north-star single-step tolerance
+
+
+def _reach_params(c, dense):
+    import math
+    from dexterity_b200 import envs
+    p = envs.TaskParams()
+    cfg = envs.REACH
+    p.task, p.successes_needed, p.steps_before_changing_goal, p.fall_termination, p.has_max_time = 1, cfg["successes_needed"], 5, 0, 1
+    p.nhand, p.nsite = 24, 5
+    for i, t in enumerate(scenes.ADROIT_FINGERTIP_SITES):
+        p.site_id[i] = c.site_names.index("adroit_hand/" + t)
+    p.dense_reward = int(dense)
+    p.reach_tanh_weight = math.atanh(math.sqrt(cfg["reward_loss_at_margin"])) / cfg["reward_margin"]
+    p.success_threshold, p.max_time_per_goal, p.time_limit = cfg["success_threshold"], cfg["max_time_per_goal"], float("inf")
+    return p
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_reach_task_kernels_on_the_adroit_scene(reach_adroit_model, dense):
+    """The fused pre- / post-step kernels of the reach task (reference manipulation/tasks/reach.py:149-210, task.py:137-204) on the
+    registered scene: 117 observation floats, per-finger goal distances, dense / sparse reward, success bookkeeping, checked
+    against the numpy restatement (oracle/task_oracle.py) at the kernels' own state."""
+    from oracle import oracle as orc
+    from oracle import task_oracle as T
+    c = reach_adroit_model
+    m = E.EmuModel(c)
+    n = 4
+    env = E.EmuEnv(m, _reach_params(c, dense), nenv=n, dtype=np.float64, seed=3)
+    env.reset()
+    a = env.a
+    assert (a["TASK_I"][:, 6] == 0).all() and (a["REWARD"] == 0).all() and (a["DISCOUNT"] == 1).all()
+    rng = np.random.RandomState(1)
+    lo, hi = c.JNT_RANGE[:, 0], c.JNT_RANGE[:, 1]
+    d = orc.OracleData(orc.OracleModel(c))
+    sites = [c.site_names.index("adroit_hand/" + t) for t in scenes.ADROIT_FINGERTIP_SITES]
+    # goals = fingertip positions of a configuration near the mid-range (what FingertipCartesianPosition.next_goal produces);
+    # env 0 gets the goal of its OWN start configuration so that it scores successes
+    goal_q = 0.5 * (lo + hi) + 0.05 * (hi - lo) * rng.randn(n, 24)
+    goal_q[0] = a["QPOS"][0, :24]
+    for e in range(n):
+        d.set_state(goal_q[e], np.zeros(24), np.zeros(24), np.zeros(24)); d.kinematics()
+        a["GOAL"][e, :15] = T.hand_observations(c, d, 24, sites)["fingertip_positions"]
+    machines = [T.GoalTaskState(0.01, 50, 5, 150 * 0.02) for _ in range(n)]
+    for m_ in machines:
+        m_.initialize_episode(0.0)
+    for it in range(4):
+        act = np.clip(goal_q + (0.3 * rng.randn(n, 24) if it % 2 else 0.0), c.ACT_CTRLRANGE[:, 0], c.ACT_CTRLRANGE[:, 1])
+        act[0] = a["QPOS"][0, :24]     # holds its pose: stays on its goal
+        env.step(act, nsub=1)
+        for e in range(n):
+            assert a["TASK_I"][e, 6] == 1
+            d.set_state(a["QPOS"][e, :24], a["QVEL"][e, :24], a["CTRL"][e, :24], np.zeros(24)); d.step1()
+            ho = T.hand_observations(c, d, 24, sites)
+            np.testing.assert_allclose(a["OBS"][e, :48], ho["joint_positions_sin_cos"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 48:72], ho["joint_velocities"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 72:87], ho["fingertip_positions"], atol=1e-12)
+            np.testing.assert_allclose(a["OBS"][e, 87:102], ho["fingertip_linear_velocities"], atol=1e-10)
+            np.testing.assert_allclose(a["OBS"][e, 102:117], a["GOAL"][e, :15], atol=0)          # goal_state observable (task.py:206-216)
+            dist = np.linalg.norm((a["GOAL"][e, :15] - ho["fingertip_positions"]).reshape(5, 3), axis=1)   # fingertip_position.py:126-130
+            np.testing.assert_allclose(a["TASK_F"][e, 2:7], dist, atol=1e-10)
+            np.testing.assert_allclose(a["REWARD"][e], T.reach_reward(dist, dense=dense), rtol=1e-9, atol=1e-12)
+            m_ = machines[e]
+            m_.before_step(a["TIME"][e] - 0.02)
+            m_.after_step(dist, a["TIME"][e])
+            assert a["TASK_I"][e, 0] == m_.successes and a["TASK_I"][e, 1] == m_.success_change_counter
+            assert a["DISCOUNT"][e] == m_.get_discount()
+    assert a["TASK_I"][0, 0] >= 1 and a["REWARD"][0] == 0.0       # the env that sits on its goal
+    assert (a["TASK_I"][1:, 0] == 0).all()
