@@ -30,7 +30,7 @@ NUM_ENVS_PER_GPU = 16384          # BASELINE.json configs[2] / configs[4] (13107
 B_ENV = 1364                      # algorithmic bytes per env-step, SURVEY.md §8(d) / BASELINE.md §3
 B_MJ = 808                        # algorithmic bytes per mj_step (state round trip)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 envs from the `ncu --set full` capture summarised in
-# profiles/r02r_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size).  k_dynamics = the dense
+# profiles/r02z_summary.md (bench.py cannot run under ncu; the figure is only reported at that batch size).  k_dynamics = the dense
 # solver kernel plus the structured kernel's contact-free form, which run side by side on two streams.
 NCU_TRAFFIC_BYTES = {"k_dynamics": 55.54e6 + 2.05e6 + 30.08e6, "k_tree": 46.55e6 + 68.79e6, "k_collide": 35.76e6, "k_narrow": 12.28e6}
 METRIC = "env-steps/sec, Shadow-hand cube reorient"
