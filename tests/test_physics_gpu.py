@@ -271,3 +271,37 @@ def test_many_contact_states(reorient_model):
         eq = relerr(b.qpos.cpu().numpy().astype(np.float64)[:, :31], ref["qpos"])
         assert (eq[same] <= tol).all(), (dtype, eq[same].max())
         assert (ev[same] <= tol).mean() >= (1.0 if dtype == torch.float64 else 0.8), (dtype, np.sort(ev[same])[-5:])
+
+
+def test_full_size_batch_is_permutation_invariant_and_deterministic(reorient_model):
+    """BASELINE.json's full size (16 384 envs): envs never interact, so five mj_steps of a batch must give every env the SAME
+    BITS whatever its index in the batch and whatever else runs beside it, run after run.  The kernels share a global
+    narrowphase work list, per-class env lists filled with atomics and two solver kernels on two streams: any race or dependence
+    on the processing order would show here."""
+    from dexterity_b200 import backend
+    compiled = reorient_model
+    base = statelib.rollout_states_batch(compiled, seed=5, nenv=64, snapshots=8, every=6, nthreads=8)
+    n, nb = 16384, len(base["qpos"])
+    rng = np.random.RandomState(0)
+    idx = rng.randint(0, nb, n)
+    states = {k: v[idx].copy() for k, v in base.items()}
+    states["qvel"] += 1e-3 * rng.randn(*states["qvel"].shape)              # make the envs differ
+    states["ctrl"] = rng.uniform(compiled.ACT_CTRLRANGE[:, 0], compiled.ACT_CTRLRANGE[:, 1], (n, compiled.nu))
+    model = backend.PhysicsModel(compiled, 0)
+    perm = rng.permutation(n)
+
+    def run(order):
+        b = backend.PhysicsBatch(model, n, torch.float32)
+        statelib.upload(b, {k: v[order] for k, v in states.items()})
+        b.step(5)
+        torch.cuda.synchronize()
+        assert (b.status.cpu().numpy() & 1 == 0).all()
+        return b.qpos.cpu().numpy(), b.qvel.cpu().numpy(), b.qacc_warmstart.cpu().numpy(), b.ncon.cpu().numpy(), b.niter.cpu().numpy()
+
+    ident = np.arange(n)
+    a = run(ident); a2 = run(ident); p = run(perm)
+    inv = np.empty(n, np.int64); inv[perm] = ident
+    for x, y, z in zip(a, a2, p):
+        assert np.array_equal(x, y), "two runs of the same batch differ"
+        assert np.array_equal(x, z[inv]), "an env's result depends on its place in the batch"
+    assert (a[3] > 0).mean() > 0.3        # the batch exercises contacts
