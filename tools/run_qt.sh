@@ -1,4 +1,5 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python tools/quick_time.py
-python tools/quick_time.py variants/libdex_mst.so
-DEX_SOLVER_MODE=0 python tools/quick_time.py
-DEX_SOLVER_MODE=0 python tools/quick_time.py variants/libdex_mst.so
+DEX_NO_PDL=1 python tools/quick_time.py
+python tools/quick_time.py
+DEX_NO_PDL=1 python tools/quick_time.py
