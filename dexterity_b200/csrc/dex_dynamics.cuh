@@ -35,6 +35,16 @@
 #define DEX_JC_ROW 32                         // global Jc scratch: [env][3 * DEX_MAXCON][DEX_JC_ROW]
 #define DEX_JC_ENV (3 * DEX_MAXCON * DEX_JC_ROW)
 
+// Timing experiments (tools/k2_breakdown.sh builds variants with these; never defined in the product build): DEX_EXP_FIXITER = a
+// fixed number of Newton iterations with a refactorisation in each, DEX_EXP_NO{EULER,FACTOR,APPLY,MATVEC,LS} drop one part of
+// the solver, and integrate == 2 (DEX_EXP, DEX_FREEZE=1 at run time) computes the step but keeps the state, so that every variant
+// sees the same workload whatever it computes.
+#ifdef DEX_EXP_FIXITER
+#define DEX_EXP_ON true
+#else
+#define DEX_EXP_ON false
+#endif
+
 // cdat layout per contact
 enum { CD_MU = 0, CD_D = 1, CD_AREF = 2 /*4*/, CD_JAR = 6 /*4*/, CD_JV = 10 /*4*/, CD_F = 14 /*3 frame-space force*/,
        CD_W = 17 /*5: W00 W01 W02 W11 W22*/, CD_MASK = 22 /*dof mask as int bits*/ };
@@ -480,8 +490,12 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     }
     grad = isdof ? (Ma - fs - jtf) : T(0);
     const T gnorm = dx_sqrt(dex_warp_sum(grad * grad));
+#ifdef DEX_EXP_FIXITER
+    if (iter >= DEX_EXP_FIXITER) break;
+#else
     if (scale * gnorm < tol || small_step) break;
-    if (iter > 0) {
+#endif
+    if (iter > 0 && !DEX_EXP_ON) {
       // MuJoCo stops on improvement < tolerance; in FP32 the cost is only good to ~1e-7 relative,
       // so the improvement test is honoured only once the gradient has stopped shrinking.
       const T improvement = scale * (oldcost - cost);
@@ -494,7 +508,11 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     // when the active set (hence H) is the same as in the previous iteration.
     const unsigned sig_changed = dex_ballot(asig != asig_prev || hdiag != hdiag_prev);
     asig_prev = asig; hdiag_prev = hdiag;
-    if (iter == 0 || sig_changed) {
+#ifdef DEX_EXP_NOFACTOR
+    if (false) {
+#else
+    if (iter == 0 || sig_changed || DEX_EXP_ON) {
+#endif
       T hd = dex_chol_load(H, M, nv) + hdiag;
       dex_syncwarp();
       bool cross = false;
@@ -516,12 +534,20 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       hinv = dex_chol_factor(H, hd, nv, cross ? nv : m.chol_split, &cfail);
       if (cfail) status |= DEX_STATUS_CHOL_FAIL;
     }
+#ifdef DEX_EXP_NOAPPLY
+    const T search = isdof ? T(-1e-3) * grad : T(0);
+#else
     const T search = dex_chol_apply(H, nv, hinv, isdof ? -grad : T(0));
+#endif
 
     // ---- exact line search along `search` (PrimalSearch)
     vecB[lane] = isdof ? search : T(0);
     dex_syncwarp();
+#ifdef DEX_EXP_NOMATVEC
+    const T Mv = search;
+#else
     const T Mv = dex_matvec(M, vecB, nv);
+#endif
     dex_contact_dots(Jc, vecB, 3 * ncon, cdot);
     if (lane < ncon) {
       T* cdt = cdat + lane * DEX_CDAT_STRIDE;
@@ -535,7 +561,11 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
     // curvature search . H search = -search . grad (H search = -grad), so the step lands on alpha = 1 exactly.
     const T g0 = dex_warp_sum(isdof ? search * grad : T(0));
     T alpha = g0 < 0 ? T(1) : T(0), lo = 0, hi = -1;   // not a descent direction: alpha stays 0
+#ifdef DEX_EXP_NOLS
+    for (int ls = 1; ls < 1 && g0 < 0; ++ls) {
+#else
     for (int ls = 1; ls < 24 && g0 < 0; ++ls) {
+#endif
       T g = q1 + alpha * q2, hh = q2;
       {  // friction loss and limit rows, branch-free (same regimes as in the force update above)
         const T x = qacc + alpha * search - f_aref, lim = f_lim;
@@ -568,7 +598,7 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
       alpha = next;
       if (conv) break;
     }
-    if (alpha == 0) break;
+    if (alpha == 0 && !DEX_EXP_ON) break;
     // MuJoCo's stopping rule "improvement * scale < tolerance", with the improvement taken from the
     // line search itself (-alpha g0 / 2 at an exact line minimum) instead of a difference of costs,
     // which FP32 cannot resolve.  The forces/gradient are still refreshed at the final iterate.
@@ -600,16 +630,23 @@ DEX_DEV void dex_dynamics_env(const DevModel<T>& m, const BatchState<T>& st, con
   // only the leading m.nv_euler dofs belong to kinematic trees with joint damping; for the rest
   // (e.g. the free object) M + hB = M is block-decoupled and the solver's qacc is already the answer
   const int ne = m.nv_euler;
+#ifdef DEX_EXP_NOEULER
+  T qacc_e = qacc + damping * fs;
+#else
   const T ehd = dex_chol_load(H, M, ne) + (lane < ne ? h * damping : T(0));
   dex_syncwarp();
   int efail = 0;
   const T einv = dex_chol_factor(H, ehd, ne, ne, &efail);
   T qacc_e = dex_chol_apply(H, ne, einv, lane < ne ? (fs + qfrc_constraint) : T(0));
+#endif
   if (lane >= ne) qacc_e = qacc;
   const T qv_new = qv + h * qacc_e;
   dex_syncwarp();
   qvel[lane] = qv_new;
   dex_syncwarp();
+#ifdef DEX_EXP
+  if (integrate == 2) { if (isdof && qv_new == T(1.2345e33)) st.niter[env] = -1; return; }   // dry run: the state stays as it is
+#endif
   if (isdof) {
     const int j = dex_ldg(m.dof_jnt + lane), da = dex_ldg(m.jnt_dofadr + j), qa = dex_ldg(m.jnt_qposadr + j);
     if (dex_ldg(m.jnt_type + j) == DEX_JNT_FREE) {
