@@ -7,7 +7,7 @@ from dexterity_b200 import backend
 from dexterity_b200.model import scenes
 from tests import statelib
 
-for scene in ("reorient_shadow", "reach_shadow"):
+for scene in ("reorient_shadow", "reach_shadow", "reach_adroit"):
     c = scenes.load_compiled(scene)
     n = 256
     states = statelib.rollout_states(c, seed=777, nstates=n, every=9, episodes=32)
