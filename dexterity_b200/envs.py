@@ -263,7 +263,7 @@ class BatchedGoalEnvironment:
     # ------------------------------------------------------------------ hand observables outside HAND_OBSERVABLES
     # The reference defines them (models/hands/dexterous_hand.py:244-350) but no registered task enables them
     # (shared/observations.py:96-103); they are served from the device state on request instead of being packed into the
-    # observation vector.  joint_torques (torque sensors, mj_rnePostConstraint) and fingertip_angular_velocities are not built.
+    # observation vector.  joint_torques (torque sensors, mj_rnePostConstraint) is not built.
     def _hand_qpos_adr(self) -> torch.Tensor:
         c = self.compiled
         ids = [i for i, n in enumerate(c.joint_names) if n.startswith(self.hand_name + "/")]
@@ -285,13 +285,18 @@ class BatchedGoalEnvironment:
 
     def fingertip_orientations(self) -> torch.Tensor:
         """[num_envs, 4 * sites] world-frame quaternions of the fingertip sites (dexterous_hand.py:286-295)."""
-        _, R, _, _ = self._site_frames()
+        _, R, _, _, _ = self._site_frames()
         return _mat_to_quat(R).reshape(self.num_envs, -1)
+
+    def fingertip_angular_velocities(self) -> torch.Tensor:
+        """[num_envs, 3 * sites] world-frame angular velocities of the fingertip sites (dexterous_hand.py:311-323:
+        mj_objectVelocity of the site, rotated to the world frame): the angular velocity of the site's body."""
+        return self._site_frames()[4].reshape(self.num_envs, -1)
 
     def fingertip_positions_ego(self) -> torch.Tensor:
         """[num_envs, 3 * sites] fingertip positions relative to the hand's root body, in that body's frame: the `framepos`
         sensors with reftype = body, refname = root_body of dexterous_hand.py:325-348."""
-        p, _, rpos, rmat = self._site_frames()
+        p, _, rpos, rmat, _ = self._site_frames()
         return torch.einsum("nji,nsj->nsi", rmat, p - rpos[:, None, :]).reshape(self.num_envs, -1)
 
     def request_reset(self, mask: torch.Tensor) -> None:
@@ -414,6 +419,9 @@ def _fk_sites(compiled, hand, physics, frames: bool = False, extra_body: Optiona
     rot = [None] * c.nbody
     eye = torch.eye(3, dtype=dt, device=dev).expand(n, 3, 3)
     pos[0], rot[0] = torch.zeros(n, 3, dtype=dt, device=dev), eye
+    omega = [None] * c.nbody                       # world-frame angular velocity of every needed body (frames only)
+    omega[0] = torch.zeros(n, 3, dtype=dt, device=dev)
+    qd = physics.qvel
     needed = set()
     for s in hand.fingertip_site_ids:
         b = int(c.SITE_BODY[s])
@@ -430,6 +438,7 @@ def _fk_sites(compiled, hand, physics, frames: bool = False, extra_body: Optiona
         R0 = torch.as_tensor(mjcf.quat_to_mat(c.BODY_QUAT[b]), dtype=dt, device=dev)
         x = pos[p] + (rot[p] @ torch.as_tensor(c.BODY_POS[b], dtype=dt, device=dev))
         R = rot[p] @ R0
+        w = omega[p]
         for j in range(int(c.BODY_JNTADR[b]), int(c.BODY_JNTADR[b] + c.BODY_JNTNUM[b])):
             if c.JNT_TYPE[j] != 3:
                 raise NotImplementedError
@@ -439,9 +448,11 @@ def _fk_sites(compiled, hand, physics, frames: bool = False, extra_body: Optiona
             K = torch.tensor([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]], dtype=dt, device=dev)
             Rj = torch.eye(3, dtype=dt, device=dev) + ang.sin()[:, None, None] * K + (1 - ang.cos())[:, None, None] * (K @ K)
             anchor = x + R @ jp
+            if frames:
+                w = w + (R @ ax) * qd[:, int(c.JNT_DOFADR[j])].unsqueeze(1)      # hinge: axis (world) x joint velocity
             R = R @ Rj
             x = anchor - R @ jp
-        pos[b], rot[b] = x, R
+        pos[b], rot[b], omega[b] = x, R, w
     out, mats = [], []
     for s in hand.fingertip_site_ids:
         b = int(c.SITE_BODY[s])
@@ -449,7 +460,8 @@ def _fk_sites(compiled, hand, physics, frames: bool = False, extra_body: Optiona
         if frames:
             mats.append(rot[b] @ torch.as_tensor(mjcf.quat_to_mat(np.asarray(c.SITE_QUAT[s])), dtype=dt, device=dev))
     if frames:
-        return torch.stack(out, 1), torch.stack(mats, 1), pos[extra_body], rot[extra_body]
+        angvel = torch.stack([omega[int(c.SITE_BODY[s])] for s in hand.fingertip_site_ids], 1)
+        return torch.stack(out, 1), torch.stack(mats, 1), pos[extra_body], rot[extra_body], angvel
     return torch.cat(out, dim=1)
 
 

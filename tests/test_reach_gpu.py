@@ -85,8 +85,8 @@ def test_reach_behaviour_like_reference():
 
 @pytest.mark.parametrize("hand", ["shadow_hand_e", "adroit_hand"])
 def test_hand_observables_outside_the_default_set(hand):
-    """joint_positions, fingertip_orientations and fingertip_positions_ego (reference dexterous_hand.py:249-251,286-295,
-    325-348; defined but enabled by no registered task) against the oracle's kinematics at the env's own state."""
+    """joint_positions, fingertip_orientations, fingertip_angular_velocities and fingertip_positions_ego (reference
+    dexterous_hand.py:249-251,286-295,311-323,325-348; defined but enabled by no registered task) against the oracle's kinematics at the env's own state."""
     from dexterity_b200 import envs
     from oracle import oracle as orc
     env = envs.load("reach", "state_dense", seed=5, num_envs=8, hand=hand)
@@ -98,17 +98,20 @@ def test_hand_observables_outside_the_default_set(hand):
     jp = env.joint_positions().cpu().numpy()
     quat = env.fingertip_orientations().cpu().numpy().reshape(8, 5, 4)
     ego = env.fingertip_positions_ego().cpu().numpy().reshape(8, 5, 3)
+    angv = env.fingertip_angular_velocities().cpu().numpy().reshape(8, 5, 3)
+    qvel = env.physics.qvel.cpu().numpy().astype(np.float64)
     tips = env.fingertip_positions().cpu().numpy().reshape(8, 5, 3)
     qpos = env.physics.qpos.cpu().numpy().astype(np.float64)
     assert jp.shape == (8, 24) and np.allclose(jp, qpos[:, :24])
     d = orc.OracleData(orc.OracleModel(c))
     root = c.body_names.index(hand + "/forearm")
     for e in range(8):
-        d.set_state(qpos[e], np.zeros(c.nv), np.zeros(c.nu), np.zeros(c.nv)); d.kinematics()
+        d.set_state(qpos[e], qvel[e], np.zeros(c.nu), np.zeros(c.nv)); d.step1()
         xpos, xmat = d.get("xpos").reshape(-1, 3), d.get("xmat").reshape(-1, 3, 3)
         for k, s in enumerate(env.hand.fingertip_site_ids):
             b = int(c.SITE_BODY[s])
             p = xpos[b] + xmat[b] @ np.asarray(c.SITE_POS[s])
+            assert np.abs(d.object_velocity(b, p)[:3] - angv[e, k]).max() < 1e-4 * max(1.0, np.abs(angv[e, k]).max())   # mj_objectVelocity, world frame
             assert np.abs(p - tips[e, k]).max() < 1e-5
             assert np.abs(xmat[root].T @ (p - xpos[root]) - ego[e, k]).max() < 1e-5
             w, x, y, z = quat[e, k]
