@@ -305,3 +305,30 @@ def test_full_size_batch_is_permutation_invariant_and_deterministic(reorient_mod
         assert np.array_equal(x, y), "two runs of the same batch differ"
         assert np.array_equal(x, z[inv]), "an env's result depends on its place in the batch"
     assert (a[3] > 0).mean() > 0.3        # the batch exercises contacts
+
+
+def test_ragged_batch_sizes(reorient_model):
+    """Batch sizes that are not multiples of the kernels' grouping (K0 packs four envs into a warp, the structured solver kernel
+    too, K1c eight envs into a CTA): 1, 3, 5, 37 and 1023 envs give every env the bits it gets inside a batch of 1024."""
+    from dexterity_b200 import backend
+    compiled = reorient_model
+    base = statelib.rollout_states_batch(compiled, seed=11, nenv=32, snapshots=4, every=8, nthreads=8)
+    rng = np.random.RandomState(2)
+    idx = rng.randint(0, len(base["qpos"]), 1024)
+    states = {k: v[idx].copy() for k, v in base.items()}
+    states["qvel"] += 1e-3 * rng.randn(*states["qvel"].shape)
+    model = backend.PhysicsModel(compiled, 0)
+
+    def run(n):
+        b = backend.PhysicsBatch(model, n, torch.float32)
+        statelib.upload(b, {k: v[:n] for k, v in states.items()})
+        b.step(2)
+        torch.cuda.synchronize()
+        return b.qpos.cpu().numpy(), b.qvel.cpu().numpy(), b.ncon.cpu().numpy(), b.status.cpu().numpy()
+
+    full = run(1024)
+    assert (full[3] & 1 == 0).all() and (full[2] > 0).any()
+    for n in (1, 3, 5, 37, 1023):
+        part = run(n)
+        for x, y in zip(full, part):
+            assert np.array_equal(x[:n], y), f"batch of {n} envs differs from the same envs inside a batch of 1024"
