@@ -53,7 +53,9 @@ constexpr int kWarpsPerBlock = DEX_WARPS_PER_BLOCK;
 #define DEX_K2_MINB 5
 #endif
 #ifndef DEX_K2_CTAS
-#define DEX_K2_CTAS 22   // resident single-warp CTAs of K2 per SM (register bound 65536 / (22 * 32) = 93; measured 18: 0.449, 20: 0.451, 22: 0.421, 24: 0.432 ms)
+#define DEX_K2_CTAS 19   // register bound of K2 (65536 / (19 * 32) -> 96 registers, 21 CTAs resident, 12 bytes of spills instead of 48 at 80
+                         // registers).  Re-tuned at the end of round 2, env step with 16 / 18 / 19 / 20 / 21 / 22 / 24: 3.63 / 3.59 / 3.57 / 3.59 /
+                         // 3.64 / 3.67 / 3.65 ms (round 1, older kernel: 18: 0.449, 20: 0.451, 22: 0.421, 24: 0.432 ms per launch)
 #endif
 
 static_assert(DEX_STATUS_BIT_BADQACC == DEX_STATUS_BADQACC && DEX_STATUS_BIT_CON_OVERFLOW == DEX_STATUS_CON_OVERFLOW &&
