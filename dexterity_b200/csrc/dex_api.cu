@@ -79,8 +79,11 @@ __global__ void __launch_bounds__(kTreeBlock) k_tree(DevModel<T> m, BatchState<T
 #define DEX_TREE_WARPS 1
 #endif
 constexpr int kTreeWarps = DEX_TREE_WARPS;  // K0, 8-lanes-per-env form: 4 envs per warp
+#ifndef DEX_TREE_MINB
+#define DEX_TREE_MINB 12   // register bound only (shared memory keeps 15 CTAs per SM): 109 registers, no spills; tree 0.132 -> 0.128 ms (15: 0.129, 18: 0.132, 20: 0.134)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kTreeWarps * 32) k_tree8(DevModel<T> m, BatchState<T> st) {
+__global__ void __launch_bounds__(kTreeWarps * 32, DEX_TREE_MINB) k_tree8(DevModel<T> m, BatchState<T> st) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0) { for (int k = 0; k < DEX_WORK_HDR; ++k) st.nwork[k] = 0; }
